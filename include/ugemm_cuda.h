@@ -1,0 +1,122 @@
+/* ugemm_cuda.h -- Blackwell (sm_100a) SGEMM backend for ugemm: the drop-in C ABI.
+ *
+ * This is the ONLY header a ugemm user includes to use the CUDA backend.  It sits next to the
+ * reference's sgemm_avx256.h / sgemm_sse.h / sgemm_ocl*.h / sgemm_gl*.h backends and keeps their
+ * conventions: BLAS-style 14-argument entry points returning void, caller-owned host buffers,
+ * blocking calls, process-global state bracketed by init/finish, errors reported out of band.
+ * Every symbol is plain C (extern "C", pointers and sizes only); the implementation is
+ * libugemm_cuda.so (ugemm_b200/csrc/ *.cu, hand-written sm_100a kernels, no CPU fallback).
+ *
+ * Semantics (identical to the reference, ugemm.h:305-409):
+ *   C <- alpha * op(A) * op(B) + beta * C        fp32 storage, fp32-accurate arithmetic
+ *   major  'R' row-major | 'C' column-major      trans 'N' | 'T' (lower case accepted)
+ *   row-major:  op(A)(m,k) = transA=='N' ? A[k + m*lda] : A[m + k*lda]
+ *               op(B)(k,n) = transB=='N' ? B[n + k*ldb] : B[k + n*ldb]     C(m,n) = C[n + m*ldc]
+ *   column-major is the mirror image (ugemm.h:359-409).
+ *   beta == 0   C is overwritten and never read (as sgemm_avx / sgemm_c / sgemm_sse do:
+ *               sgemm_avx256.h:324-330, gemm_cpu.h:119-124); NaN/Inf in C do not propagate.
+ *   alpha == 0 or K == 0   C <- beta*C over the M x N region in the GIVEN major (the reference's
+ *               fast paths index column-major regardless -- sgemm_avx256.h:415-430 -- a bug this
+ *               backend does not reproduce).
+ *   Elements of C outside the M x N region (ld padding) are never written.
+ *   Dimensions and leading dimensions stay `int` for drop-in compatibility; all internal
+ *   offsets are 64-bit (32768 x 32768 operands are supported).
+ */
+#ifndef UGEMM_CUDA_H
+#define UGEMM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Kernel selection for the *_dev entry point and for reports. */
+enum {
+	UGEMM_MODE_AUTO   = 0, /* rule-based: K1 iff eligible (see sgemm_cuda_k1_eligible), else K2 */
+	UGEMM_MODE_3XTF32 = 1, /* K1: 3xTF32 error-compensated tcgen05/TMEM/TMA kernel; ineligible => error */
+	UGEMM_MODE_SIMT   = 2  /* K2: register-blocked FFMA kernel, plain fp32 */
+};
+
+/* ---- lifecycle: replaces sgemm_ocl_init / sgemm_ocl_finish (sgemm_ocl2.h:158-165, :220-224) and the
+ * device setup in ocl.h:141-249 (oclSetup / oclKernel / oclKernelArgs) and gpgpu_gl4.h:142-169 (coInit).
+ * `device` = CUDA ordinal (-1: $UGEMM_CUDA_DEVICE or 0).  `arena_bytes` = initial size of the device
+ * staging arena used by the host-pointer entry points (0: grow on demand), like the single cl buffer the
+ * OpenCL backend sizes up front.  Returns 0 on success; on failure returns non-zero and sets last_error. */
+int  sgemm_cuda_init(int device, size_t arena_bytes);
+void sgemm_cuda_finish(void);
+
+/* ---- drop-in SGEMM, HOST pointers, blocking: H2D -> kernel -> D2H exactly like sgemm_ocl
+ * (sgemm_ocl2.h:166-218).  Same signature as sgemm_cpu (ugemm.h:287-301), sgemm_c (gemm_cpu.h:284-298),
+ * sgemm_avx (sgemm_avx256.h:392-405), sgemm_sse (sgemm_sse.h:365-379), i.e. usable as the `uut`
+ * function pointer of test_sgemm (check_sgemm.c:96-103).  Lazily calls sgemm_cuda_init(-1, 0). */
+void sgemm_cuda(char major, char transA, char transB, int M, int N, int K, float alpha,
+                const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc);
+/* forced-kernel variants so a harness can list both kernels as separate `uut` rows */
+void sgemm_cuda_3xtf32(char major, char transA, char transB, int M, int N, int K, float alpha,
+                       const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc);
+void sgemm_cuda_simt(char major, char transA, char transB, int M, int N, int K, float alpha,
+                     const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc);
+
+/* ---- the timed path: DEVICE pointers, asynchronous on `stream` (a cudaStream_t; NULL = the backend's
+ * own stream).  Replaces the body of sgemm_ocl after its uploads (kernel launch, sgemm_ocl2.h:201-215),
+ * including the work of the separate `transpose` kernel (sgemm_ocl2.h:95-128,180-199): transposes are
+ * folded into the operand loads.  Returns 0 on success. */
+int sgemm_cuda_dev(int mode, void *stream, char major, char transA, char transB, int M, int N, int K,
+                   float alpha, const float *dA, int lda, const float *dB, int ldb,
+                   float beta, float *dC, int ldc);
+
+/* 1 if UGEMM_MODE_AUTO would pick K1 for this problem: A, B 16-byte aligned, lda and ldb multiples
+ * of 4 (TMA global-stride rule), M,N >= 128 and K >= 32 (at least one full tile of tensor work). */
+int sgemm_cuda_k1_eligible(char major, char transA, char transB, int M, int N, int K,
+                           const float *dA, int lda, const float *dB, int ldb, const float *dC, int ldc);
+
+/* Time `iters` back-to-back launches (after `warmup` untimed ones) with CUDA events on the backend's
+ * stream.  ms_avg / ms_min may be NULL.  Returns 0 on success. */
+int sgemm_cuda_time_dev(int mode, int iters, int warmup, char major, char transA, char transB,
+                        int M, int N, int K, float alpha, const float *dA, int lda,
+                        const float *dB, int ldb, float beta, float *dC, int ldc,
+                        float *ms_avg, float *ms_min);
+
+/* ---- errors: entry points stay void like the reference's; failures are sticky and queryable
+ * (the reference only printf()s, ocl.h:92,235-239).  NULL when no error is pending. */
+const char *sgemm_cuda_last_error(void);
+void        sgemm_cuda_clear_error(void);
+
+/* ---- introspection used by the harnesses / bench */
+int                sgemm_cuda_last_kernel(void);   /* UGEMM_MODE_3XTF32 or UGEMM_MODE_SIMT of the last GEMM launch, 0 if none */
+unsigned long long sgemm_cuda_launch_count(void);  /* number of GEMM/fill/scale kernels launched by this library so far */
+int  ugemm_cuda_device_info(int *sm_count, int *sm_clock_khz, size_t *hbm_bytes, char *name, int name_len);
+/* Tunables of K1 (0/negative = keep).  kc_blocks: number of 32-wide k-blocks accumulated inside TMEM
+ * before the partial sums are promoted to fp32 registers with round-to-nearest adds;
+ * split: 0 = truncation split, raw tile is the "big" operand; 1 = round-to-nearest split, big rewritten.
+ * cta_group: 1 or 2 CTAs per MMA. */
+void sgemm_cuda_set_k1_tuning(int kc_blocks, int split, int cta_group);
+
+/* ---- memory helpers (replace oclKernelArgs/oclWrite/oclRead buffer plumbing, ocl.h:227-293) */
+void *ugemm_cuda_malloc(size_t bytes);            /* device memory */
+void  ugemm_cuda_free(void *dptr);
+void *ugemm_cuda_malloc_host(size_t bytes);       /* pinned host memory (fast H2D/D2H for sgemm_cuda) */
+void  ugemm_cuda_free_host(void *hptr);
+int   ugemm_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes);
+int   ugemm_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int   ugemm_cuda_sync(void);
+
+/* ---- counter-based uniform stream, identical on host and device (so a 32768^2 operand can be generated
+ * on the GPU and any sampled row regenerated on the host for verification):
+ *   x[i] = fmaf(hi-lo, (splitmix64(seed*0x9E3779B97F4A7C15 + i) >> 40) * 2^-24, lo)
+ * Plays the role of random_matrix (check_sgemm.c:47-54) with an explicit seed. */
+void ugemm_fill_uniform_host(float *x, size_t n, uint64_t seed, float lo, float hi);
+int  ugemm_fill_uniform_dev(float *dx, size_t n, uint64_t seed, float lo, float hi, void *stream);
+
+/* ---- hardware probe used by tests/DESIGN.md: runs one 128 x 16 x (8*ksteps) TF32 tcgen05 product
+ * chain on raw fp32 bit patterns and returns the 128x16 fp32 accumulator, so the rounding behaviour of
+ * the tensor core (operand truncation, accumulator rounding) can be pinned.  A: 128 x 8*ksteps row-major,
+ * B: 16 x 8*ksteps row-major (K-major both), D: 128 x 16.  Host pointers.  Returns 0 on success. */
+int ugemm_cuda_probe_tf32(const float *A, const float *B, float *D, int ksteps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGEMM_CUDA_H */

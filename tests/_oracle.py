@@ -1,0 +1,118 @@
+"""ctypes loaders for the CHECKER libraries (oracle/liboracle.so, oracle/_ref/libugemm_ref.so).
+
+Test infrastructure only: nothing under ugemm_b200/ imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libugemm_ref.so")
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_SIG14 = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_float,
+          _f32p, C.c_int, _f32p, C.c_int, C.c_float, _f32p, C.c_int]
+
+
+def build_oracle(force=False):
+    """Compile oracle/liboracle.so (and oracle/_ref when /root/reference exists)."""
+    if force or not os.path.exists(ORACLE_SO):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.exists(os.environ.get("UGEMM_REF", "/root/reference") + "/ugemm.h") and (force or not os.path.exists(REF_SO)):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        build_oracle()
+        lib = C.CDLL(ORACLE_SO)
+        lib.oracle_sgemm_naive.argtypes = _SIG14
+        lib.oracle_sgemm_naive.restype = None
+        lib.oracle_sgemm_banded.argtypes = [C.c_int] + _SIG14
+        lib.oracle_sgemm_banded.restype = None
+        lib.oracle_relerr.argtypes = [C.c_char, C.c_int, C.c_int, _f32p, _f32p, C.c_int]
+        lib.oracle_relerr.restype = C.c_double
+        lib.oracle_cmp_results.argtypes = [C.c_int, C.c_int, _f32p, _f32p, C.c_int,
+                                           np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")]
+        lib.oracle_cmp_results.restype = C.c_int
+        lib.oracle_fill_uniform.argtypes = [_f32p, C.c_size_t, C.c_uint64, C.c_float, C.c_float]
+        lib.oracle_fill_uniform.restype = None
+        lib.oracle_max_threads.restype = C.c_int
+        _oracle = lib
+    return _oracle
+
+
+def ref():
+    """The UNMODIFIED reference compiled into oracle/_ref (None if it was never built)."""
+    global _ref
+    if _ref is None:
+        build_oracle()
+        if not os.path.exists(REF_SO):
+            return None
+        lib = C.CDLL(REF_SO)
+        for name in ("ref_sgemm_cpu", "ref_sgemm_c", "ref_sgemm_avx", "ref_sgemm_sse"):
+            getattr(lib, name).argtypes = _SIG14
+            getattr(lib, name).restype = None
+        lib.ref_sgemm_avx_mt.argtypes = [C.c_int] + _SIG14
+        lib.ref_sgemm_avx_mt.restype = None
+        lib.ref_max_threads.restype = C.c_int
+        _ref = lib
+    return _ref
+
+
+def b(ch):
+    return ch.encode() if isinstance(ch, str) else ch
+
+
+def fill_uniform(n, seed, lo=0.0, hi=1.0):
+    x = np.empty(int(n), dtype=np.float32)
+    oracle().oracle_fill_uniform(x, x.size, seed, lo, hi)
+    return x
+
+
+def stored_shapes(major, ta, tb, M, N, K):
+    """(rows, cols) of A, B, C as stored, i.e. (count of ld-strided lines, line length)."""
+    if major == "R":
+        a = (M, K) if ta == "N" else (K, M)
+        bb = (K, N) if tb == "N" else (N, K)
+        c = (M, N)
+    else:
+        a = (K, M) if ta == "N" else (M, K)
+        bb = (N, K) if tb == "N" else (K, N)
+        c = (N, M)
+    return a, bb, c
+
+
+def make_problem(major, ta, tb, M, N, K, pad=(0, 0, 0), seed=1, lo=0.0, hi=1.0, sentinel=None):
+    """Seeded A, B, C buffers (1-D float32, ld-strided) + their leading dimensions."""
+    (ar, ac), (br, bc), (cr, cc) = stored_shapes(major, ta, tb, M, N, K)
+    lda, ldb, ldc = ac + pad[0], bc + pad[1], cc + pad[2]
+    A = fill_uniform(max(ar * lda, 1), seed * 3 + 0, lo, hi)
+    B = fill_uniform(max(br * ldb, 1), seed * 3 + 1, lo, hi)
+    Cm = fill_uniform(max(cr * ldc, 1), seed * 3 + 2, lo, hi)
+    if sentinel is not None and pad[2]:
+        Cm.reshape(cr, ldc)[:, cc:] = sentinel
+    return A, lda, B, ldb, Cm, ldc
+
+
+def relerr(major, M, N, ref_c, res_c, ld):
+    return float(oracle().oracle_relerr(b(major), M, N, ref_c, res_c, ld))
+
+
+def run14(fn, major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc, threads=None):
+    out = Cm.copy()
+    args = (b(major), b(ta), b(tb), M, N, K, alpha, A, lda, B, ldb, beta, out, ldc)
+    if threads is None:
+        fn(*args)
+    else:
+        fn(threads, *args)
+    return out

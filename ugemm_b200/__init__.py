@@ -1,0 +1,12 @@
+"""ugemm_b200 -- Blackwell (sm_100a) SGEMM backend for ugemm: Python host mirror of the C ABI.
+
+Only what the hot path needs: `csrc/` (hand-written CUDA kernels + the extern "C" boundary declared in
+include/ugemm_cuda.h), `build.py` (nvcc recipe) and `backend.py` (ctypes binding that mirrors the
+reference's `sgemm_*` entry points), plus `dist.py` (2-D C-tile sharding across GPUs).
+"""
+from .backend import (  # noqa: F401
+    MODE_3XTF32, MODE_AUTO, MODE_SIMT, DeviceBuffer, UgemmCudaError, check, device_info, fill_uniform_host,
+    k1_eligible, last_error, last_kernel, launch_count, lib, probe_tf32, set_k1_tuning, sgemm_cuda,
+    sgemm_cuda_3xtf32, sgemm_cuda_dev, sgemm_cuda_finish, sgemm_cuda_init, sgemm_cuda_simt, sgemm_cuda_time_dev,
+    sgemm_finish, sgemm_init, sgemm_rnn, sgemm_rnt, sgemm_rtn, sync,
+)

@@ -1,0 +1,281 @@
+"""Host-side mirror of the reference's SGEMM backend interface, bound to libugemm_cuda.so via ctypes.
+
+Names, argument order and error behaviour follow the reference (`uut(major, transA, transB, M, N, K, alpha,
+A, lda, B, ldb, beta, C, ldc)`, check_sgemm.c:96-103; `sgemm_init / sgemm_finish / sgemm_rnn / sgemm_rnt /
+sgemm_rtn`, sgemm_test.c:19-33).  This module contains NO arithmetic: every call goes through the C ABI of
+include/ugemm_cuda.h into the hand-written sm_100a kernels.  If the shared library is missing it is built
+with nvcc; if that is impossible the import fails loudly -- there is no CPU or PyTorch fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MODE_AUTO, MODE_3XTF32, MODE_SIMT = 0, 1, 2
+_MODES = {"auto": MODE_AUTO, "3xtf32": MODE_3XTF32, "simt": MODE_SIMT, 0: 0, 1: 1, 2: 2}
+
+_lib = None
+
+
+class UgemmCudaError(RuntimeError):
+    pass
+
+
+def _ptr(x):
+    """Host numpy array / device pointer int / object with data_ptr() -> c_void_p."""
+    if x is None:
+        return C.c_void_p(0)
+    if isinstance(x, np.ndarray):
+        if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+            raise TypeError("host buffers must be C-contiguous float32 numpy arrays")
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(int(x))
+
+
+def lib():
+    """Load (building first if needed) libugemm_cuda.so.  Raises if the CUDA extension is unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # stale-but-present library is still usable on a box without nvcc
+            if not os.path.exists(path):
+                raise UgemmCudaError(f"libugemm_cuda.so is missing and could not be built: {e}") from e
+    L = C.CDLL(path)
+    sig14 = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_float,
+             C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int]
+    L.sgemm_cuda_init.argtypes = [C.c_int, C.c_size_t]
+    L.sgemm_cuda_init.restype = C.c_int
+    L.sgemm_cuda_finish.restype = None
+    for n in ("sgemm_cuda", "sgemm_cuda_3xtf32", "sgemm_cuda_simt"):
+        getattr(L, n).argtypes = sig14
+        getattr(L, n).restype = None
+    L.sgemm_cuda_dev.argtypes = [C.c_int, C.c_void_p] + sig14
+    L.sgemm_cuda_dev.restype = C.c_int
+    L.sgemm_cuda_k1_eligible.argtypes = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.sgemm_cuda_k1_eligible.restype = C.c_int
+    L.sgemm_cuda_time_dev.argtypes = [C.c_int, C.c_int, C.c_int] + sig14 + [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.sgemm_cuda_time_dev.restype = C.c_int
+    L.sgemm_cuda_last_error.restype = C.c_char_p
+    L.sgemm_cuda_clear_error.restype = None
+    L.sgemm_cuda_last_kernel.restype = C.c_int
+    L.sgemm_cuda_launch_count.restype = C.c_ulonglong
+    L.ugemm_cuda_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.c_char_p, C.c_int]
+    L.ugemm_cuda_device_info.restype = C.c_int
+    L.sgemm_cuda_set_k1_tuning.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.sgemm_cuda_set_k1_tuning.restype = None
+    L.ugemm_cuda_malloc.argtypes = [C.c_size_t]
+    L.ugemm_cuda_malloc.restype = C.c_void_p
+    L.ugemm_cuda_free.argtypes = [C.c_void_p]
+    L.ugemm_cuda_malloc_host.argtypes = [C.c_size_t]
+    L.ugemm_cuda_malloc_host.restype = C.c_void_p
+    L.ugemm_cuda_free_host.argtypes = [C.c_void_p]
+    L.ugemm_cuda_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.ugemm_cuda_memcpy_h2d.restype = C.c_int
+    L.ugemm_cuda_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.ugemm_cuda_memcpy_d2h.restype = C.c_int
+    L.ugemm_cuda_sync.restype = C.c_int
+    L.ugemm_fill_uniform_host.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_float, C.c_float]
+    L.ugemm_fill_uniform_host.restype = None
+    L.ugemm_fill_uniform_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_float, C.c_float, C.c_void_p]
+    L.ugemm_fill_uniform_dev.restype = C.c_int
+    L.ugemm_cuda_probe_tf32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.ugemm_cuda_probe_tf32.restype = C.c_int
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "sgemm_cuda_init", "sgemm_cuda_finish", "sgemm_cuda", "sgemm_cuda_3xtf32", "sgemm_cuda_simt",
+    "sgemm_cuda_dev", "sgemm_cuda_k1_eligible", "sgemm_cuda_time_dev", "sgemm_cuda_last_error",
+    "sgemm_cuda_clear_error", "sgemm_cuda_last_kernel", "sgemm_cuda_launch_count", "ugemm_cuda_device_info",
+    "sgemm_cuda_set_k1_tuning", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
+    "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
+    "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_cuda_probe_tf32",
+]
+
+
+def _b(ch):
+    return ch.encode() if isinstance(ch, str) else ch
+
+
+def last_error():
+    e = lib().sgemm_cuda_last_error()
+    return e.decode() if e else None
+
+
+def check():
+    """Raise (and clear) the sticky error of the void entry points, if any."""
+    e = last_error()
+    if e:
+        lib().sgemm_cuda_clear_error()
+        raise UgemmCudaError(e)
+
+
+def sgemm_cuda_init(device=-1, arena_bytes=0):
+    if lib().sgemm_cuda_init(device, arena_bytes):
+        check()
+
+
+def sgemm_cuda_finish():
+    lib().sgemm_cuda_finish()
+
+
+def _host14(fn, major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    fn(_b(major), _b(ta), _b(tb), M, N, K, alpha, _ptr(A), lda, _ptr(B), ldb, beta, _ptr(Cm), ldc)
+    check()
+
+
+def sgemm_cuda(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    """Drop-in `uut`: host buffers, blocking, C updated in place (rule-based K1/K2 choice)."""
+    _host14(lib().sgemm_cuda, major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc)
+
+
+def sgemm_cuda_3xtf32(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    _host14(lib().sgemm_cuda_3xtf32, major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc)
+
+
+def sgemm_cuda_simt(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    _host14(lib().sgemm_cuda_simt, major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc)
+
+
+def sgemm_cuda_dev(mode, stream, major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc):
+    """Device pointers (ints, or anything with .data_ptr()); asynchronous on `stream` (int handle or None)."""
+    rc = lib().sgemm_cuda_dev(_MODES[mode], C.c_void_p(stream or 0), _b(major), _b(ta), _b(tb), M, N, K, alpha,
+                              _ptr(dA), lda, _ptr(dB), ldb, beta, _ptr(dC), ldc)
+    if rc:
+        check()
+        raise UgemmCudaError("sgemm_cuda_dev failed")
+
+
+def sgemm_cuda_time_dev(mode, iters, warmup, major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc):
+    """(avg_ms, min_ms) of `iters` launches timed with CUDA events on the backend stream."""
+    avg, best = C.c_float(0), C.c_float(0)
+    rc = lib().sgemm_cuda_time_dev(_MODES[mode], iters, warmup, _b(major), _b(ta), _b(tb), M, N, K, alpha,
+                                   _ptr(dA), lda, _ptr(dB), ldb, beta, _ptr(dC), ldc, C.byref(avg), C.byref(best))
+    if rc:
+        check()
+        raise UgemmCudaError("sgemm_cuda_time_dev failed")
+    return avg.value, best.value
+
+
+def k1_eligible(major, ta, tb, M, N, K, dA, lda, dB, ldb, dC, ldc):
+    return bool(lib().sgemm_cuda_k1_eligible(_b(major), _b(ta), _b(tb), M, N, K, _ptr(dA), lda, _ptr(dB), ldb, _ptr(dC), ldc))
+
+
+def set_k1_tuning(kc_blocks=-1, split=-1, cta_group=-1):
+    lib().sgemm_cuda_set_k1_tuning(kc_blocks, split, cta_group)
+
+
+def last_kernel():
+    return {0: None, 1: "3xtf32", 2: "simt"}[lib().sgemm_cuda_last_kernel()]
+
+
+def launch_count():
+    return int(lib().sgemm_cuda_launch_count())
+
+
+def device_info():
+    sm, khz, mem = C.c_int(0), C.c_int(0), C.c_size_t(0)
+    name = C.create_string_buffer(128)
+    if lib().ugemm_cuda_device_info(C.byref(sm), C.byref(khz), C.byref(mem), name, 128):
+        check()
+    return {"sm_count": sm.value, "sm_clock_khz": khz.value, "hbm_bytes": mem.value, "name": name.value.decode()}
+
+
+class DeviceBuffer:
+    """A float32 device allocation owned through the C ABI (ugemm_cuda_malloc / ugemm_cuda_free)."""
+
+    def __init__(self, n_floats):
+        self.n = int(n_floats)
+        self.ptr = lib().ugemm_cuda_malloc(max(self.n, 1) * 4)
+        if not self.ptr:
+            check()
+            raise UgemmCudaError("ugemm_cuda_malloc failed")
+
+    def data_ptr(self):
+        return self.ptr
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=np.float32)
+        assert host.size <= self.n
+        if lib().ugemm_cuda_memcpy_h2d(C.c_void_p(self.ptr), _ptr(host), host.size * 4):
+            check()
+        return self
+
+    def download(self, n=None, offset=0):
+        n = self.n - offset if n is None else n
+        out = np.empty(n, dtype=np.float32)
+        if lib().ugemm_cuda_memcpy_d2h(_ptr(out), C.c_void_p(self.ptr + offset * 4), n * 4):
+            check()
+        return out
+
+    def fill_uniform(self, seed, lo=0.0, hi=1.0, n=None, offset=0):
+        n = self.n - offset if n is None else n
+        if lib().ugemm_fill_uniform_dev(C.c_void_p(self.ptr + offset * 4), n, seed, lo, hi, None):
+            check()
+        return self
+
+    def free(self):
+        if self.ptr:
+            lib().ugemm_cuda_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def fill_uniform_host(n, seed, lo=0.0, hi=1.0):
+    x = np.empty(int(n), dtype=np.float32)
+    lib().ugemm_fill_uniform_host(_ptr(x), x.size, seed, lo, hi)
+    return x
+
+
+def sync():
+    if lib().ugemm_cuda_sync():
+        check()
+
+
+def probe_tf32(A, B, ksteps):
+    """A: (128, 8*ksteps), B: (16, 8*ksteps) float32 -> D (128, 16): chained TF32 tcgen05 MMAs."""
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    assert A.shape == (128, 8 * ksteps) and B.shape == (16, 8 * ksteps)
+    D = np.empty((128, 16), dtype=np.float32)
+    if lib().ugemm_cuda_probe_tf32(_ptr(A), _ptr(B), _ptr(D), ksteps):
+        check()
+        raise UgemmCudaError("probe failed")
+    return D
+
+
+# ---- the macro API of the reference's GPU harness (sgemm_test.c:19-33): tight row-major, no ld ----------
+def sgemm_init(s1=0, s2=0, s3=0):
+    """sgemm_init(M*K, K*N, M*N) -> sgemm_ocl_init(0, 0, (s1+s2+s3)*10*sizeof(float)) in the reference."""
+    sgemm_cuda_init(-1, (s1 + s2 + s3) * 4)
+
+
+def sgemm_finish():
+    sgemm_cuda_finish()
+
+
+def sgemm_rnn(M, N, K, alpha, a, b, beta, c):
+    sgemm_cuda("R", "N", "N", M, N, K, alpha, a, K, b, N, beta, c, N)
+
+
+def sgemm_rnt(M, N, K, alpha, a, b, beta, c):
+    sgemm_cuda("R", "N", "T", M, N, K, alpha, a, K, b, K, beta, c, N)
+
+
+def sgemm_rtn(M, N, K, alpha, a, b, beta, c):
+    sgemm_cuda("R", "T", "N", M, N, K, alpha, a, M, b, N, beta, c, N)

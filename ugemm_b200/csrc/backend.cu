@@ -1,0 +1,431 @@
+// backend.cu -- the extern "C" boundary of the CUDA backend (include/ugemm_cuda.h).
+//
+// Replaces the reference's device-setup layers (ocl.h:141-360 oclSetup/oclKernel/oclKernelArgs/oclWrite/
+// oclRead/oclRun/oclFinish; gpgpu_gl4.h:42-174 coInit/coCreateBuffer/coRun/coRead/coWrite/coTerm) with a thin
+// CUDA runtime layer, and the per-call body of sgemm_ocl (sgemm_ocl2.h:166-218) with: validate -> normalise
+// to row-major -> rule-based kernel choice (K1 3xTF32 tcgen05 | K2 SIMT FFMA) -> launch.  There is no CPU
+// fallback anywhere in this file: if the device, the driver entry point or a launch fails, the error is
+// recorded (sgemm_cuda_last_error) and the call returns without touching C.
+#include "../../include/ugemm_cuda.h"
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+using namespace ugemm;
+
+namespace {
+
+struct State {
+	bool ready = false;
+	int device = 0;
+	int sm_count = 0;
+	int clock_khz = 0;
+	size_t hbm_bytes = 0;
+	char name[128] = {0};
+	cudaStream_t stream = nullptr;   // compute + H2D
+	cudaStream_t stream_d2h = nullptr;
+	// staging arena of the host-pointer entry points (one buffer like the OpenCL backend's `gm`)
+	char *arena = nullptr;
+	size_t arena_bytes = 0;
+	K1Tuning tuning = {0, 0, 2};
+	int last_kernel = 0;
+	unsigned long long launches = 0;
+} g;
+
+std::mutex g_mu;
+char g_err[512];
+bool g_has_err = false;
+
+void set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+	g_has_err = true;
+	if (getenv("UGEMM_CUDA_VERBOSE")) fprintf(stderr, "ugemm_cuda: %s\n", g_err);
+}
+
+#define CU_TRY(expr, what)                                                                   \
+	do {                                                                                     \
+		cudaError_t e__ = (expr);                                                            \
+		if (e__ != cudaSuccess) {                                                            \
+			set_error("%s failed: %s", what, cudaGetErrorString(e__));                       \
+			return 1;                                                                        \
+		}                                                                                    \
+	} while (0)
+
+int ensure_init()
+{
+	if (g.ready) return 0;
+	return sgemm_cuda_init(-1, 0);
+}
+
+int upper(char c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
+
+// Validate BLAS arguments and map to the row-major Problem.  Column-major C = op(A) op(B) is the row-major
+// product C^T = op(B)^T op(A)^T over the same buffers: swap (A,transA,M,lda) <-> (B,transB,N,ldb).
+int normalise(char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda,
+              const float *B, int ldb, float beta, float *C, int ldc, Problem *p)
+{
+	major = (char)upper(major); ta = (char)upper(ta); tb = (char)upper(tb);
+	if (major != 'R' && major != 'C') { set_error("major must be 'R' or 'C' (got 0x%02x)", major); return 1; }
+	if ((ta != 'N' && ta != 'T') || (tb != 'N' && tb != 'T')) { set_error("transA/transB must be 'N' or 'T'"); return 1; }
+	if (M < 0 || N < 0 || K < 0) { set_error("negative dimension M=%d N=%d K=%d", M, N, K); return 1; }
+	if (major == 'C') {
+		const float *tp = A; A = B; B = tp;
+		int ti = lda; lda = ldb; ldb = ti;
+		ti = M; M = N; N = ti;
+		char tc = ta; ta = tb; tb = tc;
+	}
+	const int a_cols = ta == 'N' ? K : M, b_cols = tb == 'N' ? N : K;
+	if (lda < (a_cols > 1 ? a_cols : 1) || ldb < (b_cols > 1 ? b_cols : 1) || ldc < (N > 1 ? N : 1)) {
+		set_error("leading dimension too small (lda=%d ldb=%d ldc=%d for stored widths %d %d %d)", lda, ldb, ldc, a_cols, b_cols, N);
+		return 1;
+	}
+	p->M = M; p->N = N; p->K = K; p->alpha = alpha; p->beta = beta;
+	p->A = A; p->lda = lda; p->a_kmajor = (ta == 'N');
+	p->B = B; p->ldb = ldb; p->b_kmajor = (tb == 'T');
+	p->C = C; p->ldc = ldc;
+	return 0;
+}
+
+bool auto_prefers_k1(const Problem &p)
+{
+	return k1_eligible(p, nullptr) && p.M >= 128 && p.N >= 128 && p.K >= 32;
+}
+
+// device-pointer GEMM on `stream`
+int run_dev(int mode, cudaStream_t stream, const Problem &p)
+{
+	// quick returns of the reference (sgemm_avx256.h:410)
+	if (p.M == 0 || p.N == 0) return 0;
+	if ((p.alpha == 0.f || p.K == 0) && p.beta == 1.f) return 0;
+	if (p.alpha == 0.f || p.K == 0) {
+		CU_TRY(launch_scale_c(p, stream), "scale_c launch");
+		g.launches++;
+		return 0;
+	}
+	int use = mode;
+	if (mode == UGEMM_MODE_AUTO) use = auto_prefers_k1(p) ? UGEMM_MODE_3XTF32 : UGEMM_MODE_SIMT;
+	if (use == UGEMM_MODE_3XTF32) {
+		const char *why = nullptr;
+		if (!k1_eligible(p, &why)) { set_error("3xTF32 kernel not applicable: %s", why); return 1; }
+		CU_TRY(launch_k1_3xtf32(p, g.tuning, stream, g.sm_count), "K1 (3xTF32 tcgen05) launch");
+	} else if (use == UGEMM_MODE_SIMT) {
+		CU_TRY(launch_k2_simt(p, stream, g.sm_count), "K2 (SIMT FFMA) launch");
+	} else {
+		set_error("unknown mode %d", mode);
+		return 1;
+	}
+	g.last_kernel = use;
+	g.launches++;
+	return 0;
+}
+
+int ensure_arena(size_t bytes)
+{
+	if (bytes <= g.arena_bytes) return 0;
+	if (g.arena) cudaFree(g.arena);
+	g.arena = nullptr; g.arena_bytes = 0;
+	size_t want = bytes + (bytes >> 3) + (1u << 20);
+	CU_TRY(cudaMalloc(&g.arena, want), "arena cudaMalloc");
+	g.arena_bytes = want;
+	return 0;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Host-pointer GEMM: stage operands into the arena, run, copy C back.  Blocking, like sgemm_ocl.
+void run_host(int mode, char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda,
+              const float *B, int ldb, float beta, float *C, int ldc)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (ensure_init()) return;
+	Problem p;
+	if (normalise(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, &p)) return;
+	if (p.M == 0 || p.N == 0) return;
+	if ((p.alpha == 0.f || p.K == 0) && p.beta == 1.f) return;
+
+	const bool need_ab = !(p.alpha == 0.f || p.K == 0);
+	const long long a_lines = p.a_kmajor ? p.M : p.K, a_cols = p.a_kmajor ? p.K : p.M;
+	const long long b_lines = p.b_kmajor ? p.N : p.K, b_cols = p.b_kmajor ? p.K : p.N;
+	// device copies keep the caller's leading dimensions (so eligibility and alignment are the caller's)
+	const size_t a_bytes = need_ab ? (size_t)((a_lines - 1) * p.lda + a_cols) * 4 : 0;
+	const size_t b_bytes = need_ab ? (size_t)((b_lines - 1) * p.ldb + b_cols) * 4 : 0;
+	const size_t c_bytes = (size_t)((long long)(p.M - 1) * p.ldc + p.N) * 4;
+	const size_t offA = 0, offB = align_up(offA + a_bytes, 256), offC = align_up(offB + b_bytes, 256);
+	if (ensure_arena(offC + c_bytes)) return;
+	float *dA = reinterpret_cast<float *>(g.arena + offA), *dB = reinterpret_cast<float *>(g.arena + offB);
+	float *dC = reinterpret_cast<float *>(g.arena + offC);
+
+	cudaError_t e = cudaSuccess;
+	auto up2d = [&](float *d, const float *h, long long ld, long long lines, long long cols) {
+		if (e != cudaSuccess || lines <= 0 || cols <= 0) return;
+		if (ld == cols) e = cudaMemcpyAsync(d, h, (size_t)lines * cols * 4, cudaMemcpyHostToDevice, g.stream);
+		else e = cudaMemcpy2DAsync(d, (size_t)ld * 4, h, (size_t)ld * 4, (size_t)cols * 4, (size_t)lines, cudaMemcpyHostToDevice, g.stream);
+	};
+	if (need_ab) {
+		up2d(dA, p.A, p.lda, a_lines, a_cols);
+		up2d(dB, p.B, p.ldb, b_lines, b_cols);
+	}
+	if (p.beta != 0.f) up2d(dC, p.C, p.ldc, p.M, p.N);   // C is uploaded only when it is read (sgemm_ocl2.h:177)
+	if (e != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(e)); return; }
+
+	Problem d = p;
+	d.A = dA; d.B = dB; d.C = dC;
+	if (mode == UGEMM_MODE_3XTF32) {
+		// eligibility is judged on the caller's layout; the arena copy preserves ld and 256-B alignment
+		const char *why = nullptr;
+		if (!k1_eligible(d, &why)) { set_error("3xTF32 kernel not applicable: %s", why); return; }
+	}
+	if (run_dev(mode, g.stream, d)) return;
+	// only the M x N region comes back: ld padding on the host is never written
+	if (p.ldc == p.N) e = cudaMemcpyAsync(p.C, dC, (size_t)p.M * p.N * 4, cudaMemcpyDeviceToHost, g.stream);
+	else e = cudaMemcpy2DAsync(p.C, (size_t)p.ldc * 4, dC, (size_t)p.ldc * 4, (size_t)p.N * 4, (size_t)p.M, cudaMemcpyDeviceToHost, g.stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+	if (e != cudaSuccess) {
+		const unsigned *dg = k1_diag_host();
+		if (dg && dg[0]) set_error("GEMM failed: %s (K1 watchdog code %u, block %u, thread %u)", cudaGetErrorString(e), dg[0], dg[1], dg[2]);
+		else set_error("GEMM failed: %s", cudaGetErrorString(e));
+	}
+}
+
+__global__ void fill_uniform_kernel(float *x, size_t n, unsigned long long base, float lo, float span)
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (; i < n; i += stride) x[i] = uniform_at(base, i, lo, span);
+}
+
+} // namespace
+
+extern "C" {
+
+int sgemm_cuda_init(int device, size_t arena_bytes)
+{
+	if (g.ready) return 0;
+	if (device < 0) {
+		const char *env = getenv("UGEMM_CUDA_DEVICE");
+		device = env ? atoi(env) : 0;
+	}
+	int count = 0;
+	CU_TRY(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
+	if (device >= count) { set_error("device %d requested but only %d visible", device, count); return 1; }
+	CU_TRY(cudaSetDevice(device), "cudaSetDevice");
+	cudaDeviceProp prop;
+	CU_TRY(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+	if (prop.major != 10) {
+		set_error("device %d (%s) is sm_%d%d; this backend is built for sm_100a only", device, prop.name, prop.major, prop.minor);
+		return 1;
+	}
+	g.device = device;
+	g.sm_count = prop.multiProcessorCount;
+	g.hbm_bytes = prop.totalGlobalMem;
+	int khz = 0;
+	cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+	g.clock_khz = khz;
+	strncpy(g.name, prop.name, sizeof g.name - 1);
+	CU_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	CU_TRY(cudaStreamCreateWithFlags(&g.stream_d2h, cudaStreamNonBlocking), "cudaStreamCreate");
+	g.ready = true;
+	if (arena_bytes && ensure_arena(arena_bytes)) { g.ready = false; return 1; }
+	return 0;
+}
+
+void sgemm_cuda_finish(void)
+{
+	if (!g.ready) return;
+	cudaStreamSynchronize(g.stream);
+	if (g.arena) cudaFree(g.arena);
+	g.arena = nullptr; g.arena_bytes = 0;
+	cudaStreamDestroy(g.stream);
+	cudaStreamDestroy(g.stream_d2h);
+	g.stream = g.stream_d2h = nullptr;
+	g.ready = false;
+}
+
+void sgemm_cuda(char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda,
+                const float *B, int ldb, float beta, float *C, int ldc)
+{ run_host(UGEMM_MODE_AUTO, major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc); }
+
+void sgemm_cuda_3xtf32(char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda,
+                       const float *B, int ldb, float beta, float *C, int ldc)
+{ run_host(UGEMM_MODE_3XTF32, major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc); }
+
+void sgemm_cuda_simt(char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda,
+                     const float *B, int ldb, float beta, float *C, int ldc)
+{ run_host(UGEMM_MODE_SIMT, major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc); }
+
+int sgemm_cuda_dev(int mode, void *stream, char major, char ta, char tb, int M, int N, int K, float alpha,
+                   const float *dA, int lda, const float *dB, int ldb, float beta, float *dC, int ldc)
+{
+	if (ensure_init()) return 1;
+	Problem p;
+	if (normalise(major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, &p)) return 1;
+	return run_dev(mode, stream ? static_cast<cudaStream_t>(stream) : g.stream, p);
+}
+
+int sgemm_cuda_k1_eligible(char major, char ta, char tb, int M, int N, int K, const float *dA, int lda,
+                           const float *dB, int ldb, const float *dC, int ldc)
+{
+	if (ensure_init()) return 0;
+	Problem p;
+	if (normalise(major, ta, tb, M, N, K, 1.f, dA, lda, dB, ldb, 0.f, const_cast<float *>(dC), ldc, &p)) {
+		sgemm_cuda_clear_error();
+		return 0;
+	}
+	return auto_prefers_k1(p) ? 1 : 0;
+}
+
+int sgemm_cuda_time_dev(int mode, int iters, int warmup, char major, char ta, char tb, int M, int N, int K,
+                        float alpha, const float *dA, int lda, const float *dB, int ldb, float beta, float *dC,
+                        int ldc, float *ms_avg, float *ms_min)
+{
+	if (ensure_init()) return 1;
+	if (iters < 1) iters = 1;
+	Problem p;
+	if (normalise(major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, &p)) return 1;
+	for (int i = 0; i < warmup; i++)
+		if (run_dev(mode, g.stream, p)) return 1;
+	cudaEvent_t e0, e1;
+	CU_TRY(cudaEventCreate(&e0), "cudaEventCreate");
+	CU_TRY(cudaEventCreate(&e1), "cudaEventCreate");
+	float total = 0.f, best = 1e30f;
+	int rc = 0;
+	for (int i = 0; i < iters && !rc; i++) {
+		cudaEventRecord(e0, g.stream);
+		rc = run_dev(mode, g.stream, p);
+		cudaEventRecord(e1, g.stream);
+		cudaError_t e = cudaEventSynchronize(e1);
+		if (e != cudaSuccess) { set_error("timed launch failed: %s", cudaGetErrorString(e)); rc = 1; break; }
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		total += ms;
+		if (ms < best) best = ms;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if (ms_avg) *ms_avg = total / iters;
+	if (ms_min) *ms_min = best;
+	return rc;
+}
+
+const char *sgemm_cuda_last_error(void) { return g_has_err ? g_err : nullptr; }
+void sgemm_cuda_clear_error(void) { g_has_err = false; g_err[0] = 0; }
+int sgemm_cuda_last_kernel(void) { return g.last_kernel; }
+unsigned long long sgemm_cuda_launch_count(void) { return g.launches; }
+
+int ugemm_cuda_device_info(int *sm_count, int *sm_clock_khz, size_t *hbm_bytes, char *name, int name_len)
+{
+	if (ensure_init()) return 1;
+	if (sm_count) *sm_count = g.sm_count;
+	if (sm_clock_khz) *sm_clock_khz = g.clock_khz;
+	if (hbm_bytes) *hbm_bytes = g.hbm_bytes;
+	if (name && name_len > 0) { strncpy(name, g.name, (size_t)name_len - 1); name[name_len - 1] = 0; }
+	return 0;
+}
+
+void sgemm_cuda_set_k1_tuning(int kc_blocks, int split, int cta_group)
+{
+	if (kc_blocks >= 0) g.tuning.kc_blocks = kc_blocks;
+	if (split >= 0) g.tuning.split = split ? 1 : 0;
+	if (cta_group == 1 || cta_group == 2) g.tuning.cta_group = cta_group;
+}
+
+void *ugemm_cuda_malloc(size_t bytes)
+{
+	if (ensure_init()) return nullptr;
+	void *p = nullptr;
+	cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+	if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
+	return p;
+}
+void ugemm_cuda_free(void *d) { if (d) cudaFree(d); }
+void *ugemm_cuda_malloc_host(size_t bytes)
+{
+	if (ensure_init()) return nullptr;
+	void *p = nullptr;
+	cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+	if (e != cudaSuccess) { set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
+	return p;
+}
+void ugemm_cuda_free_host(void *h) { if (h) cudaFreeHost(h); }
+int ugemm_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes)
+{
+	if (ensure_init()) return 1;
+	CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g.stream), "H2D copy");
+	CU_TRY(cudaStreamSynchronize(g.stream), "H2D sync");
+	return 0;
+}
+int ugemm_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes)
+{
+	if (ensure_init()) return 1;
+	CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g.stream), "D2H copy");
+	CU_TRY(cudaStreamSynchronize(g.stream), "D2H sync");
+	return 0;
+}
+int ugemm_cuda_sync(void)
+{
+	if (ensure_init()) return 1;
+	cudaError_t e = cudaStreamSynchronize(g.stream);
+	if (e == cudaSuccess) e = cudaDeviceSynchronize();
+	if (e != cudaSuccess) {
+		const unsigned *dg = k1_diag_host();
+		if (dg && dg[0]) set_error("sync failed: %s (K1 watchdog code %u, block %u, thread %u)", cudaGetErrorString(e), dg[0], dg[1], dg[2]);
+		else set_error("sync failed: %s", cudaGetErrorString(e));
+		return 1;
+	}
+	return 0;
+}
+
+void ugemm_fill_uniform_host(float *x, size_t n, uint64_t seed, float lo, float hi)
+{
+	const unsigned long long base = seed * 0x9E3779B97F4A7C15ull;
+	const float span = hi - lo;
+	for (size_t i = 0; i < n; i++) x[i] = uniform_at(base, i, lo, span);
+}
+
+int ugemm_fill_uniform_dev(float *dx, size_t n, uint64_t seed, float lo, float hi, void *stream)
+{
+	if (ensure_init()) return 1;
+	if (n == 0) return 0;
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+	size_t blocks = (n + 255) / 256;
+	const size_t cap = (size_t)g.sm_count * 32;
+	if (blocks > cap) blocks = cap;
+	fill_uniform_kernel<<<(unsigned)blocks, 256, 0, s>>>(dx, n, seed * 0x9E3779B97F4A7C15ull, lo, hi - lo);
+	CU_TRY(cudaGetLastError(), "fill_uniform launch");
+	g.launches++;
+	return 0;
+}
+
+int ugemm_cuda_probe_tf32(const float *A, const float *B, float *D, int ksteps)
+{
+	if (ensure_init()) return 1;
+	if (ksteps < 1 || ksteps > 4) { set_error("probe: ksteps must be 1..4"); return 1; }
+	const size_t abytes = (size_t)128 * 8 * ksteps * 4, bbytes = (size_t)16 * 8 * ksteps * 4, dbytes = 128 * 16 * 4;
+	float *dA = nullptr, *dB = nullptr, *dD = nullptr;
+	CU_TRY(cudaMalloc(&dA, abytes), "probe cudaMalloc");
+	CU_TRY(cudaMalloc(&dB, bbytes), "probe cudaMalloc");
+	CU_TRY(cudaMalloc(&dD, dbytes), "probe cudaMalloc");
+	int rc = 1;
+	do {
+		if (cudaMemcpyAsync(dA, A, abytes, cudaMemcpyHostToDevice, g.stream) != cudaSuccess) break;
+		if (cudaMemcpyAsync(dB, B, bbytes, cudaMemcpyHostToDevice, g.stream) != cudaSuccess) break;
+		if (launch_probe_tf32(dA, dB, dD, ksteps, g.stream) != cudaSuccess) break;
+		g.launches++;
+		if (cudaMemcpyAsync(D, dD, dbytes, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess) break;
+		cudaError_t e = cudaStreamSynchronize(g.stream);
+		if (e != cudaSuccess) { set_error("probe failed: %s", cudaGetErrorString(e)); break; }
+		rc = 0;
+	} while (0);
+	if (rc && !g_has_err) set_error("probe failed: %s", cudaGetErrorString(cudaGetLastError()));
+	cudaFree(dA); cudaFree(dB); cudaFree(dD);
+	return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,48 @@
+// common.cuh -- shared declarations of the CUDA backend (internal; the public ABI is include/ugemm_cuda.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace ugemm {
+
+// A GEMM already normalised to row-major (column-major callers are mapped by operand swap, see
+// backend.cu: normalise()).  a_kmajor: op(A)'s k index is the contiguous one in memory (transA=='N');
+// b_kmajor: op(B)'s k index is contiguous (transB=='T').
+struct Problem {
+	int M, N, K;
+	float alpha, beta;
+	const float *A; long long lda; bool a_kmajor;
+	const float *B; long long ldb; bool b_kmajor;
+	float *C; long long ldc;
+};
+
+struct K1Tuning { int kc_blocks; int split; int cta_group; };
+
+// K2: register-blocked FFMA kernel (k2_simt.cu)
+cudaError_t launch_k2_simt(const Problem &p, cudaStream_t stream, int sm_count);
+// K1: 3xTF32 tcgen05 kernel (k1_tcgen05.cu).  *why (optional) receives a static string on ineligibility.
+bool        k1_eligible(const Problem &p, const char **why);
+cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count);
+// C <- beta*C over the M x N region (alpha==0 or K==0 path)
+cudaError_t launch_scale_c(const Problem &p, cudaStream_t stream);
+// probe (k1_tcgen05.cu)
+cudaError_t launch_probe_tf32(const float *dA, const float *dB, float *dD, int ksteps, cudaStream_t stream);
+// last diagnostic record written by a K1 watchdog (host-mapped memory), 0 if none
+const unsigned *k1_diag_host();
+
+// counter-based uniform stream shared by host and device (see ugemm_cuda.h)
+__host__ __device__ inline unsigned long long mix64(unsigned long long z)
+{
+	z += 0x9E3779B97F4A7C15ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+__host__ __device__ inline float uniform_at(unsigned long long base, unsigned long long i, float lo, float span)
+{
+	float u = (float)(mix64(base + i) >> 40) * 5.9604644775390625e-08f; // 2^-24, exact
+	return fmaf(span, u, lo);
+}
+
+} // namespace ugemm

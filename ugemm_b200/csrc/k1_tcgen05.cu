@@ -1,0 +1,513 @@
+// k1_tcgen05.cu -- K1: 3xTF32 error-compensated SGEMM on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+// C = alpha * op(A) op(B) + beta * C with fp32-class accuracy from TF32 tensor-core products:
+//     a = a_big + a_small,  a_big = tf32(a) (top 19 bits),  a_small = a - a_big  (exact in fp32)
+//     a*b ~= a_small*b_big + a_big*b_small + a_big*b_big        (a_small*b_small ~ 2^-22 dropped)
+// Three tcgen05.mma per k-step, credited as 2*M*N*K flop (effective roofline = dense TF32 peak / 3).
+//
+// Replaces the reference's blocked inner loops (sgemm_avx256.h:20-390, gemm_cpu.h:96-282, the OpenCL
+// gemm_fast / gemm_rnn kernels sgemm_ocl.h:444-538, sgemm_ocl2.h:17-90) for TMA-eligible problems.
+//
+// Structure (one CTA per SM, optionally paired as a 2-CTA cluster issuing cta_group::2 MMAs):
+//   warp 0      TMA producer: raw fp32 tiles of op(A) (128 rows) and op(B) (128 rows) per k-block of 32,
+//               128B-swizzled, into a 3-stage shared-memory ring.  K-major operands: one {32 k x 128 row}
+//               box, SWIZZLE_128B.  MN-major operands (transA=='T' / transB=='N'): four {32 mn x 32 k}
+//               boxes, SWIZZLE_128B_ATOM_32B (the only MN-major layout tcgen05 accepts for 32-bit types).
+//               Ragged M/N/K edges are zero-filled by TMA out-of-bounds handling.
+//   warps 4-7   transform: read each landed stage, write the "small" operand copies (same swizzled
+//               layout, so the transform is a flat element-wise pass), fence.proxy.async, signal the MMA.
+//   warp 1      MMA issuer (leader CTA only): per k-step of 8: small*big, big*small, big*big into the TMEM
+//               accumulator; tcgen05.commit releases the stage; accumulators are double-buffered in TMEM.
+//   warps 8-15  epilogue: tcgen05.ld the accumulator, (optionally) promote partial sums every kc_blocks
+//               k-blocks into fp32 registers with round-to-nearest adds, then fused alpha/beta and
+//               direct global stores (row per thread, 128 B contiguous per 32-column group).
+//   Persistent: each CTA (pair) walks a static, L2-friendly grouped tile order.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace ugemm {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int BK = 32;                        // fp32 elements per k-block = one 128-byte swizzle line
+constexpr int ROWS = 128;                     // rows of op(A) / rows of op(B) staged per CTA per k-block
+constexpr int OPER_BYTES = ROWS * BK * 4;     // 16 KiB
+constexpr int RAW_BYTES = 2 * OPER_BYTES;     // A raw | B raw
+constexpr int STAGE_BYTES = 2 * RAW_BYTES;    // A raw | B raw | A small | B small = 64 KiB
+constexpr int STAGES = 3;
+constexpr int NUM_THREADS = 512;              // 16 warps, see role map above
+constexpr int BAR_BYTES = 128;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024; // + slack for 1024-B alignment
+constexpr long long WATCHDOG_CYCLES = 6000000000LL;
+
+struct K1Params {
+	int M, N, K;
+	float alpha, beta;
+	float *C;
+	long long ldc;
+	int a_kmajor, b_kmajor;
+	int tiles_m, tiles_n, num_tiles;
+	int num_k_blocks, kc_blocks, split, vecC;
+	unsigned *diag;
+};
+
+__device__ __forceinline__ void watchdog_fail(unsigned *diag, int code, uint32_t parity)
+{
+	if (diag) {
+		diag[1] = blockIdx.x; diag[2] = threadIdx.x; diag[3] = parity; diag[0] = (unsigned)code;
+		__threadfence_system();
+	}
+	__trap();
+}
+// spin on an mbarrier phase with a watchdog so that a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned *diag, int code)
+{
+	if (mbar_try_wait(bar, parity)) return;
+	const long long t0 = clock64();
+	while (!mbar_try_wait(bar, parity))
+		if (clock64() - t0 > WATCHDOG_CYCLES) watchdog_fail(diag, code, parity);
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, unsigned *diag, int code)
+{
+	if (mbar_try_wait_cluster(bar, parity)) return;
+	const long long t0 = clock64();
+	while (!mbar_try_wait_cluster(bar, parity))
+		if (clock64() - t0 > WATCHDOG_CYCLES) watchdog_fail(diag, code, parity);
+}
+
+// grouped tile order: 8 consecutive m-tiles share an n sweep so a wave's A and B panels stay in L2
+__device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int &tm, int &tn)
+{
+	constexpr int GROUP = 8;
+	const int per_group = GROUP * tiles_n;
+	const int group = tile / per_group;
+	const int first_m = group * GROUP;
+	const int gsize = min(tiles_m - first_m, GROUP);
+	const int r = tile - group * per_group;
+	tm = first_m + r % gsize;
+	tn = r / gsize;
+}
+
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_rna(float x)
+{
+	uint32_t r;
+	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+	return __uint_as_float(r);
+}
+
+template <int CG>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const K1Params P)
+{
+	constexpr int BN = 128 * CG;          // accumulator columns (UMMA N)
+	constexpr int UMMA_M = 128 * CG;
+	constexpr int NG = BN / 2 / 32;       // 32-column groups per epilogue thread
+	constexpr uint32_t TMEM_COLS = 2 * BN;
+
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+	auto full_bar  = [&](int s) { return bar_base + 8u * s; };
+	auto xf_bar    = [&](int s) { return bar_base + 8u * (STAGES + s); };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+	auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
+	auto tempty_bar= [&](int a) { return bar_base + 8u * (3 * STAGES + 2 + a); };
+	const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+	volatile uint32_t *tmem_slot_ptr =
+	    reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+	const int warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+	const int cluster_id = (CG == 2) ? (int)cluster_id_x() : (int)blockIdx.x;
+	const int num_clusters = (CG == 2) ? (int)num_clusters_x() : (int)gridDim.x;
+	const int nkb = P.num_k_blocks;
+	const int kc = P.kc_blocks;
+
+	// ---- one-time setup --------------------------------------------------------------------------------
+	if (warp == 0 && lane == 0) {
+		prefetch_tmap(&tmA);
+		prefetch_tmap(&tmB);
+		for (int s = 0; s < STAGES; s++) {
+			mbar_init(full_bar(s), 1);
+			mbar_init(xf_bar(s), 4 * CG);     // 4 transform warps per CTA of the pair
+			mbar_init(empty_bar(s), 1);
+		}
+		for (int a = 0; a < 2; a++) {
+			mbar_init(tfull_bar(a), 1);
+			mbar_init(tempty_bar(a), 8 * CG);  // 8 epilogue warps per CTA of the pair
+		}
+		fence_mbar_init();
+	}
+	__syncwarp();
+	if (warp == 1) {
+		tmem_alloc<CG>(tmem_slot, TMEM_COLS);
+		tmem_relinquish<CG>();
+	}
+	tc_fence_before();
+	if (CG == 2) { cluster_arrive(); cluster_wait(); } else __syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot_ptr;
+
+	if (warp < 4) {
+		reg_dec<48>();
+		if (warp == 0 && lane == 0) {
+			// ================= TMA producer =================
+			int it = 0;
+			for (int tile = cluster_id; tile < P.num_tiles; tile += num_clusters) {
+				int tm, tn;
+				decode_tile(tile, P.tiles_m, P.tiles_n, tm, tn);
+				const int a_row0 = tm * UMMA_M + (int)cta_rank * ROWS;
+				const int b_row0 = tn * BN + (int)cta_rank * ROWS;
+				for (int kb = 0; kb < nkb; kb++, it++) {
+					const int s = it % STAGES;
+					const uint32_t ph = (it / STAGES) & 1;
+					mbar_wait(empty_bar(s), ph ^ 1u, P.diag, 1);
+					mbar_arrive_expect_tx(full_bar(s), RAW_BYTES);
+					const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + OPER_BYTES;
+					const int k0 = kb * BK;
+					if (P.a_kmajor) tma_load_2d(sA, &tmA, full_bar(s), k0, a_row0);
+					else
+						for (int j = 0; j < ROWS / 32; j++) tma_load_2d(sA + j * 4096, &tmA, full_bar(s), a_row0 + 32 * j, k0);
+					if (P.b_kmajor) tma_load_2d(sB, &tmB, full_bar(s), k0, b_row0);
+					else
+						for (int j = 0; j < ROWS / 32; j++) tma_load_2d(sB + j * 4096, &tmB, full_bar(s), b_row0 + 32 * j, k0);
+				}
+			}
+		} else if (warp == 1 && lane == 0 && cta_rank == 0) {
+			// ================= MMA issuer (leader CTA) =================
+			const uint32_t idesc = idesc_tf32(UMMA_M, BN, P.a_kmajor ? 0 : 1, P.b_kmajor ? 0 : 1);
+			// K-major SW128: LBO(enc)=1, SBO=1024 B, k-step (8 fp32) = +32 B inside the swizzle line.
+			// MN-major SW128/32B-atom: LBO=4096 B between 32-wide mn groups, SBO=512 B between 4-row
+			// k groups, k-step (8 rows) = +1024 B.
+			const uint32_t a_lbo = P.a_kmajor ? 1u : 256u, a_sbo = P.a_kmajor ? 64u : 32u, a_lay = P.a_kmajor ? 2u : 1u;
+			const uint32_t b_lbo = P.b_kmajor ? 1u : 256u, b_sbo = P.b_kmajor ? 64u : 32u, b_lay = P.b_kmajor ? 2u : 1u;
+			const uint32_t a_kstep = P.a_kmajor ? 32u : 1024u, b_kstep = P.b_kmajor ? 32u : 1024u;
+			int it = 0, ci = 0;
+			for (int tile = cluster_id; tile < P.num_tiles; tile += num_clusters) {
+				for (int kb0 = 0; kb0 < nkb; kb0 += kc, ci++) {
+					const int acc = ci & 1;
+					const uint32_t aph = (ci >> 1) & 1;
+					if (CG == 2) mbar_wait_cluster(tempty_bar(acc), aph ^ 1u, P.diag, 2);
+					else mbar_wait(tempty_bar(acc), aph ^ 1u, P.diag, 2);
+					tc_fence_after();
+					const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+					const int kb1 = min(kb0 + kc, nkb);
+					for (int kb = kb0; kb < kb1; kb++, it++) {
+						const int s = it % STAGES;
+						const uint32_t ph = (it / STAGES) & 1;
+						if (CG == 2) mbar_wait_cluster(xf_bar(s), ph, P.diag, 3);
+						else mbar_wait(xf_bar(s), ph, P.diag, 3);
+						tc_fence_after();
+						const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + OPER_BYTES;
+						const uint32_t sAs = sA + RAW_BYTES, sBs = sB + RAW_BYTES;
+#pragma unroll
+						for (int k4 = 0; k4 < BK / 8; k4++) {
+							const uint64_t dAb = smem_desc(sA + k4 * a_kstep, a_lbo, a_sbo, a_lay);
+							const uint64_t dAs = smem_desc(sAs + k4 * a_kstep, a_lbo, a_sbo, a_lay);
+							const uint64_t dBb = smem_desc(sB + k4 * b_kstep, b_lbo, b_sbo, b_lay);
+							const uint64_t dBs = smem_desc(sBs + k4 * b_kstep, b_lbo, b_sbo, b_lay);
+							mma_tf32_ss<CG>(d_tmem, dAs, dBb, idesc, (kb > kb0 || k4 > 0) ? 1u : 0u);
+							mma_tf32_ss<CG>(d_tmem, dAb, dBs, idesc, 1u);
+							mma_tf32_ss<CG>(d_tmem, dAb, dBb, idesc, 1u);
+						}
+						mma_commit<CG>(empty_bar(s));   // stage free once these MMAs have read it
+					}
+					mma_commit<CG>(tfull_bar(acc));     // accumulator chunk complete
+				}
+			}
+		}
+		__syncwarp();   // reconverge before the .aligned teardown barrier
+	} else if (warp < 8) {
+		// ================= transform warps: write the "small" operand copies =================
+		reg_dec<64>();
+		const int t = threadIdx.x - 128;
+		int it = 0;
+		for (int tile = cluster_id; tile < P.num_tiles; tile += num_clusters) {
+			for (int kb = 0; kb < nkb; kb++, it++) {
+				const int s = it % STAGES;
+				const uint32_t ph = (it / STAGES) & 1;
+				mbar_wait(full_bar(s), ph, P.diag, 4);
+				const uint32_t raw = smem_base + s * STAGE_BYTES;
+#pragma unroll
+				for (int half = 0; half < 2; half++) {
+					float4 v[8];
+#pragma unroll
+					for (int i = 0; i < 8; i++) v[i] = lds128(raw + (uint32_t)(t + 128 * (half * 8 + i)) * 16u);
+#pragma unroll
+					for (int i = 0; i < 8; i++) {
+						const uint32_t off = (uint32_t)(t + 128 * (half * 8 + i)) * 16u;
+						float4 b, sm;
+						if (P.split == 0) {
+							b.x = tf32_trunc(v[i].x); b.y = tf32_trunc(v[i].y); b.z = tf32_trunc(v[i].z); b.w = tf32_trunc(v[i].w);
+						} else {
+							b.x = tf32_rna(v[i].x); b.y = tf32_rna(v[i].y); b.z = tf32_rna(v[i].z); b.w = tf32_rna(v[i].w);
+						}
+						sm.x = v[i].x - b.x; sm.y = v[i].y - b.y; sm.z = v[i].z - b.z; sm.w = v[i].w - b.w;
+						sts128(raw + RAW_BYTES + off, sm);
+						if (P.split != 0) sts128(raw + off, b);
+					}
+				}
+				fence_proxy_async_smem();
+				__syncwarp();
+				if (lane == 0) {
+					if (CG == 2) mbar_arrive_cluster(xf_bar(s), 0);
+					else mbar_arrive(xf_bar(s));
+				}
+			}
+		}
+	} else {
+		// ================= epilogue warps =================
+		reg_inc<200>();
+		const int e = warp - 8;
+		const int q = e & 3;        // TMEM lane quarter (must equal warp % 4)
+		const int h = e >> 2;       // column half
+		const float alpha = P.alpha, beta = P.beta;
+		int ci = 0;
+		for (int tile = cluster_id; tile < P.num_tiles; tile += num_clusters) {
+			int tm, tn;
+			decode_tile(tile, P.tiles_m, P.tiles_n, tm, tn);
+			float acc[NG][32];
+#pragma unroll
+			for (int g = 0; g < NG; g++)
+#pragma unroll
+				for (int i = 0; i < 32; i++) acc[g][i] = 0.f;
+			for (int kb0 = 0; kb0 < nkb; kb0 += kc, ci++) {
+				const int ab = ci & 1;
+				const uint32_t aph = (ci >> 1) & 1;
+				mbar_wait(tfull_bar(ab), aph, P.diag, 5);
+				tc_fence_after();
+				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * (BN / 2));
+#pragma unroll
+				for (int g = 0; g < NG; g++) {
+					float v[32];
+					tmem_ld_32x32b_x32(taddr + g * 32, v);
+#pragma unroll
+					for (int i = 0; i < 32; i++) acc[g][i] += v[i];   // fp32 round-to-nearest promotion
+				}
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0) {
+					if (CG == 2) mbar_arrive_cluster(tempty_bar(ab), 0);
+					else mbar_arrive(tempty_bar(ab));
+				}
+			}
+			// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
+			const long long row = (long long)tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane;
+			if (row < P.M) {
+				float *crow = P.C + row * P.ldc;
+#pragma unroll
+				for (int g = 0; g < NG; g++) {
+					const long long col0 = (long long)tn * BN + h * (BN / 2) + g * 32;
+					if (P.vecC && col0 + 31 < P.N) {
+#pragma unroll
+						for (int i = 0; i < 32; i += 4) {
+							float4 *cp = reinterpret_cast<float4 *>(crow + col0 + i);
+							float4 o;
+							if (beta != 0.f) {
+								const float4 cv = *cp;
+								o.x = fmaf(alpha, acc[g][i + 0], beta * cv.x); o.y = fmaf(alpha, acc[g][i + 1], beta * cv.y);
+								o.z = fmaf(alpha, acc[g][i + 2], beta * cv.z); o.w = fmaf(alpha, acc[g][i + 3], beta * cv.w);
+							} else {
+								o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1];
+								o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
+							}
+							*cp = o;
+						}
+					} else {
+#pragma unroll
+						for (int i = 0; i < 32; i++) {
+							if (col0 + i < P.N) {
+								float o = alpha * acc[g][i];
+								if (beta != 0.f) o = fmaf(alpha, acc[g][i], beta * crow[col0 + i]);
+								crow[col0 + i] = o;
+							}
+						}
+					}
+				}
+			}
+		}
+	}
+
+	// ---- teardown: everyone (both CTAs of a pair) done before TMEM is returned ------------------------------
+	tc_fence_before();
+	if (CG == 2) { cluster_arrive(); cluster_wait(); } else __syncthreads();
+	if (warp == 1) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Probe: one CTA, manual K-major SWIZZLE_128B staging (no TMA), `ksteps` chained 128x16x8 TF32 MMAs.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+probe_tf32_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ D, int ksteps, unsigned *diag)
+{
+	__shared__ __align__(1024) uint8_t sA[128 * 128];
+	__shared__ __align__(1024) uint8_t sB[16 * 128];
+	__shared__ __align__(8) uint64_t bar;
+	__shared__ uint32_t tmem_slot;
+	const int tid = threadIdx.x, warp = tid >> 5;
+	const int K = 8 * ksteps; // <= 32
+	// K-major SW128: element (r,k) at r*128 + ((k/4) ^ (r%8))*16 + (k%4)*4
+	for (int idx = tid; idx < 128 * 32; idx += 128) {
+		int r = idx / 32, k = idx % 32;
+		float v = k < K ? A[r * K + k] : 0.f;
+		*reinterpret_cast<float *>(sA + r * 128 + (((k >> 2) ^ (r & 7)) << 4) + (k & 3) * 4) = v;
+	}
+	for (int idx = tid; idx < 16 * 32; idx += 128) {
+		int r = idx / 32, k = idx % 32;
+		float v = k < K ? B[r * K + k] : 0.f;
+		*reinterpret_cast<float *>(sB + r * 128 + (((k >> 2) ^ (r & 7)) << 4) + (k & 3) * 4) = v;
+	}
+	if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+	if (warp == 0) { tmem_alloc<1>(smem_u32(&tmem_slot), 32); tmem_relinquish<1>(); }
+	fence_proxy_async_smem();
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = tmem_slot;
+	if (tid == 0) {
+		const uint32_t idesc = idesc_tf32(128, 16, 0, 0);
+		for (int k = 0; k < ksteps; k++) {
+			const uint64_t da = smem_desc(smem_u32(sA) + k * 32, 1, 64, 2);
+			const uint64_t db = smem_desc(smem_u32(sB) + k * 32, 1, 64, 2);
+			mma_tf32_ss<1>(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
+		}
+		mma_commit<1>(smem_u32(&bar));
+	}
+	mbar_wait(smem_u32(&bar), 0, diag, 9);
+	tc_fence_after();
+	float v[16];
+	tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+	for (int i = 0; i < 16; i++) D[tid * 16 + i] = v[i];
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 0) tmem_dealloc<1>(tmem_base, 32);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+	static EncodeTiledFn fn = nullptr;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+		    q == cudaDriverEntryPointSuccess)
+			fn = reinterpret_cast<EncodeTiledFn>(p);
+	});
+	return fn;
+}
+
+// K-major operand: `rows` lines of `K` contiguous fp32, pitch ld  -> dims {K, rows}, box {32, 128}, SWIZZLE_128B
+// MN-major operand: `K` lines of `rows` contiguous fp32, pitch ld -> dims {rows, K}, box {32, 32}, SWIZZLE_128B_ATOM_32B
+bool make_operand_map(CUtensorMap *map, const float *base, long long rows, long long K, long long ld, bool kmajor)
+{
+	EncodeTiledFn fn = encode_fn();
+	if (!fn) return false;
+	cuuint64_t gdim[2], gstride[1];
+	cuuint32_t box[2], estr[2] = {1, 1};
+	CUtensorMapSwizzle sw;
+	if (kmajor) { gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows; box[0] = BK; box[1] = ROWS; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
+	else        { gdim[0] = (cuuint64_t)rows; gdim[1] = (cuuint64_t)K; box[0] = 32; box[1] = BK; sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; }
+	gstride[0] = (cuuint64_t)ld * 4;
+	CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
+	                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return r == CUDA_SUCCESS;
+}
+
+unsigned *g_diag_host = nullptr, *g_diag_dev = nullptr;
+unsigned *diag_dev()
+{
+	static std::once_flag once;
+	std::call_once(once, [] {
+		if (cudaHostAlloc(&g_diag_host, 64, cudaHostAllocMapped) == cudaSuccess) {
+			for (int i = 0; i < 16; i++) g_diag_host[i] = 0;
+			if (cudaHostGetDevicePointer(&g_diag_dev, g_diag_host, 0) != cudaSuccess) g_diag_dev = nullptr;
+		}
+	});
+	return g_diag_dev;
+}
+
+template <int CG>
+cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
+{
+	CUtensorMap tmA, tmB;
+	if (!make_operand_map(&tmA, p.A, p.M, p.K, p.lda, p.a_kmajor)) return cudaErrorInvalidValue;
+	if (!make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.b_kmajor)) return cudaErrorInvalidValue;
+	K1Params P;
+	P.M = p.M; P.N = p.N; P.K = p.K; P.alpha = p.alpha; P.beta = p.beta; P.C = p.C; P.ldc = p.ldc;
+	P.a_kmajor = p.a_kmajor; P.b_kmajor = p.b_kmajor;
+	const int tile_m = 128 * CG, tile_n = 128 * CG;
+	P.tiles_m = (p.M + tile_m - 1) / tile_m;
+	P.tiles_n = (p.N + tile_n - 1) / tile_n;
+	const long long nt = (long long)P.tiles_m * P.tiles_n;
+	if (nt > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+	P.num_tiles = (int)nt;
+	P.num_k_blocks = (p.K + BK - 1) / BK;
+	P.kc_blocks = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
+	P.split = t.split;
+	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0) ? 1 : 0;
+	P.diag = diag_dev();
+
+	static bool attr_set[3] = {false, false, false};
+	if (!attr_set[CG]) {
+		cudaError_t e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+		if (e != cudaSuccess) return e;
+		attr_set[CG] = true;
+	}
+	const int max_clusters = sm_count / CG;
+	const int clusters = (int)(nt < max_clusters ? nt : max_clusters);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)(clusters * CG));
+	cfg.blockDim = dim3(NUM_THREADS);
+	cfg.dynamicSmemBytes = SMEM_BYTES;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG>, tmA, tmB, P);
+}
+
+} // namespace
+
+const unsigned *k1_diag_host() { return g_diag_host; }
+
+bool k1_eligible(const Problem &p, const char **why)
+{
+	const char *w = nullptr;
+	if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.B) & 15)) w = "A or B not 16-byte aligned (TMA base rule)";
+	else if (p.lda % 4 || p.ldb % 4) w = "lda or ldb not a multiple of 4 (TMA global stride must be a multiple of 16 bytes)";
+	else if (p.M < 1 || p.N < 1 || p.K < 1) w = "empty problem";
+	else if (!encode_fn()) w = "cuTensorMapEncodeTiled unavailable";
+	if (why) *why = w;
+	return w == nullptr;
+}
+
+cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
+{
+	if (t.cta_group == 1) return launch_cg<1>(p, t, stream, sm_count);
+	return launch_cg<2>(p, t, stream, sm_count);
+}
+
+cudaError_t launch_probe_tf32(const float *dA, const float *dB, float *dD, int ksteps, cudaStream_t stream)
+{
+	if (ksteps < 1 || ksteps > 4) return cudaErrorInvalidValue;
+	probe_tf32_kernel<<<1, 128, 0, stream>>>(dA, dB, dD, ksteps, diag_dev());
+	return cudaGetLastError();
+}
+
+} // namespace ugemm

@@ -1,0 +1,237 @@
+// k2_simt.cu -- K2: register-blocked FFMA SGEMM for sm_100a (plain fp32, SIMT).
+//
+// Role (north_star): small, skinny, oddly-strided and transposed shapes that TMA cannot take
+// (lda/ldb not multiples of 4, misaligned bases), and the plain-fp32 reference mode.  Replaces the
+// reference's OpenCL `gemm_rnn` kernels (sgemm_ocl1.h:14-41, sgemm_ocl2.h:17-90) AND its separate
+// `transpose` kernel (sgemm_ocl2.h:95-128): op(A)/op(B) are never materialised, the transposition is
+// folded into the global->shared staging.
+//
+// Shape of the kernel: BM x BN C tile per CTA (128x128 or 64x64), BK = 16, 256 threads, each thread an
+// (TM x TN) = 8x8 or 4x4 register tile split in two halves per dimension so the shared-memory reads are
+// conflict-free 128-bit (64-bit) loads.  Global loads are 128-bit when the operand allows it (base 16 B
+// aligned, ld % 4 == 0, quad fully in range) and guarded scalars otherwise; the next k-tile is prefetched
+// into registers while the current one is multiplied (double-buffered shared memory, one barrier per tile).
+// Algorithmic cost per C element: 2K flop; roofline = FP32 FFMA peak (SMs x 128 x 2 x clock).
+#include "common.cuh"
+
+namespace ugemm {
+
+namespace {
+
+constexpr int K2_BK = 16;
+constexpr int K2_THREADS = 256;
+constexpr int K2_PAD = 4;
+
+__device__ __forceinline__ float4 load_quad(const float *__restrict__ line, long long c, long long cmax,
+                                            bool line_ok, bool vec)
+{
+	float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (!line_ok) return v;
+	if (vec && c + 3 < cmax) return __ldg(reinterpret_cast<const float4 *>(line + c));
+	if (c + 0 < cmax) v.x = __ldg(line + c + 0);
+	if (c + 1 < cmax) v.y = __ldg(line + c + 1);
+	if (c + 2 < cmax) v.z = __ldg(line + c + 2);
+	if (c + 3 < cmax) v.w = __ldg(line + c + 3);
+	return v;
+}
+
+// Operand staging.  The shared tile is always [BK][BMN + PAD] (k-major rows of the M or N extent).
+//   KCONTIG: global lines run along k (row-major 'N' A, or 'T' B): line index = m (or n), column = k
+//   else   : global lines run along m/n (row-major 'T' A, or 'N' B): line index = k, column = m (or n)
+template <int BMN, bool KCONTIG>
+struct Stager {
+	static constexpr int QUADS = BMN * K2_BK / 4 / K2_THREADS;
+	float4 r[QUADS];
+
+	__device__ __forceinline__ void load(const float *__restrict__ base, long long ld, long long mn0, long long mn_max,
+	                                     long long k0, long long k_max, bool vec, int tid)
+	{
+#pragma unroll
+		for (int i = 0; i < QUADS; i++) {
+			int f = tid + i * K2_THREADS;
+			if (KCONTIG) {
+				int line = f / (K2_BK / 4), kq = (f % (K2_BK / 4)) * 4;
+				long long mn = mn0 + line;
+				r[i] = load_quad(base + mn * ld, k0 + kq, k_max, mn < mn_max, vec);
+			} else {
+				int k = f / (BMN / 4), q = (f % (BMN / 4)) * 4;
+				long long kk = k0 + k;
+				r[i] = load_quad(base + kk * ld, mn0 + q, mn_max, kk < k_max, vec);
+			}
+		}
+	}
+	__device__ __forceinline__ void store(float (*s)[BMN + K2_PAD], int tid) const
+	{
+#pragma unroll
+		for (int i = 0; i < QUADS; i++) {
+			int f = tid + i * K2_THREADS;
+			if (KCONTIG) {
+				int line = f / (K2_BK / 4), kq = (f % (K2_BK / 4)) * 4;
+				s[kq + 0][line] = r[i].x; s[kq + 1][line] = r[i].y;
+				s[kq + 2][line] = r[i].z; s[kq + 3][line] = r[i].w;
+			} else {
+				int k = f / (BMN / 4), q = (f % (BMN / 4)) * 4;
+				*reinterpret_cast<float4 *>(&s[k][q]) = r[i];
+			}
+		}
+	}
+};
+
+template <int BM, int BN, int TM, int TN, bool AK, bool BKM>
+__global__ void __launch_bounds__(K2_THREADS, (BM >= 128 ? 2 : 3))
+k2_simt_kernel(const Problem p, const int tiles_m, const int tiles_n, const bool vecA, const bool vecB, const bool vecC)
+{
+	static_assert((BM / TM) * (BN / TN) == K2_THREADS, "thread tile must cover the CTA tile");
+	constexpr int HM = TM / 2, HN = TN / 2;
+	__shared__ __align__(16) float As[2][K2_BK][BM + K2_PAD];
+	__shared__ __align__(16) float Bs[2][K2_BK][BN + K2_PAD];
+
+	const int tid = threadIdx.x;
+	const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+
+	// grouped tile order: 16 consecutive m-tiles share the same n-tile sweep (keeps A/B panels in L2)
+	constexpr int GROUP = 16;
+	const long long tile = blockIdx.x;
+	const long long per_group = (long long)GROUP * tiles_n;
+	const int group = (int)(tile / per_group);
+	const int first_m = group * GROUP;
+	const int gsize = min(tiles_m - first_m, GROUP);
+	const int tm = first_m + (int)((tile % per_group) % gsize);
+	const int tn = (int)((tile % per_group) / gsize);
+	const long long m0 = (long long)tm * BM, n0 = (long long)tn * BN;
+
+	float acc[TM][TN];
+#pragma unroll
+	for (int i = 0; i < TM; i++)
+#pragma unroll
+		for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+
+	Stager<BM, AK> sa;
+	Stager<BN, BKM> sb;
+	const int ktiles = (p.K + K2_BK - 1) / K2_BK;
+
+	sa.load(p.A, p.lda, m0, p.M, 0, p.K, vecA, tid);
+	sb.load(p.B, p.ldb, n0, p.N, 0, p.K, vecB, tid);
+	sa.store(As[0], tid);
+	sb.store(Bs[0], tid);
+	__syncthreads();
+
+	for (int t = 0; t < ktiles; t++) {
+		const int cur = t & 1;
+		if (t + 1 < ktiles) {
+			sa.load(p.A, p.lda, m0, p.M, (long long)(t + 1) * K2_BK, p.K, vecA, tid);
+			sb.load(p.B, p.ldb, n0, p.N, (long long)(t + 1) * K2_BK, p.K, vecB, tid);
+		}
+#pragma unroll
+		for (int kk = 0; kk < K2_BK; kk++) {
+			float a[TM], b[TN];
+#pragma unroll
+			for (int i = 0; i < HM; i++) {
+				a[i] = As[cur][kk][ty * HM + i];
+				a[HM + i] = As[cur][kk][BM / 2 + ty * HM + i];
+			}
+#pragma unroll
+			for (int j = 0; j < HN; j++) {
+				b[j] = Bs[cur][kk][tx * HN + j];
+				b[HN + j] = Bs[cur][kk][BN / 2 + tx * HN + j];
+			}
+#pragma unroll
+			for (int i = 0; i < TM; i++)
+#pragma unroll
+				for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+		}
+		if (t + 1 < ktiles) {
+			sa.store(As[cur ^ 1], tid);
+			sb.store(Bs[cur ^ 1], tid);
+		}
+		__syncthreads();
+	}
+
+	// fused epilogue: C = alpha*acc + beta*C (C never read when beta == 0), ld padding never touched
+	const float alpha = p.alpha, beta = p.beta;
+#pragma unroll
+	for (int i = 0; i < TM; i++) {
+		const long long m = m0 + (i < HM ? ty * HM + i : BM / 2 + ty * HM + (i - HM));
+		if (m >= p.M) continue;
+		float *crow = p.C + m * p.ldc;
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const long long n = n0 + h * (BN / 2) + tx * HN;
+			if (HN == 4 && vecC && n + 3 < p.N) {
+				float4 o;
+				float4 *cp = reinterpret_cast<float4 *>(crow + n);
+				if (beta != 0.f) {
+					float4 c = *cp;
+					o.x = fmaf(alpha, acc[i][h * HN + 0], beta * c.x);
+					o.y = fmaf(alpha, acc[i][h * HN + 1], beta * c.y);
+					o.z = fmaf(alpha, acc[i][h * HN + 2], beta * c.z);
+					o.w = fmaf(alpha, acc[i][h * HN + 3], beta * c.w);
+				} else {
+					o.x = alpha * acc[i][h * HN + 0]; o.y = alpha * acc[i][h * HN + 1];
+					o.z = alpha * acc[i][h * HN + 2]; o.w = alpha * acc[i][h * HN + 3];
+				}
+				*cp = o;
+			} else {
+#pragma unroll
+				for (int j = 0; j < HN; j++) {
+					if (n + j < p.N) {
+						float v = alpha * acc[i][h * HN + j];
+						if (beta != 0.f) v = fmaf(alpha, acc[i][h * HN + j], beta * crow[n + j]);
+						crow[n + j] = v;
+					}
+				}
+			}
+		}
+	}
+}
+
+__global__ void scale_c_kernel(float *C, long long ldc, int M, int N, float beta)
+{
+	long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	long long m = blockIdx.y;
+	if (n >= N) return;
+	for (; m < M; m += gridDim.y) {
+		float *c = C + m * ldc + n;
+		*c = (beta == 0.f) ? 0.f : beta * *c;
+	}
+}
+
+template <int BM, int BN, int TM, int TN>
+cudaError_t launch_cfg(const Problem &p, cudaStream_t stream)
+{
+	const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+	const long long tiles = (long long)tiles_m * tiles_n;
+	if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+	auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+	const bool vecA = al16(p.A) && (p.lda % 4 == 0);
+	const bool vecB = al16(p.B) && (p.ldb % 4 == 0);
+	const bool vecC = al16(p.C) && (p.ldc % 4 == 0);
+	dim3 grid((unsigned)tiles), block(K2_THREADS);
+#define K2_LAUNCH(AK, BKM) \
+	k2_simt_kernel<BM, BN, TM, TN, AK, BKM><<<grid, block, 0, stream>>>(p, tiles_m, tiles_n, vecA, vecB, vecC)
+	if (p.a_kmajor) { if (p.b_kmajor) K2_LAUNCH(true, true); else K2_LAUNCH(true, false); }
+	else            { if (p.b_kmajor) K2_LAUNCH(false, true); else K2_LAUNCH(false, false); }
+#undef K2_LAUNCH
+	return cudaGetLastError();
+}
+
+} // namespace
+
+cudaError_t launch_k2_simt(const Problem &p, cudaStream_t stream, int sm_count)
+{
+	// 128x128 tiles once they fill the machine (>= one CTA per SM); 64x64 below that so that small and
+	// skinny problems still spread over the 148 SMs.
+	const long long big_tiles = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128);
+	if (big_tiles >= sm_count) return launch_cfg<128, 128, 8, 8>(p, stream);
+	return launch_cfg<64, 64, 4, 4>(p, stream);
+}
+
+cudaError_t launch_scale_c(const Problem &p, cudaStream_t stream)
+{
+	if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+	dim3 block(256), grid((unsigned)((p.N + 255) / 256), (unsigned)min(p.M, 65535));
+	scale_c_kernel<<<grid, block, 0, stream>>>(p.C, p.ldc, p.M, p.N, p.beta);
+	return cudaGetLastError();
+}
+
+} // namespace ugemm
