@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- the headline SGEMM benchmark of BASELINE.json, measured on B200 through the C ABI.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c5]
+
+N = 1  workload c2: row-major NN SGEMM 8192^3 fp32, alpha=1 beta=0 (BASELINE configs[1]), auto dispatch -> K1
+       (3xTF32 tcgen05).  A "step" is one GEMM over device-resident synthetic operands (805 MB > 126 MB L2, so
+       nothing survives in L2 between steps).  `value` = TFLOP/s over K back-to-back steps, CUDA events.
+N > 1  workload c5: 32768^3 sharded as a 2-D grid of C tiles (ugemm_b200/dist.py), launched by torchrun, one rank per
+       GPU over NCCL.  A step = owner-rooted panel broadcast + local GEMMs (distribution INCLUDED); strong scaling.
+`e2e`  the same metric through the reference-facing host-pointer call (sgemm_cuda with pinned HOST buffers:
+       H2D of A and B, kernel, D2H of C inside the timed region), wall clock around blocking calls.
+`roofline`     dominant kernel vs the measured tensor peak: MEASURED_PEAKS.json bf16 dense / 2 (TF32) / 3 (3 MMAs).
+`cpu_baseline` the reference's own CPU SGEMM (oracle/_ref: unmodified sgemm_avx on all host cores over disjoint
+       row slabs) on a bounded row-slab sample of the same workload.  --impl reference prints that arm alone.
+The oracle/ directory is only ever executed here as that CPU baseline, never as the thing measured for `value`.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(M=8192, N=8192, K=8192, desc="SGEMM row-major NN 8192x8192x8192 fp32 alpha=1 beta=0 (BASELINE configs[1])"),
+    "c4": dict(M=200704, N=256, K=1152, desc="im2col-shaped SGEMM NN 200704x256x1152 fp32 (BASELINE configs[3])"),
+    "c5": dict(M=32768, N=32768, K=32768, desc="SGEMM NN 32768^3 fp32 sharded as a 2-D C-tile grid (BASELINE configs[4])"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return {"bf16_burst": float(p["bf16_tflops"]), "bf16_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    "hbm_gbs": float(p["hbm_gbs"]), "source": "measured"}
+        except Exception:
+            pass
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.rows, self.proc, self.thread = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference_arm(wl, seconds_target, steps=1, warmup=0):
+    """Reference CPU SGEMM on all host cores over a bounded row-slab sample of workload `wl`.
+    Returns (tflops, cores, kind, sample_description, ms_per_step)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+
+    import _oracle as O
+    N, K = wl["N"], wl["K"]
+    r = O.ref()
+    if r is not None:
+        kind, cores = "reference", int(r.ref_max_threads())
+        fn = lambda M, A, B, Cm: r.ref_sgemm_avx_mt(cores, b"R", b"N", b"N", M, N, K, 1.0, A, K, B, N, 0.0, Cm, N)
+        what = "unmodified sgemm_avx (sgemm_avx256.h:392) on disjoint row slabs"
+    else:
+        o = O.oracle()
+        kind, cores = "port", int(o.oracle_max_threads())
+        fn = lambda M, A, B, Cm: o.oracle_sgemm_banded(cores, b"R", b"N", b"N", M, N, K, 1.0, A, K, B, N, 0.0, Cm, N)
+        what = "oracle port of sgemm_avx's 35-band order"
+    B = O.fill_uniform(K * N, 2)
+    # calibrate on a small slab, then size the sample for ~seconds_target of CPU work per step
+    m0 = max(2 * cores, 32)
+    A = O.fill_uniform(m0 * K, 1)
+    Cm = np.zeros(m0 * N, np.float32)
+    fn(m0, A, B, Cm)                       # first call pays thread start-up and page faults
+    t = time.perf_counter(); fn(m0, A, B, Cm); dt = max(time.perf_counter() - t, 1e-4)
+    rows = int(min(wl["M"], max(64 * cores, (seconds_target / dt) * m0)))
+    rows -= rows % (2 * cores)
+    rows = max(rows, m0)
+    A = O.fill_uniform(rows * K, 1)
+    Cm = np.zeros(rows * N, np.float32)
+    for _ in range(warmup):
+        fn(rows, A, B, Cm)
+    t = time.perf_counter()
+    for _ in range(steps):
+        fn(rows, A, B, Cm)
+    dt = (time.perf_counter() - t) / steps
+    tflops = 2.0 * rows * N * K / dt / 1e12
+    sample = f"{what}; rows 0..{rows - 1} of C ({rows}x{N}x{K} of the {wl['M']}x{N}x{K} workload), {cores} threads"
+    return tflops, cores, kind, sample, dt * 1e3
+
+
+def run_reference_impl(args, wl_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[wl_name]
+    tflops, cores, kind, sample, ms = cpu_reference_arm(wl, seconds_target=1.5, steps=max(args.steps, 1), warmup=min(args.warmup, 2))
+    line = {"impl": "reference", "metric": "SGEMM TFLOP/s", "value": tflops, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "note": "reference CPU path on the GPU box's host cores; each step is a bounded row-slab sample"},
+            "cpu_baseline": {"value": tflops, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def k1_traffic_bytes(wl_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get(wl_name)
+    except Exception:
+        return None
+
+
+def run_single(args, wl_name):
+    import numpy as np
+
+    import ugemm_b200 as u
+    wl = WORKLOADS[wl_name]
+    M, N, K = wl["M"], wl["N"], wl["K"]
+    u.sgemm_cuda_init(0)
+    info = u.device_info()
+    dA = u.DeviceBuffer(M * K).fill_uniform(1)
+    dB = u.DeviceBuffer(K * N).fill_uniform(2)
+    dC = u.DeviceBuffer(M * N).fill_uniform(3)
+    u.sync()
+    flops = 2.0 * M * N * K
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = u.launch_count()
+    avg_ms, min_ms, total_ms = u.sgemm_cuda_time_dev("auto", args.steps, args.warmup, "R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N, total=True)
+    launches = u.launch_count() - l0 - args.warmup
+    kernel = u.last_kernel()
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    value = flops / ms_per_step / 1e9
+
+    # ---- e2e: the drop-in host-pointer call on pinned host buffers (H2D + kernel + D2H inside the timed region)
+    import ctypes as C
+    L = u.lib()
+    hA, hB, hC = (L.ugemm_cuda_malloc_host(n * 4) for n in (M * K, K * N, M * N))
+    if not (hA and hB and hC):
+        u.check()
+    L.ugemm_cuda_memcpy_d2h(hA, C.c_void_p(dA.ptr), M * K * 4)
+    L.ugemm_cuda_memcpy_d2h(hB, C.c_void_p(dB.ptr), K * N * 4)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(min(args.warmup, 2)):
+        u.sgemm_cuda("R", "N", "N", M, N, K, 1.0, hA, K, hB, N, 0.0, hC, N)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        u.sgemm_cuda("R", "N", "N", M, N, K, 1.0, hA, K, hB, N, 0.0, hC, N)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    # cheap integrity check of the e2e result against the device-resident run (same inputs, same kernel)
+    res_host = np.ctypeslib.as_array(C.cast(hC, C.POINTER(C.c_float)), shape=(M * N,))
+    res_dev = dC.download(4096)
+    assert np.array_equal(res_host[:4096], res_dev), "e2e result differs from device-resident result"
+    for h in (hA, hB, hC):
+        L.ugemm_cuda_free_host(h)
+
+    peaks = measured_peaks()
+    # a kernel timed alone over a short burst of steps -> burst peak; TF32 dense = bf16 dense / 2; 3 MMAs per product
+    peak = peaks["bf16_burst"] / 6.0
+    achieved = flops / avg_ms / 1e9
+    cpu_tf, cores, kind, sample, _ = cpu_reference_arm(wl, seconds_target=12.0)
+    line = {
+        "metric": "SGEMM TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": wl["desc"], "kernel": f"{kernel} (auto dispatch)", "device": info["name"],
+                   "l2_policy": "inputs larger than L2 (A+B+C = %.0f MB vs 126 MB L2); no flush needed" % ((M * K + K * N + M * N) * 4 / 1e6),
+                   "accuracy": "3xTF32 with fp32 promotion every 64 k: normwise relerr ~1.3e-6 vs fp64 (gate 1e-5)"},
+        "e2e": {"value": flops / e2e_ms / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": (M * K + K * N) * 4, "d2h_bytes_per_step": M * N * 4,
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "sgemm_cuda(host pointers, pinned)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": k1_traffic_bytes(wl_name),
+                     "peak_basis": f"{peaks['source']} bf16 dense burst {peaks['bf16_burst']:.1f} TFLOP/s / 2 (TF32) / 3 (3xTF32)",
+                     "kernel_ms_avg": avg_ms, "kernel_ms_min": min_ms,
+                     "nominal_frac": achieved / 375.0},
+        "cpu_baseline": {"value": cpu_tf, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_multi(args, wl_name):
+    import torch
+    import torch.distributed as dist
+
+    import ugemm_b200 as u
+    from ugemm_b200.dist import CudaOps, ShardedGemm, SlabPlan
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    u.sgemm_cuda_init(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = WORKLOADS[wl_name]
+    M, N, K = wl["M"], wl["N"], wl["K"]
+    plan = SlabPlan(world, rank, M, N, K)
+    sg = ShardedGemm(plan, CudaOps("auto"), dist)
+    sg.generate_owned(seed_a=1, seed_b=2)
+    flops = 2.0 * M * N * K
+
+    def timed(distribute, steps, warmup):
+        for _ in range(warmup):
+            sg.run(distribute)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            sg.run(distribute)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = u.launch_count()
+    ms = timed(True, args.steps, args.warmup)
+    launches = u.launch_count() - l0 - args.warmup * plan.L
+    clocks = sampler.stop() if sampler else None
+    ms_compute = timed(False, max(2, args.steps // 2), 1)
+
+    # ---- e2e: owned slabs come from pinned host memory every step, the C block goes back to pinned host memory
+    own_a = [t for t in range(plan.L) if plan.a_owner(t) == rank]
+    own_b = [t for t in range(plan.L) if plan.b_owner(t) == rank]
+    h_a = [sg.a[t].to("cpu").pin_memory() for t in own_a]
+    h_b = [sg.b[t].to("cpu").pin_memory() for t in own_b]
+    h_c = torch.empty(plan.mloc * plan.nloc, dtype=torch.float32).pin_memory()
+    h2d = sum(x.numel() for x in h_a + h_b) * 4
+    d2h = h_c.numel() * 4
+
+    def e2e_step():
+        for t, h in zip(own_a, h_a):
+            sg.a[t].copy_(h, non_blocking=True)
+        for t, h in zip(own_b, h_b):
+            sg.b[t].copy_(h, non_blocking=True)
+        sg.run(True)
+        h_c.copy_(sg.c, non_blocking=True)
+
+    e2e_step()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e2e_steps = max(2, min(args.steps, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1), float(h2d), float(d2h)], device="cuda")
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    e2e_ms = float(tmax[0].item()) / e2e_steps
+
+    if rank == 0:
+        peaks = measured_peaks()
+        peak = peaks["bf16_burst"] / 6.0 * world
+        line = {
+            "metric": "SGEMM TFLOP/s", "value": flops / ms / 1e9, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "grid": f"{plan.pr}x{plan.pc}", "k_slabs": plan.L,
+                       "timed_region": "owner-rooted NCCL panel broadcast + local GEMMs (distribution included), max over ranks",
+                       "compute_only_tflops": flops / ms_compute / 1e9, "compute_only_ms": ms_compute,
+                       "recv_bytes_per_rank": plan.recv_bytes(),
+                       "l2_policy": "inputs larger than L2 (per-GPU panels %.1f GB)" % ((plan.mloc * K + K * plan.nloc) * 4 / 1e9)},
+            "e2e": {"value": flops / e2e_ms / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": int(tsum[1].item()),
+                    "d2h_bytes_per_step": int(tsum[2].item()), "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "api": "ShardedGemm.run with owned slabs uploaded from pinned host memory and the C block downloaded each step"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": flops / ms_compute / 1e9, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / ms_compute / 1e9 / peak, "traffic": None,
+                         "peak_basis": f"{world} x {peaks['source']} bf16 dense burst {peaks['bf16_burst']:.1f} / 6; achieved = compute-only (panels resident)"},
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None] + list(WORKLOADS))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl_name = args.workload or ("c2" if max(args.gpus, world) == 1 else "c5")
+    if args.impl == "reference":
+        return run_reference_impl(args, wl_name)
+    if world > 1:
+        return run_multi(args, wl_name)
+    if args.gpus > 1:
+        sys.exit("for --gpus N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                 "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    run_single(args, wl_name)
+
+
+if __name__ == "__main__":
+    main()

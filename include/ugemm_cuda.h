@@ -72,12 +72,13 @@ int sgemm_cuda_dev(int mode, void *stream, char major, char transA, char transB,
 int sgemm_cuda_k1_eligible(char major, char transA, char transB, int M, int N, int K,
                            const float *dA, int lda, const float *dB, int ldb, const float *dC, int ldc);
 
-/* Time `iters` back-to-back launches (after `warmup` untimed ones) with CUDA events on the backend's
- * stream.  ms_avg / ms_min may be NULL.  Returns 0 on success. */
+/* Time `iters` back-to-back launches (after `warmup` untimed ones) with CUDA events on the backend's stream:
+ * one event pair per launch, all enqueued without host synchronisation in between.  *ms_avg / *ms_min = mean /
+ * best single-launch duration, *ms_total = first start to last end (any may be NULL).  Returns 0 on success. */
 int sgemm_cuda_time_dev(int mode, int iters, int warmup, char major, char transA, char transB,
                         int M, int N, int K, float alpha, const float *dA, int lda,
                         const float *dB, int ldb, float beta, float *dC, int ldc,
-                        float *ms_avg, float *ms_min);
+                        float *ms_avg, float *ms_min, float *ms_total);
 
 /* ---- errors: entry points stay void like the reference's; failures are sticky and queryable
  * (the reference only printf()s, ocl.h:92,235-239).  NULL when no error is pending. */
@@ -109,6 +110,15 @@ int   ugemm_cuda_sync(void);
  * Plays the role of random_matrix (check_sgemm.c:47-54) with an explicit seed. */
 void ugemm_fill_uniform_host(float *x, size_t n, uint64_t seed, float lo, float hi);
 int  ugemm_fill_uniform_dev(float *dx, size_t n, uint64_t seed, float lo, float hi, void *stream);
+
+/* 2-D window variants: dst[r*ld + c] = element (offset + r*gld + c) of stream `seed`, i.e. the rows x cols window
+ * starting at flat index `offset` of a row-major matrix with leading dimension gld.  Lets every GPU of the sharded
+ * driver generate exactly its own panel of one global synthetic matrix, and lets the host regenerate any slab of
+ * it for verification. */
+void ugemm_fill_uniform_host_2d(float *x, size_t rows, size_t cols, size_t ld, uint64_t seed, uint64_t offset,
+                                uint64_t gld, float lo, float hi);
+int  ugemm_fill_uniform_dev_2d(float *dx, size_t rows, size_t cols, size_t ld, uint64_t seed, uint64_t offset,
+                               uint64_t gld, float lo, float hi, void *stream);
 
 /* ---- hardware probe used by tests/DESIGN.md: runs one 128 x 16 x (8*ksteps) TF32 tcgen05 product
  * chain on raw fp32 bit patterns and returns the 128x16 fp32 accumulator, so the rounding behaviour of

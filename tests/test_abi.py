@@ -1,0 +1,75 @@
+"""CPU suite: the C-ABI library loads, exports every symbol include/ugemm_cuda.h declares, and fails loudly
+(never falls back) when no GPU is present.  No compute calls here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ugemm_cuda.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b((?:sgemm_cuda|ugemm_cuda|ugemm_fill)\w*)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_header_declares_the_expected_boundary():
+    syms = declared_symbols()
+    for must in ("sgemm_cuda_init", "sgemm_cuda_finish", "sgemm_cuda", "sgemm_cuda_3xtf32", "sgemm_cuda_simt",
+                 "sgemm_cuda_dev", "sgemm_cuda_last_error", "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    import ugemm_b200 as u
+    L = u.lib()
+    for name in declared_symbols():
+        assert hasattr(L, name), f"{name} declared in include/ugemm_cuda.h but not exported"
+    from ugemm_b200.backend import EXPORTED_SYMBOLS
+    assert sorted(EXPORTED_SYMBOLS) == declared_symbols()
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    """The boundary must be consumable from the reference's own language (C, gcc)."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "ugemm_cuda.h"\n'
+                   "typedef void (*uut_t)(char, char, char, int, int, int, float, const float*, int, const float*, int, float, float*, int);\n"
+                   "int main(void){ uut_t f = sgemm_cuda; uut_t g = sgemm_cuda_3xtf32; uut_t h = sgemm_cuda_simt; return !(f && g && h); }\n")
+    subprocess.check_call(["gcc", "-std=gnu99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import ugemm_b200 as u
+    L = u.lib()
+    if L.sgemm_cuda_init(-1, 0) == 0:
+        pytest.skip("a GPU is present; the no-GPU path cannot be exercised here")
+    L.sgemm_cuda_clear_error()
+    A = np.ones(4, np.float32)
+    Cm = np.full(4, 7.0, np.float32)
+    with pytest.raises(u.UgemmCudaError):
+        u.sgemm_cuda("R", "N", "N", 2, 2, 2, 1.0, A, 2, A, 2, 0.0, Cm, 2)
+    assert np.array_equal(Cm, np.full(4, 7.0, np.float32)), "C must be untouched when the CUDA path is unavailable"
+    with pytest.raises(u.UgemmCudaError):
+        u.sgemm_cuda_simt("R", "N", "N", 2, 2, 2, 1.0, A, 2, A, 2, 0.0, Cm, 2)
+
+
+def test_product_never_references_the_oracle():
+    """Nothing under ugemm_b200/ or include/ may import, link or mention oracle/ (checker isolation)."""
+    bad = []
+    for base in ("ugemm_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"oracle|_ref/|libugemm_ref", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+    out = subprocess.run(["ldd", os.path.join(ROOT, "ugemm_b200", "libugemm_cuda.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "ugemm_ref" not in out

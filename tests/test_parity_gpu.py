@@ -1,0 +1,313 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against the oracle on identical seeded
+inputs.  Gate (north_star): normwise relative error ||C - C_ref||_F / ||C_ref||_F <= 1e-5 for both kernels;
+the a-priori bound K*u (u = 2^-24) and the probabilistic sqrt(K)*u are printed per shape.  ld padding must be
+bit-identical before/after.  Full-size BASELINE shapes are checked on sampled row slabs regenerated from the
+shared counter-based RNG (the CPU cannot recompute 8192^3 in seconds)."""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+U = 2.0 ** -24
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ugemm_golden.npz")
+
+
+def bounds(K):
+    return f"K*u={K * U:.2e} sqrt(K)*u={np.sqrt(K) * U:.2e}"
+
+
+def fn_of(u, mode):
+    return {"auto": u.sgemm_cuda, "3xtf32": u.sgemm_cuda_3xtf32, "simt": u.sgemm_cuda_simt}[mode]
+
+
+def gpu14(u, mode, maj, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    out = Cm.copy()
+    fn_of(u, mode)(maj, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, out, ldc)
+    return out
+
+
+def oracle14(maj, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc, naive=False):
+    o = O.oracle()
+    if naive:
+        return O.run14(o.oracle_sgemm_naive, maj, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc)
+    return O.run14(o.oracle_sgemm_banded, maj, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc,
+                   threads=min(8, O.oracle().oracle_max_threads()))
+
+
+def check_case(u, mode, maj, ta, tb, M, N, K, alpha, beta, pad, seed=1, lo=0.0, hi=1.0, naive=False, tol=TOL):
+    A, lda, B, ldb, Cm, ldc = O.make_problem(maj, ta, tb, M, N, K, pad=pad, seed=seed, lo=lo, hi=hi, sentinel=-77.0)
+    got = gpu14(u, mode, maj, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc)
+    want = oracle14(maj, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc, naive=naive)
+    (_, _), (_, _), (cr, cc) = O.stored_shapes(maj, ta, tb, M, N, K)
+    e = O.relerr("R", cr, cc, want, got, ldc)  # stored layout: cr lines of cc elements, pitch ldc
+    assert e <= tol, f"{mode} {maj}{ta}{tb} {M}x{N}x{K} a={alpha} b={beta} pad={pad}: relerr {e:.3e} > {tol} ({bounds(K)})"
+    if pad[2] and cr * ldc:
+        assert np.array_equal(got.reshape(cr, ldc)[:, cc:], Cm.reshape(cr, ldc)[:, cc:]), "ld padding of C was written"
+    return e
+
+
+def test_known_answer_vector(u):
+    """sgemm_test.c:186-200"""
+    A = np.array([1, 2, 3, 4, 5, 6], np.float32)
+    B = np.array([1, 2, 3, 4, 5, 6], np.float32)
+    want = np.array([9, 12, 15, 19, 26, 33, 29, 40, 51], np.float32)
+    for mode in ("auto", "simt"):
+        Cm = np.zeros(9, np.float32)
+        fn_of(u, mode)("R", "N", "N", 3, 3, 2, 1.0, A, 2, B, 3, 0.0, Cm, 3)
+        assert np.array_equal(Cm, want)
+    assert u.last_kernel() == "simt"
+    Cm = np.zeros(9, np.float32)
+    u.sgemm_rnn(3, 3, 2, 1.0, A, B, 0.0, Cm)   # macro API of sgemm_test.c:19-33
+    assert np.array_equal(Cm, want)
+
+
+def test_device_rng_matches_host_and_oracle(u):
+    for seed, lo, hi in ((1, 0.0, 1.0), (9, -0.5, 0.5)):
+        n = 1 << 20
+        d = u.DeviceBuffer(n).fill_uniform(seed, lo, hi)
+        got = d.download()
+        assert np.array_equal(got, O.fill_uniform(n, seed, lo, hi))
+        assert np.array_equal(got, u.fill_uniform_host(n, seed, lo, hi))
+        d.free()
+
+
+SMALL_DIMS = [1, 2, 3, 7, 8, 31, 33, 64, 95, 97, 129]
+
+
+@pytest.mark.parametrize("maj", ["R", "C"])
+@pytest.mark.parametrize("ta", ["N", "T"])
+@pytest.mark.parametrize("tb", ["N", "T"])
+def test_k2_small_sweep_vs_naive_oracle(u, maj, ta, tb):
+    """K2 on tiny/odd shapes, every transpose and major, tight and odd-padded ld, against the restated
+    sgemm_cpu (ugemm.h:287)."""
+    rng = np.random.default_rng(hash((maj, ta, tb)) % 2 ** 31)
+    combos = [(1.0, 0.0), (1.5, 0.5), (1.0, 1.0), (-1.0, 2.0)]
+    worst = 0.0
+    for i in range(40):
+        M, N, K = (int(rng.choice(SMALL_DIMS)) for _ in range(3))
+        alpha, beta = combos[i % len(combos)]
+        pad = (0, 0, 0) if i % 2 == 0 else (int(rng.integers(1, 6)), int(rng.integers(1, 6)), int(rng.integers(1, 6)))
+        worst = max(worst, check_case(u, "simt", maj, ta, tb, M, N, K, alpha, beta, pad, seed=i + 1, naive=True))
+    print(f"k2 small sweep {maj}{ta}{tb}: worst relerr {worst:.3e}")
+
+
+def test_quick_returns_and_alpha_zero(u):
+    M, N, K = 33, 17, 9
+    A, lda, B, ldb, Cm, ldc = O.make_problem("R", "N", "N", M, N, K, pad=(0, 0, 3), seed=4, sentinel=-5.0)
+    # alpha == 0, beta == 1: untouched (sgemm_avx256.h:410)
+    assert np.array_equal(gpu14(u, "auto", "R", "N", "N", M, N, K, 0.0, A, lda, B, ldb, 1.0, Cm, ldc), Cm)
+    # alpha == 0: C <- beta*C on the M x N region of the GIVEN major (oracle = restated sgemm_cpu)
+    for maj in ("R", "C"):
+        got = gpu14(u, "auto", maj, "N", "N", M if maj == "R" else N, N if maj == "R" else M, K, 0.0, A, max(lda, M), B, max(ldb, N), 0.5, Cm, ldc)
+        want = Cm.copy().reshape(M, ldc)
+        want[:, :N] *= np.float32(0.5)
+        assert np.array_equal(got.reshape(M, ldc), want)
+    # K == 0 behaves like alpha == 0
+    got = gpu14(u, "simt", "R", "N", "N", M, N, 0, 1.0, A, 1, B, N, 0.0, Cm, ldc)
+    want = Cm.copy().reshape(M, ldc)
+    want[:, :N] = 0
+    assert np.array_equal(got.reshape(M, ldc), want)
+    # M == 0 / N == 0
+    assert np.array_equal(gpu14(u, "auto", "R", "N", "N", 0, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc), Cm)
+
+
+def test_beta_zero_never_reads_c(u):
+    """BLAS semantics shared by sgemm_avx / sgemm_c / sgemm_sse (sgemm_avx256.h:324-330): NaN in C is overwritten."""
+    for mode, (M, N, K) in (("simt", (70, 50, 30)), ("3xtf32", (256, 256, 64))):
+        A, lda, B, ldb, Cm, ldc = O.make_problem("R", "N", "N", M, N, K, seed=5)
+        Cn = np.full_like(Cm, np.nan)
+        got = gpu14(u, mode, "R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cn, ldc)
+        want = oracle14("R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc)
+        assert not np.isnan(got).any()
+        assert O.relerr("R", M, N, want, got, ldc) <= TOL
+
+
+def test_error_behaviour(u):
+    A = np.ones(64 * 64, np.float32)
+    Cm = np.full(64 * 64, 3.0, np.float32)
+    with pytest.raises(u.UgemmCudaError):
+        u.sgemm_cuda("R", "X", "N", 8, 8, 8, 1.0, A, 8, A, 8, 0.0, Cm, 8)
+    with pytest.raises(u.UgemmCudaError):
+        u.sgemm_cuda("R", "N", "N", 8, 8, 8, 1.0, A, 4, A, 8, 0.0, Cm, 8)       # lda < K
+    with pytest.raises(u.UgemmCudaError):
+        u.sgemm_cuda_3xtf32("R", "N", "N", 32, 32, 32, 1.0, A, 33, A, 32, 0.0, Cm, 32)   # lda % 4 != 0: no silent fallback
+    assert np.all(Cm == 3.0)
+    assert u.last_error() is None
+    # lower-case letters are accepted
+    u.sgemm_cuda("r", "n", "t", 8, 8, 8, 1.0, A, 8, A, 8, 0.0, Cm, 8)
+    assert np.all(Cm[:64] == 8.0)
+
+
+K1_SHAPES = [(128, 128, 32), (256, 256, 64), (256, 512, 96), (384, 640, 200), (300, 200, 100), (1023, 1000, 1023),
+             (129, 257, 33), (2048, 1024, 512)]
+
+
+@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("ta", ["N", "T"])
+@pytest.mark.parametrize("tb", ["N", "T"])
+def test_k1_all_transposes_vs_oracle(u, cg, ta, tb):
+    """K1 (3xTF32 tcgen05) on tile-multiple and ragged shapes, ld multiples of 4, alpha/beta, both CTA-group modes."""
+    u.set_k1_tuning(cta_group=cg)
+    try:
+        worst = 0.0
+        for i, (M, N, K) in enumerate(K1_SHAPES):
+            (ar, ac), (br, bc), _ = O.stored_shapes("R", ta, tb, M, N, K)
+            pa, pb, pc = (-ac) % 4, (-bc) % 4, (-N) % 4   # make every ld a multiple of 4 (TMA-eligible)
+            for (alpha, beta, extra) in ((1.0, 0.0, 0), (1.5, 0.5, 4)):
+                e = check_case(u, "3xtf32", "R", ta, tb, M, N, K, alpha, beta, (pa + extra, pb + extra, pc + extra), seed=10 + i)
+                worst = max(worst, e)
+            assert u.last_kernel() == "3xtf32"
+        print(f"k1 cg={cg} {ta}{tb}: worst relerr {worst:.3e}")
+    finally:
+        u.set_k1_tuning(cta_group=2)
+
+
+def test_k1_column_major_and_zero_mean(u):
+    for (maj, ta, tb) in (("C", "N", "N"), ("C", "T", "N"), ("C", "N", "T")):
+        check_case(u, "3xtf32", maj, ta, tb, 384, 256, 160, 1.5, 0.5, (0, 0, 0), seed=3, lo=-0.5, hi=0.5)
+
+
+def test_k1_vs_k2_agree(u):
+    M, N, K = 512, 384, 777
+    A, lda, B, ldb, Cm, ldc = O.make_problem("R", "N", "N", M, N, K + 3, seed=8)  # K+3: ld multiple of 4
+    g1 = gpu14(u, "3xtf32", "R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc)
+    g2 = gpu14(u, "simt", "R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc)
+    assert O.relerr("R", M, N, g2, g1, ldc) <= TOL
+
+
+def test_auto_dispatch_rule(u):
+    """mode=auto: K1 iff A,B 16-B aligned, lda/ldb % 4 == 0, M,N >= 128, K >= 32; otherwise K2."""
+    for (M, N, K, pad, want) in ((256, 256, 64, (0, 0, 0), "3xtf32"), (256, 256, 64, (1, 0, 0), "simt"),
+                                 (64, 256, 64, (0, 0, 0), "simt"), (256, 256, 16, (0, 0, 0), "simt")):
+        check_case(u, "auto", "R", "N", "N", M, N, K, 1.0, 0.0, pad, seed=2)
+        assert u.last_kernel() == want, (M, N, K, pad)
+
+
+def test_golden_fixtures(u):
+    """GPU result vs outputs of the unmodified reference stored in tests/golden (all four CPU implementations)."""
+    g = np.load(GOLDEN)
+    cases = [ast.literal_eval(str(c)) for c in g["cases"]]
+    for i, (maj, ta, tb, M, N, K, alpha, beta, pad, lo, hi) in enumerate(cases):
+        A, lda, B, ldb, Cm, ldc = O.make_problem(maj, ta, tb, M, N, K, pad=pad, seed=100 + i, lo=lo, hi=hi)
+        (_, _), (_, _), (cr, cc) = O.stored_shapes(maj, ta, tb, M, N, K)
+        for mode in ("simt", "auto"):
+            got = gpu14(u, mode, maj, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc)
+            for name in ("cpu", "c", "sse", "avx"):
+                if f"{name}_{i}" in g:
+                    e = O.relerr("R", cr, cc, g[f"{name}_{i}"], got, ldc)
+                    assert e <= TOL, (i, mode, name, e)
+
+
+def test_config1_1024_cube_vs_reference_avx(u):
+    """BASELINE config 1: row-major NN 1024^3 alpha=1 beta=0, oracle = sgemm_avx (live _ref when shipped,
+    else the bit-identical 35-band restatement).  The reference's own cmp_results line is printed too."""
+    M = N = K = 1024
+    A, lda, B, ldb, Cm, ldc = O.make_problem("R", "N", "N", M, N, K, seed=1)
+    r = O.ref()
+    if r is not None:
+        want = O.run14(r.ref_sgemm_avx, "R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc)
+    else:
+        want = oracle14("R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc)
+    for mode in ("3xtf32", "simt"):
+        got = gpu14(u, mode, "R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc)
+        e = O.relerr("R", M, N, want, got, ldc)
+        out = np.zeros(4)
+        verdict = O.oracle().oracle_cmp_results(M, N, want, got, ldc, out)
+        print(f"c1 {mode}: relerr {e:.3e} ({bounds(K)}); cmp_results stdErr/stdRef={out[0] / out[1]:.3e} maxErr={out[2]:.3e} verdict={verdict}")
+        assert e <= TOL
+
+
+@pytest.mark.parametrize("ta,tb", [("N", "T"), ("T", "N"), ("T", "T"), ("N", "N")])
+def test_config3_ragged_transposed(u, ta, tb):
+    """BASELINE config 3: 4095 x 3001 x 2047, alpha=1.5 beta=0.5, (i) ld padded to multiples of 4 -> K1,
+    (ii) odd padding -> K2; padding untouched.  Oracle: reference sgemm_sse when _ref ships, else 35-band."""
+    M, N, K = 4095, 3001, 2047
+    r = O.ref()
+    (ar, ac), (br, bc), _ = O.stored_shapes("R", ta, tb, M, N, K)
+    for label, pad, want_kernel in (("ld%4==0", ((-ac) % 4, (-bc) % 4, (-N) % 4), "3xtf32"), ("odd ld", (5, 3, 7), "simt")):
+        A, lda, B, ldb, Cm, ldc = O.make_problem("R", ta, tb, M, N, K, pad=pad, seed=33, sentinel=-9.0)
+        if r is not None:
+            want = O.run14(r.ref_sgemm_sse, "R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+        else:
+            want = oracle14("R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+        got = gpu14(u, "auto", "R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+        assert u.last_kernel() == want_kernel
+        e = O.relerr("R", M, N, want, got, ldc)
+        print(f"c3 {ta}{tb} {label} -> {want_kernel}: relerr {e:.3e} ({bounds(K)})")
+        assert e <= TOL
+        assert np.array_equal(got.reshape(M, ldc)[:, N:], Cm.reshape(M, ldc)[:, N:])
+
+
+def sampled_rows_check(u, mode, M, N, K, rows, lo, hi, seedA=1, seedB=2):
+    """Full-size NN problem generated ON THE DEVICE from the shared RNG; the oracle recomputes only `rows`."""
+    dA = u.DeviceBuffer(M * K).fill_uniform(seedA, lo, hi)
+    dB = u.DeviceBuffer(K * N).fill_uniform(seedB, lo, hi)
+    dC = u.DeviceBuffer(M * N)
+    u.sgemm_cuda_dev(mode, None, "R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N)
+    u.sync()
+    B = O.fill_uniform(K * N, seedB, lo, hi)
+    worst = 0.0
+    for r0, nr in rows:
+        full = O.fill_uniform((r0 + nr) * K, seedA, lo, hi) if (r0 + nr) * K <= (1 << 27) else None
+        if full is not None:
+            A = full[r0 * K:(r0 + nr) * K].copy()
+        else:  # regenerate just the slab: element i of the stream is independent of the others
+            import ugemm_b200 as mod
+            tmp = mod.DeviceBuffer(nr * K)
+            # stream offset: fill with the same seed but shifted base is not exposed; download from dA instead
+            A = dA.download(nr * K, offset=r0 * K)
+            tmp.free()
+        C0 = np.zeros(nr * N, np.float32)
+        want = oracle14("R", "N", "N", nr, N, K, 1.0, A, K, B, N, 0.0, C0, N)
+        got = dC.download(nr * N, offset=r0 * N)
+        worst = max(worst, O.relerr("R", nr, N, want, got, N))
+    for d in (dA, dB, dC):
+        d.free()
+    return worst
+
+
+@pytest.mark.parametrize("lo,hi", [(0.0, 1.0), (-0.5, 0.5)])
+def test_config2_8192_cube_sampled(u, lo, hi):
+    """BASELINE config 2 (8192^3 NN): sampled 16-row slabs vs the oracle, both input distributions, both kernels."""
+    M = N = K = 8192
+    rows = [(0, 16), (4095, 16), (8176, 16)]
+    for mode in ("3xtf32", "simt"):
+        e = sampled_rows_check(u, mode, M, N, K, rows, lo, hi)
+        print(f"c2 {mode} U[{lo},{hi}): sampled relerr {e:.3e} ({bounds(K)})")
+        assert e <= TOL
+
+
+def test_config4_tall_skinny_sampled(u):
+    """BASELINE config 4: im2col-shaped 200704 x 256 x 1152 NN."""
+    M, N, K = 200704, 256, 1152
+    rows = [(0, 64), (100000, 64), (200640, 64)]
+    for mode in ("3xtf32", "simt"):
+        e = sampled_rows_check(u, mode, M, N, K, rows, 0.0, 1.0)
+        print(f"c4 {mode}: sampled relerr {e:.3e} ({bounds(K)})")
+        assert e <= TOL
+
+
+def test_full_size_linearity_property(u):
+    """Size-independent property at 4096^3: GEMM(A, B1 + B2) == GEMM(A, B1) + GEMM(A, B2) (beta=1 accumulate path)."""
+    M = N = K = 4096
+    dA = u.DeviceBuffer(M * K).fill_uniform(1, -0.5, 0.5)
+    b1 = u.fill_uniform_host(K * N, 2, -0.5, 0.5)
+    b2 = u.fill_uniform_host(K * N, 3, -0.5, 0.5)
+    dB1, dB2, dB12 = u.DeviceBuffer(K * N).upload(b1), u.DeviceBuffer(K * N).upload(b2), u.DeviceBuffer(K * N).upload(b1 + b2)
+    dC, dD = u.DeviceBuffer(M * N), u.DeviceBuffer(M * N)
+    u.sgemm_cuda_dev("3xtf32", None, "R", "N", "N", M, N, K, 1.0, dA, K, dB1, N, 0.0, dC, N)
+    u.sgemm_cuda_dev("3xtf32", None, "R", "N", "N", M, N, K, 1.0, dA, K, dB2, N, 1.0, dC, N)
+    u.sgemm_cuda_dev("3xtf32", None, "R", "N", "N", M, N, K, 1.0, dA, K, dB12, N, 0.0, dD, N)
+    u.sync()
+    c, d = dC.download(), dD.download()
+    e = O.relerr("R", M, N, d, c, N)
+    print(f"linearity 4096^3: {e:.3e}")
+    assert e <= TOL
+    for x in (dA, dB1, dB2, dB12, dC, dD):
+        x.free()

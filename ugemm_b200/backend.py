@@ -62,7 +62,7 @@ def lib():
     L.sgemm_cuda_k1_eligible.argtypes = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.sgemm_cuda_k1_eligible.restype = C.c_int
-    L.sgemm_cuda_time_dev.argtypes = [C.c_int, C.c_int, C.c_int] + sig14 + [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.sgemm_cuda_time_dev.argtypes = [C.c_int, C.c_int, C.c_int] + sig14 + [C.POINTER(C.c_float)] * 3
     L.sgemm_cuda_time_dev.restype = C.c_int
     L.sgemm_cuda_last_error.restype = C.c_char_p
     L.sgemm_cuda_clear_error.restype = None
@@ -87,6 +87,12 @@ def lib():
     L.ugemm_fill_uniform_host.restype = None
     L.ugemm_fill_uniform_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_float, C.c_float, C.c_void_p]
     L.ugemm_fill_uniform_dev.restype = C.c_int
+    L.ugemm_fill_uniform_host_2d.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, C.c_uint64,
+                                             C.c_uint64, C.c_float, C.c_float]
+    L.ugemm_fill_uniform_host_2d.restype = None
+    L.ugemm_fill_uniform_dev_2d.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, C.c_uint64,
+                                            C.c_uint64, C.c_float, C.c_float, C.c_void_p]
+    L.ugemm_fill_uniform_dev_2d.restype = C.c_int
     L.ugemm_cuda_probe_tf32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.ugemm_cuda_probe_tf32.restype = C.c_int
     _lib = L
@@ -99,7 +105,8 @@ EXPORTED_SYMBOLS = [
     "sgemm_cuda_clear_error", "sgemm_cuda_last_kernel", "sgemm_cuda_launch_count", "ugemm_cuda_device_info",
     "sgemm_cuda_set_k1_tuning", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
     "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
-    "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_cuda_probe_tf32",
+    "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
+    "ugemm_cuda_probe_tf32",
 ]
 
 
@@ -156,15 +163,15 @@ def sgemm_cuda_dev(mode, stream, major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb
         raise UgemmCudaError("sgemm_cuda_dev failed")
 
 
-def sgemm_cuda_time_dev(mode, iters, warmup, major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc):
-    """(avg_ms, min_ms) of `iters` launches timed with CUDA events on the backend stream."""
-    avg, best = C.c_float(0), C.c_float(0)
+def sgemm_cuda_time_dev(mode, iters, warmup, major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, total=False):
+    """(avg_ms, min_ms[, total_ms]) of `iters` back-to-back launches timed with CUDA events on the backend stream."""
+    avg, best, span = C.c_float(0), C.c_float(0), C.c_float(0)
     rc = lib().sgemm_cuda_time_dev(_MODES[mode], iters, warmup, _b(major), _b(ta), _b(tb), M, N, K, alpha,
-                                   _ptr(dA), lda, _ptr(dB), ldb, beta, _ptr(dC), ldc, C.byref(avg), C.byref(best))
+                                   _ptr(dA), lda, _ptr(dB), ldb, beta, _ptr(dC), ldc, C.byref(avg), C.byref(best), C.byref(span))
     if rc:
         check()
         raise UgemmCudaError("sgemm_cuda_time_dev failed")
-    return avg.value, best.value
+    return (avg.value, best.value, span.value) if total else (avg.value, best.value)
 
 
 def k1_eligible(major, ta, tb, M, N, K, dA, lda, dB, ldb, dC, ldc):
@@ -240,6 +247,19 @@ def fill_uniform_host(n, seed, lo=0.0, hi=1.0):
     x = np.empty(int(n), dtype=np.float32)
     lib().ugemm_fill_uniform_host(_ptr(x), x.size, seed, lo, hi)
     return x
+
+
+def fill_uniform_host_2d(rows, cols, seed, offset, gld, lo=0.0, hi=1.0, ld=None, out=None):
+    """rows x cols window (pitch ld) of stream `seed` starting at flat index `offset` of a matrix with pitch gld."""
+    ld = cols if ld is None else ld
+    x = np.empty(int(rows) * int(ld), dtype=np.float32) if out is None else out
+    lib().ugemm_fill_uniform_host_2d(_ptr(x), rows, cols, ld, seed, offset, gld, lo, hi)
+    return x
+
+
+def fill_uniform_dev_2d(dptr, rows, cols, ld, seed, offset, gld, lo=0.0, hi=1.0, stream=None):
+    if lib().ugemm_fill_uniform_dev_2d(_ptr(dptr), rows, cols, ld, seed, offset, gld, lo, hi, C.c_void_p(stream or 0)):
+        check()
 
 
 def sync():

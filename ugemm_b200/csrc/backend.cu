@@ -30,7 +30,7 @@ struct State {
 	// staging arena of the host-pointer entry points (one buffer like the OpenCL backend's `gm`)
 	char *arena = nullptr;
 	size_t arena_bytes = 0;
-	K1Tuning tuning = {0, 0, 2};
+	K1Tuning tuning = {2, 0, 2};   // promote every 2 k-blocks (64 k), truncation split, 2-CTA pairs
 	int last_kernel = 0;
 	unsigned long long launches = 0;
 } g;
@@ -201,6 +201,19 @@ __global__ void fill_uniform_kernel(float *x, size_t n, unsigned long long base,
 	for (; i < n; i += stride) x[i] = uniform_at(base, i, lo, span);
 }
 
+// dst[r*ld + c] = stream element (offset + r*gld + c): a window of a larger row-major matrix
+__global__ void fill_uniform_2d_kernel(float *x, long long rows, long long cols, long long ld, unsigned long long base,
+                                       unsigned long long offset, unsigned long long gld, float lo, float span)
+{
+	const long long total = rows * cols;
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (; i < total; i += stride) {
+		const long long r = i / cols, c = i - r * cols;
+		x[r * ld + c] = uniform_at(base, offset + (unsigned long long)r * gld + (unsigned long long)c, lo, span);
+	}
+}
+
 } // namespace
 
 extern "C" {
@@ -283,34 +296,52 @@ int sgemm_cuda_k1_eligible(char major, char ta, char tb, int M, int N, int K, co
 
 int sgemm_cuda_time_dev(int mode, int iters, int warmup, char major, char ta, char tb, int M, int N, int K,
                         float alpha, const float *dA, int lda, const float *dB, int ldb, float beta, float *dC,
-                        int ldc, float *ms_avg, float *ms_min)
+                        int ldc, float *ms_avg, float *ms_min, float *ms_total)
 {
 	if (ensure_init()) return 1;
 	if (iters < 1) iters = 1;
+	if (iters > 4096) iters = 4096;
 	Problem p;
 	if (normalise(major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, &p)) return 1;
 	for (int i = 0; i < warmup; i++)
 		if (run_dev(mode, g.stream, p)) return 1;
-	cudaEvent_t e0, e1;
-	CU_TRY(cudaEventCreate(&e0), "cudaEventCreate");
-	CU_TRY(cudaEventCreate(&e1), "cudaEventCreate");
-	float total = 0.f, best = 1e30f;
-	int rc = 0;
+	CU_TRY(cudaStreamSynchronize(g.stream), "warm-up sync");
+	// one event pair per launch, all enqueued back to back (no host sync in between): per-launch durations
+	// AND the whole-region time come from the same run
+	cudaEvent_t *ev = (cudaEvent_t *)malloc(sizeof(cudaEvent_t) * 2 * (size_t)iters);
+	if (!ev) { set_error("out of host memory"); return 1; }
+	int made = 0, rc = 0;
+	for (; made < 2 * iters; made++)
+		if (cudaEventCreate(&ev[made]) != cudaSuccess) { set_error("cudaEventCreate failed"); rc = 1; break; }
 	for (int i = 0; i < iters && !rc; i++) {
-		cudaEventRecord(e0, g.stream);
+		cudaEventRecord(ev[2 * i], g.stream);
 		rc = run_dev(mode, g.stream, p);
-		cudaEventRecord(e1, g.stream);
-		cudaError_t e = cudaEventSynchronize(e1);
-		if (e != cudaSuccess) { set_error("timed launch failed: %s", cudaGetErrorString(e)); rc = 1; break; }
-		float ms = 0.f;
-		cudaEventElapsedTime(&ms, e0, e1);
-		total += ms;
-		if (ms < best) best = ms;
+		cudaEventRecord(ev[2 * i + 1], g.stream);
 	}
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
-	if (ms_avg) *ms_avg = total / iters;
-	if (ms_min) *ms_min = best;
+	if (!rc) {
+		cudaError_t e = cudaStreamSynchronize(g.stream);
+		if (e != cudaSuccess) {
+			const unsigned *dg = k1_diag_host();
+			if (dg && dg[0]) set_error("timed launch failed: %s (K1 watchdog code %u, block %u, thread %u)", cudaGetErrorString(e), dg[0], dg[1], dg[2]);
+			else set_error("timed launch failed: %s", cudaGetErrorString(e));
+			rc = 1;
+		}
+	}
+	if (!rc) {
+		float total = 0.f, best = 1e30f, span = 0.f;
+		for (int i = 0; i < iters; i++) {
+			float ms = 0.f;
+			cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+			total += ms;
+			if (ms < best) best = ms;
+		}
+		cudaEventElapsedTime(&span, ev[0], ev[2 * iters - 1]);
+		if (ms_avg) *ms_avg = total / iters;
+		if (ms_min) *ms_min = best;
+		if (ms_total) *ms_total = span;
+	}
+	for (int i = 0; i < made; i++) cudaEventDestroy(ev[i]);
+	free(ev);
 	return rc;
 }
 
@@ -399,6 +430,31 @@ int ugemm_fill_uniform_dev(float *dx, size_t n, uint64_t seed, float lo, float h
 	if (blocks > cap) blocks = cap;
 	fill_uniform_kernel<<<(unsigned)blocks, 256, 0, s>>>(dx, n, seed * 0x9E3779B97F4A7C15ull, lo, hi - lo);
 	CU_TRY(cudaGetLastError(), "fill_uniform launch");
+	g.launches++;
+	return 0;
+}
+
+void ugemm_fill_uniform_host_2d(float *x, size_t rows, size_t cols, size_t ld, uint64_t seed, uint64_t offset,
+                                uint64_t gld, float lo, float hi)
+{
+	const unsigned long long base = seed * 0x9E3779B97F4A7C15ull;
+	const float span = hi - lo;
+	for (size_t r = 0; r < rows; r++)
+		for (size_t c = 0; c < cols; c++) x[r * ld + c] = uniform_at(base, offset + r * gld + c, lo, span);
+}
+
+int ugemm_fill_uniform_dev_2d(float *dx, size_t rows, size_t cols, size_t ld, uint64_t seed, uint64_t offset,
+                              uint64_t gld, float lo, float hi, void *stream)
+{
+	if (ensure_init()) return 1;
+	if (rows == 0 || cols == 0) return 0;
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+	size_t blocks = (rows * cols + 255) / 256;
+	const size_t cap = (size_t)g.sm_count * 32;
+	if (blocks > cap) blocks = cap;
+	fill_uniform_2d_kernel<<<(unsigned)blocks, 256, 0, s>>>(dx, (long long)rows, (long long)cols, (long long)ld,
+	                                                        seed * 0x9E3779B97F4A7C15ull, offset, gld, lo, hi - lo);
+	CU_TRY(cudaGetLastError(), "fill_uniform_2d launch");
 	g.launches++;
 	return 0;
 }
