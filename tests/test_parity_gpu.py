@@ -230,7 +230,9 @@ def test_config3_ragged_transposed(u, ta, tb):
     M, N, K = 4095, 3001, 2047
     r = O.ref()
     (ar, ac), (br, bc), _ = O.stored_shapes("R", ta, tb, M, N, K)
-    for label, pad, want_kernel in (("ld%4==0", ((-ac) % 4, (-bc) % 4, (-N) % 4), "3xtf32"), ("odd ld", (5, 3, 7), "simt")):
+    odd = lambda w, p: p if (w + p) % 4 else p + 1   # a pad that leaves the leading dimension NOT a multiple of 4
+    for label, pad, want_kernel in (("ld%4==0", ((-ac) % 4, (-bc) % 4, (-N) % 4), "3xtf32"),
+                                    ("odd ld", (odd(ac, 5), odd(bc, 3), odd(N, 7)), "simt")):
         A, lda, B, ldb, Cm, ldc = O.make_problem("R", ta, tb, M, N, K, pad=pad, seed=33, sentinel=-9.0)
         if r is not None:
             want = O.run14(r.ref_sgemm_sse, "R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
