@@ -30,7 +30,7 @@ struct State {
 	// staging arena of the host-pointer entry points (one buffer like the OpenCL backend's `gm`)
 	char *arena = nullptr;
 	size_t arena_bytes = 0;
-	K1Tuning tuning = {2, 0, 2};   // promote every 2 k-blocks (64 k), truncation split, 2-CTA pairs
+	K1Tuning tuning = {4, 0, 2, 0};   // promote every 4 k-blocks (128 k), truncation split, 2-CTA pairs
 	int last_kernel = 0;
 	unsigned long long launches = 0;
 } g;
@@ -244,6 +244,7 @@ int sgemm_cuda_init(int device, size_t arena_bytes)
 	strncpy(g.name, prop.name, sizeof g.name - 1);
 	CU_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate");
 	CU_TRY(cudaStreamCreateWithFlags(&g.stream_d2h, cudaStreamNonBlocking), "cudaStreamCreate");
+	if (const char *f = getenv("UGEMM_K1_FLAGS")) g.tuning.flags = atoi(f);   // debug / ablation, see common.cuh
 	g.ready = true;
 	if (arena_bytes && ensure_arena(arena_bytes)) { g.ready = false; return 1; }
 	return 0;

@@ -17,7 +17,11 @@ struct Problem {
 	float *C; long long ldc;
 };
 
-struct K1Tuning { int kc_blocks; int split; int cta_group; };
+// flags: bit0 = share one shared-memory read of A_big between big*small and big*big (A collector);
+// bits 1-4 are ABLATION switches for bottleneck analysis only (results are wrong with them):
+// 2 transform skips its stores, 4 transform skips loads and stores, 8 only big*big is issued, 16 epilogue skips stores,
+// 32 per-role cycle counters to stderr, 64 MMA free-run (no TMA / transform / stage barriers: raw tensor-pipe ceiling).
+struct K1Tuning { int kc_blocks; int split; int cta_group; int flags; };
 
 // K2: register-blocked FFMA kernel (k2_simt.cu)
 cudaError_t launch_k2_simt(const Problem &p, cudaStream_t stream, int sm_count);

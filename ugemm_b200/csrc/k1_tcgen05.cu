@@ -51,8 +51,9 @@ struct K1Params {
 	long long ldc;
 	int a_kmajor, b_kmajor;
 	int tiles_m, tiles_n, num_tiles;
-	int num_k_blocks, kc_blocks, split, vecC;
+	int num_k_blocks, kc_blocks, split, vecC, flags;
 	unsigned *diag;
+	long long *prof;   // flags & 32: per-role cycle counters of the first 4 CTAs (16 slots each), debug only
 };
 
 __device__ __forceinline__ void watchdog_fail(unsigned *diag, int code, uint32_t parity)
@@ -128,6 +129,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 	const int num_clusters = (CG == 2) ? (int)num_clusters_x() : (int)gridDim.x;
 	const int nkb = P.num_k_blocks;
 	const int kc = P.kc_blocks;
+	long long *prof = (P.prof && blockIdx.x < 4) ? P.prof + 16 * blockIdx.x : nullptr;
 
 	// ---- one-time setup --------------------------------------------------------------------------------
 	if (warp == 0 && lane == 0) {
@@ -159,7 +161,8 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		if (warp == 0 && lane == 0) {
 			// ================= TMA producer =================
 			int it = 0;
-			for (int tile = cluster_id; tile < P.num_tiles; tile += num_clusters) {
+			long long w_empty = 0; const long long t_begin = clock64();
+			for (int tile = cluster_id; tile < P.num_tiles && !(P.flags & 64); tile += num_clusters) {
 				int tm, tn;
 				decode_tile(tile, P.tiles_m, P.tiles_n, tm, tn);
 				const int a_row0 = tm * UMMA_M + (int)cta_rank * ROWS;
@@ -167,7 +170,9 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				for (int kb = 0; kb < nkb; kb++, it++) {
 					const int s = it % STAGES;
 					const uint32_t ph = (it / STAGES) & 1;
+					const long long tw = clock64();
 					mbar_wait(empty_bar(s), ph ^ 1u, P.diag, 1);
+					w_empty += clock64() - tw;
 					mbar_arrive_expect_tx(full_bar(s), RAW_BYTES);
 					const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + OPER_BYTES;
 					const int k0 = kb * BK;
@@ -179,6 +184,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 						for (int j = 0; j < ROWS / 32; j++) tma_load_2d(sB + j * 4096, &tmB, full_bar(s), b_row0 + 32 * j, k0);
 				}
 			}
+			if (prof) { prof[0] = w_empty; prof[1] = clock64() - t_begin; }
 		} else if (warp == 1 && lane == 0 && cta_rank == 0) {
 			// ================= MMA issuer (leader CTA) =================
 			const uint32_t idesc = idesc_tf32(UMMA_M, BN, P.a_kmajor ? 0 : 1, P.b_kmajor ? 0 : 1);
@@ -189,20 +195,27 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			const uint32_t b_lbo = P.b_kmajor ? 1u : 256u, b_sbo = P.b_kmajor ? 64u : 32u, b_lay = P.b_kmajor ? 2u : 1u;
 			const uint32_t a_kstep = P.a_kmajor ? 32u : 1024u, b_kstep = P.b_kmajor ? 32u : 1024u;
 			int it = 0, ci = 0;
+			long long w_xf = 0, w_te = 0; const long long t_begin = clock64();
 			for (int tile = cluster_id; tile < P.num_tiles; tile += num_clusters) {
 				for (int kb0 = 0; kb0 < nkb; kb0 += kc, ci++) {
 					const int acc = ci & 1;
 					const uint32_t aph = (ci >> 1) & 1;
+					long long tw = clock64();
 					if (CG == 2) mbar_wait_cluster(tempty_bar(acc), aph ^ 1u, P.diag, 2);
 					else mbar_wait(tempty_bar(acc), aph ^ 1u, P.diag, 2);
+					w_te += clock64() - tw;
 					tc_fence_after();
 					const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
 					const int kb1 = min(kb0 + kc, nkb);
 					for (int kb = kb0; kb < kb1; kb++, it++) {
 						const int s = it % STAGES;
 						const uint32_t ph = (it / STAGES) & 1;
-						if (CG == 2) mbar_wait_cluster(xf_bar(s), ph, P.diag, 3);
-						else mbar_wait(xf_bar(s), ph, P.diag, 3);
+						tw = clock64();
+						if (!(P.flags & 64)) {
+							if (CG == 2) mbar_wait_cluster(xf_bar(s), ph, P.diag, 3);
+							else mbar_wait(xf_bar(s), ph, P.diag, 3);
+						}
+						w_xf += clock64() - tw;
 						tc_fence_after();
 						const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + OPER_BYTES;
 						const uint32_t sAs = sA + RAW_BYTES, sBs = sB + RAW_BYTES;
@@ -212,15 +225,23 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 							const uint64_t dAs = smem_desc(sAs + k4 * a_kstep, a_lbo, a_sbo, a_lay);
 							const uint64_t dBb = smem_desc(sB + k4 * b_kstep, b_lbo, b_sbo, b_lay);
 							const uint64_t dBs = smem_desc(sBs + k4 * b_kstep, b_lbo, b_sbo, b_lay);
-							mma_tf32_ss<CG>(d_tmem, dAs, dBb, idesc, (kb > kb0 || k4 > 0) ? 1u : 0u);
-							mma_tf32_ss<CG>(d_tmem, dAb, dBs, idesc, 1u);
-							mma_tf32_ss<CG>(d_tmem, dAb, dBb, idesc, 1u);
+							const uint32_t first = (kb > kb0 || k4 > 0) ? 1u : 0u;
+							if (P.flags & 8) { mma_tf32_ss<CG>(d_tmem, dAb, dBb, idesc, first); continue; }
+							mma_tf32_ss<CG>(d_tmem, dAs, dBb, idesc, first);
+							if (P.flags & 1) {
+								mma_tf32_ss_coll<CG, 1>(d_tmem, dAb, dBs, idesc, 1u);
+								mma_tf32_ss_coll<CG, 2>(d_tmem, dAb, dBb, idesc, 1u);
+							} else {
+								mma_tf32_ss<CG>(d_tmem, dAb, dBs, idesc, 1u);
+								mma_tf32_ss<CG>(d_tmem, dAb, dBb, idesc, 1u);
+							}
 						}
-						mma_commit<CG>(empty_bar(s));   // stage free once these MMAs have read it
+						if (!(P.flags & 64)) mma_commit<CG>(empty_bar(s));   // stage free once these MMAs have read it
 					}
 					mma_commit<CG>(tfull_bar(acc));     // accumulator chunk complete
 				}
 			}
+			if (prof) { prof[2] = w_xf; prof[3] = w_te; prof[4] = clock64() - t_begin; }
 		}
 		__syncwarp();   // reconverge before the .aligned teardown barrier
 	} else if (warp < 8) {
@@ -228,14 +249,18 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		reg_dec<64>();
 		const int t = threadIdx.x - 128;
 		int it = 0;
-		for (int tile = cluster_id; tile < P.num_tiles; tile += num_clusters) {
+		long long w_full = 0, t_work = 0, t_fence = 0; const long long t_begin = clock64();
+		for (int tile = cluster_id; tile < P.num_tiles && !(P.flags & 64); tile += num_clusters) {
 			for (int kb = 0; kb < nkb; kb++, it++) {
 				const int s = it % STAGES;
 				const uint32_t ph = (it / STAGES) & 1;
+				const long long t0 = clock64();
 				mbar_wait(full_bar(s), ph, P.diag, 4);
+				const long long t1 = clock64();
 				const uint32_t raw = smem_base + s * STAGE_BYTES;
 #pragma unroll
 				for (int half = 0; half < 2; half++) {
+					if (P.flags & 4) break;
 					float4 v[8];
 #pragma unroll
 					for (int i = 0; i < 8; i++) v[i] = lds128(raw + (uint32_t)(t + 128 * (half * 8 + i)) * 16u);
@@ -249,18 +274,23 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 							b.x = tf32_rna(v[i].x); b.y = tf32_rna(v[i].y); b.z = tf32_rna(v[i].z); b.w = tf32_rna(v[i].w);
 						}
 						sm.x = v[i].x - b.x; sm.y = v[i].y - b.y; sm.z = v[i].z - b.z; sm.w = v[i].w - b.w;
+						if (P.flags & 2) continue;
 						sts128(raw + RAW_BYTES + off, sm);
 						if (P.split != 0) sts128(raw + off, b);
 					}
 				}
+				const long long t2 = clock64();
 				fence_proxy_async_smem();
 				__syncwarp();
 				if (lane == 0) {
 					if (CG == 2) mbar_arrive_cluster(xf_bar(s), 0);
 					else mbar_arrive(xf_bar(s));
 				}
+				const long long t3 = clock64();
+				w_full += t1 - t0; t_work += t2 - t1; t_fence += t3 - t2;
 			}
 		}
+		if (prof && t == 0) { prof[5] = w_full; prof[6] = t_work; prof[7] = t_fence; prof[8] = clock64() - t_begin; }
 	} else {
 		// ================= epilogue warps =================
 		reg_inc<200>();
@@ -269,6 +299,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		const int h = e >> 2;       // column half
 		const float alpha = P.alpha, beta = P.beta;
 		int ci = 0;
+		long long w_tf = 0, t_drain = 0, t_store = 0; const long long t_begin = clock64();
 		for (int tile = cluster_id; tile < P.num_tiles; tile += num_clusters) {
 			int tm, tn;
 			decode_tile(tile, P.tiles_m, P.tiles_n, tm, tn);
@@ -280,7 +311,9 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			for (int kb0 = 0; kb0 < nkb; kb0 += kc, ci++) {
 				const int ab = ci & 1;
 				const uint32_t aph = (ci >> 1) & 1;
+				const long long t0 = clock64();
 				mbar_wait(tfull_bar(ab), aph, P.diag, 5);
+				const long long t1 = clock64();
 				tc_fence_after();
 				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * (BN / 2));
 #pragma unroll
@@ -296,10 +329,12 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					if (CG == 2) mbar_arrive_cluster(tempty_bar(ab), 0);
 					else mbar_arrive(tempty_bar(ab));
 				}
+				w_tf += t1 - t0; t_drain += clock64() - t1;
 			}
+			const long long ts0 = clock64();
 			// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
 			const long long row = (long long)tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane;
-			if (row < P.M) {
+			if (row < P.M && !(P.flags & 16)) {
 				float *crow = P.C + row * P.ldc;
 #pragma unroll
 				for (int g = 0; g < NG; g++) {
@@ -331,7 +366,9 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					}
 				}
 			}
+			t_store += clock64() - ts0;
 		}
+		if (prof && threadIdx.x == 256) { prof[9] = w_tf; prof[10] = t_drain; prof[11] = t_store; prof[12] = clock64() - t_begin; }
 	}
 
 	// ---- teardown: everyone (both CTAs of a pair) done before TMEM is returned ------------------------------
@@ -459,8 +496,16 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	P.num_k_blocks = (p.K + BK - 1) / BK;
 	P.kc_blocks = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
 	P.split = t.split;
+	P.flags = t.flags;
 	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0) ? 1 : 0;
 	P.diag = diag_dev();
+	P.prof = nullptr;
+	static long long *prof_dev = nullptr;
+	if (t.flags & 32) {
+		if (!prof_dev) cudaMalloc(&prof_dev, 64 * sizeof(long long));
+		cudaMemsetAsync(prof_dev, 0, 64 * sizeof(long long), stream);
+		P.prof = prof_dev;
+	}
 
 	static bool attr_set[3] = {false, false, false};
 	if (!attr_set[CG]) {
@@ -479,7 +524,16 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr; cfg.numAttrs = 1;
-	return cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG>, tmA, tmB, P);
+	cudaError_t le = cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG>, tmA, tmB, P);
+	if (le == cudaSuccess && (t.flags & 32)) {   // debug: per-role cycle breakdown of CTAs 0..3 on stderr
+		long long h[64];
+		if (cudaStreamSynchronize(stream) == cudaSuccess && cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
+			for (int c = 0; c < 4; c++)
+				fprintf(stderr, "k1prof cta%d producer: wait_empty %lld / %lld | mma: wait_xf %lld wait_tempty %lld / %lld | transform: wait_full %lld work %lld fence %lld / %lld | epilogue: wait_tfull %lld drain %lld store %lld / %lld\n",
+				        c, h[16 * c + 0], h[16 * c + 1], h[16 * c + 2], h[16 * c + 3], h[16 * c + 4], h[16 * c + 5], h[16 * c + 6], h[16 * c + 7],
+				        h[16 * c + 8], h[16 * c + 9], h[16 * c + 10], h[16 * c + 11], h[16 * c + 12]);
+	}
+	return le;
 }
 
 } // namespace
