@@ -303,6 +303,24 @@ def run_multi(args, wl_name):
     tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
     e2e_ms = float(tmax[0].item()) / e2e_steps
 
+    # ---- sampled verification of this rank's C block against fp64 dot products of regenerated windows
+    import numpy as np
+    sg.run(True)
+    torch.cuda.synchronize()
+    r0, c0, rows, cols = plan.c_window()
+    rs = np.linspace(0, rows - 1, 6).astype(int)
+    cs = np.linspace(0, cols - 1, 48).astype(int)
+    cblk = sg.c.view(rows, cols)[torch.as_tensor(rs, device="cuda")][:, torch.as_tensor(cs, device="cuda")].cpu().numpy()
+    a_rows = np.stack([u.fill_uniform_host_2d(1, K, 1, (r0 + int(r)) * K, K) for r in rs]).astype(np.float64)
+    b_cols = np.stack([u.fill_uniform_host_2d(K, 1, 2, c0 + int(c), N) for c in cs], axis=1).astype(np.float64)
+    ref = a_rows @ b_cols
+    verr = float(np.linalg.norm(cblk - ref) / np.linalg.norm(ref))
+    tv = torch.tensor([verr], device="cuda")
+    dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+    verr = float(tv.item())
+    if not verr <= 1e-5:
+        raise SystemExit(f"sharded result failed verification: sampled relerr {verr:.3e} > 1e-5")
+
     if rank == 0:
         peaks = measured_peaks()
         peak = peaks["bf16_burst"] / 6.0 * world
@@ -313,7 +331,7 @@ def run_multi(args, wl_name):
             "config": {"workload": wl["desc"], "grid": f"{plan.pr}x{plan.pc}", "k_slabs": plan.L,
                        "timed_region": "owner-rooted NCCL panel broadcast + local GEMMs (distribution included), max over ranks",
                        "compute_only_tflops": flops / ms_compute / 1e9, "compute_only_ms": ms_compute,
-                       "recv_bytes_per_rank": plan.recv_bytes(),
+                       "recv_bytes_per_rank": plan.recv_bytes(), "verified_sampled_relerr_max_over_ranks": verr,
                        "l2_policy": "inputs larger than L2 (per-GPU panels %.1f GB)" % ((plan.mloc * K + K * plan.nloc) * 4 / 1e9)},
             "e2e": {"value": flops / e2e_ms / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": int(tsum[1].item()),
                     "d2h_bytes_per_step": int(tsum[2].item()), "ms_per_step": e2e_ms, "steps": e2e_steps,

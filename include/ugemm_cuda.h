@@ -60,7 +60,7 @@ void sgemm_cuda_simt(char major, char transA, char transB, int M, int N, int K, 
                      const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc);
 
 /* ---- the timed path: DEVICE pointers, asynchronous on `stream` (a cudaStream_t; NULL = the backend's
- * own stream).  Replaces the body of sgemm_ocl after its uploads (kernel launch, sgemm_ocl2.h:201-215),
+ * own non-blocking stream -- pass cudaStreamLegacy (0x1) to mean CUDA's legacy default stream).  Replaces the body of sgemm_ocl after its uploads (kernel launch, sgemm_ocl2.h:201-215),
  * including the work of the separate `transpose` kernel (sgemm_ocl2.h:95-128,180-199): transposes are
  * folded into the operand loads.  Returns 0 on success. */
 int sgemm_cuda_dev(int mode, void *stream, char major, char transA, char transB, int M, int N, int K,

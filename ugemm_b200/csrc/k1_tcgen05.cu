@@ -14,11 +14,12 @@
 //               box, SWIZZLE_128B.  MN-major operands (transA=='T' / transB=='N'): four {32 mn x 32 k}
 //               boxes, SWIZZLE_128B_ATOM_32B (the only MN-major layout tcgen05 accepts for 32-bit types).
 //               Ragged M/N/K edges are zero-filled by TMA out-of-bounds handling.
-//   warps 4-7   transform: read each landed stage, write the "small" operand copies (same swizzled
-//               layout, so the transform is a flat element-wise pass), fence.proxy.async, signal the MMA.
+//   warps 4-11  transform (two warpgroups alternating k-blocks, so the shared-memory round trips and the proxy
+//               fence of one stage overlap the next): read each landed stage, write the "small" operand copies
+//               (same swizzled layout, so the transform is a flat element-wise pass), fence.proxy.async, signal.
 //   warp 1      MMA issuer (leader CTA only): per k-step of 8: small*big, big*small, big*big into the TMEM
 //               accumulator; tcgen05.commit releases the stage; accumulators are double-buffered in TMEM.
-//   warps 8-15  epilogue: tcgen05.ld the accumulator, (optionally) promote partial sums every kc_blocks
+//   warps 12-19 epilogue: tcgen05.ld the accumulator, (optionally) promote partial sums every kc_blocks
 //               k-blocks into fp32 registers with round-to-nearest adds, then fused alpha/beta and
 //               direct global stores (row per thread, 128 B contiguous per 32-column group).
 //   Persistent: each CTA (pair) walks a static, L2-friendly grouped tile order.
@@ -39,8 +40,10 @@ constexpr int OPER_BYTES = ROWS * BK * 4;     // 16 KiB
 constexpr int RAW_BYTES = 2 * OPER_BYTES;     // A raw | B raw
 constexpr int STAGE_BYTES = 2 * RAW_BYTES;    // A raw | B raw | A small | B small = 64 KiB
 constexpr int STAGES = 3;
-constexpr int NUM_THREADS = 512;              // 16 warps, see role map above
-constexpr int BAR_BYTES = 128;
+constexpr int NUM_THREADS = 640;              // 20 warps, see role map above
+constexpr int XF_GROUPS = 2;                  // transform warpgroups, alternating k-blocks
+constexpr int BAR_BYTES = 256;
+constexpr int SCHED_SLOTS = 4;               // depth of the dynamic tile-index ring
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024; // + slack for 1024-B alignment
 constexpr long long WATCHDOG_CYCLES = 6000000000LL;
 
@@ -53,6 +56,7 @@ struct K1Params {
 	int tiles_m, tiles_n, num_tiles;
 	int num_k_blocks, kc_blocks, split, vecC, flags;
 	unsigned *diag;
+	int *sched;        // [0] next tile index (atomic), [1] clusters finished; self-resetting
 	long long *prof;   // flags & 32: per-role cycle counters of the first 4 CTAs (16 slots each), debug only
 };
 
@@ -91,6 +95,28 @@ __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, 
 	const int r = tile - group * per_group;
 	tm = first_m + r % gsize;
 	tn = r / gsize;
+}
+
+// ---- dynamic tile scheduler ------------------------------------------------------------------------------------
+// One thread per cluster (leader CTA, warp 2) claims tile indices from a global atomic counter and publishes them
+// through a 4-deep shared-memory ring to every role of both CTAs; a CTA pair that starts late (SMs busy with another
+// kernel, e.g. NCCL) simply claims fewer tiles.  sched_full[slot] (count 1, one per CTA) / sched_empty[slot] (leader
+// only; one arrival per consuming role) are mbarriers; a negative index ends the kernel.
+template <int CG>
+__device__ __forceinline__ int next_tile(uint32_t bar_base, int &n, bool warp_collective, int lane, unsigned *diag)
+{
+	const int slot = n & (SCHED_SLOTS - 1);
+	const uint32_t ph = (n / SCHED_SLOTS) & 1;
+	n++;
+	const uint32_t full = bar_base + 8u * (14 + slot), empty = bar_base + 8u * (14 + SCHED_SLOTS + slot);
+	if (CG == 2) mbar_wait_cluster(full, ph, diag, 6); else mbar_wait(full, ph, diag, 6);
+	int tile;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tile) : "r"(bar_base + 8u * (14 + 2 * SCHED_SLOTS) + 4u * slot) : "memory");
+	if (warp_collective) __syncwarp();
+	if (!warp_collective || lane == 0) {
+		if (CG == 2) mbar_arrive_cluster(empty, 0); else mbar_arrive(empty);
+	}
+	return tile;
 }
 
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
@@ -144,6 +170,11 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			mbar_init(tfull_bar(a), 1);
 			mbar_init(tempty_bar(a), 8 * CG);  // 8 epilogue warps per CTA of the pair
 		}
+		for (int d = 0; d < SCHED_SLOTS; d++) {
+			mbar_init(bar_base + 8u * (14 + d), 1);
+			// consumers of a tile index: TMA thread, 8 transform warps, 8 epilogue warps per CTA + the MMA thread
+			mbar_init(bar_base + 8u * (14 + SCHED_SLOTS + d), (1 + 4 * XF_GROUPS + 8) * CG + 1);
+		}
 		fence_mbar_init();
 	}
 	__syncwarp();
@@ -157,17 +188,20 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 	const uint32_t tmem_base = *tmem_slot_ptr;
 
 	if (warp < 4) {
-		reg_dec<48>();
+		reg_dec<40>();
 		if (warp == 0 && lane == 0) {
 			// ================= TMA producer =================
 			int it = 0;
 			long long w_empty = 0; const long long t_begin = clock64();
-			for (int tile = cluster_id; tile < P.num_tiles && !(P.flags & 64); tile += num_clusters) {
+			const uint64_t hintA = (P.flags & 128) ? L2_EVICT_LAST : (P.flags & 1024) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+			const uint64_t hintB = (P.flags & 512) ? L2_EVICT_LAST : (P.flags & 256) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+			int nt = 0;
+			for (int tile; (tile = next_tile<CG>(bar_base, nt, false, 0, P.diag)) >= 0;) {
 				int tm, tn;
 				decode_tile(tile, P.tiles_m, P.tiles_n, tm, tn);
 				const int a_row0 = tm * UMMA_M + (int)cta_rank * ROWS;
 				const int b_row0 = tn * BN + (int)cta_rank * ROWS;
-				for (int kb = 0; kb < nkb; kb++, it++) {
+				for (int kb = 0; kb < nkb && !(P.flags & 64); kb++, it++) {
 					const int s = it % STAGES;
 					const uint32_t ph = (it / STAGES) & 1;
 					const long long tw = clock64();
@@ -176,12 +210,12 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					mbar_arrive_expect_tx(full_bar(s), RAW_BYTES);
 					const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + OPER_BYTES;
 					const int k0 = kb * BK;
-					if (P.a_kmajor) tma_load_2d(sA, &tmA, full_bar(s), k0, a_row0);
+					if (P.a_kmajor) tma_load_2d_hint(sA, &tmA, full_bar(s), k0, a_row0, hintA);
 					else
-						for (int j = 0; j < ROWS / 32; j++) tma_load_2d(sA + j * 4096, &tmA, full_bar(s), a_row0 + 32 * j, k0);
-					if (P.b_kmajor) tma_load_2d(sB, &tmB, full_bar(s), k0, b_row0);
+						for (int j = 0; j < ROWS / 32; j++) tma_load_2d_hint(sA + j * 4096, &tmA, full_bar(s), a_row0 + 32 * j, k0, hintA);
+					if (P.b_kmajor) tma_load_2d_hint(sB, &tmB, full_bar(s), k0, b_row0, hintB);
 					else
-						for (int j = 0; j < ROWS / 32; j++) tma_load_2d(sB + j * 4096, &tmB, full_bar(s), b_row0 + 32 * j, k0);
+						for (int j = 0; j < ROWS / 32; j++) tma_load_2d_hint(sB + j * 4096, &tmB, full_bar(s), b_row0 + 32 * j, k0, hintB);
 				}
 			}
 			if (prof) { prof[0] = w_empty; prof[1] = clock64() - t_begin; }
@@ -196,7 +230,8 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			const uint32_t a_kstep = P.a_kmajor ? 32u : 1024u, b_kstep = P.b_kmajor ? 32u : 1024u;
 			int it = 0, ci = 0;
 			long long w_xf = 0, w_te = 0; const long long t_begin = clock64();
-			for (int tile = cluster_id; tile < P.num_tiles; tile += num_clusters) {
+			int nt = 0;
+			while (next_tile<CG>(bar_base, nt, false, 0, P.diag) >= 0) {
 				for (int kb0 = 0; kb0 < nkb; kb0 += kc, ci++) {
 					const int acc = ci & 1;
 					const uint32_t aph = (ci >> 1) & 1;
@@ -242,16 +277,44 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				}
 			}
 			if (prof) { prof[2] = w_xf; prof[3] = w_te; prof[4] = clock64() - t_begin; }
+		} else if (warp == 2 && lane == 0 && cta_rank == 0) {
+			// ================= tile scheduler (leader CTA) =================
+			const uint32_t slots = bar_base + 8u * (14 + 2 * SCHED_SLOTS);
+			for (int n = 0;; n++) {
+				const int slot = n & (SCHED_SLOTS - 1);
+				const uint32_t ph = (n / SCHED_SLOTS) & 1;
+				const uint32_t full = bar_base + 8u * (14 + slot), empty = bar_base + 8u * (14 + SCHED_SLOTS + slot);
+				if (CG == 2) mbar_wait_cluster(empty, ph ^ 1u, P.diag, 7); else mbar_wait(empty, ph ^ 1u, P.diag, 7);
+				int tile = atomicAdd(P.sched, 1);
+				if (tile >= P.num_tiles) tile = -1;
+				asm volatile("st.shared.b32 [%0], %1;" ::"r"(slots + 4u * slot), "r"(tile) : "memory");
+				if (CG == 2) {
+					asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 1;\n\t"
+					             "st.shared::cluster.b32 [ra], %1;\n\t}" ::"r"(slots + 4u * slot), "r"(tile) : "memory");
+					mbar_arrive_cluster(full, 0);
+					mbar_arrive_cluster(full, 1);
+				} else {
+					mbar_arrive(full);
+				}
+				if (tile < 0) {
+					// the last cluster to run dry re-arms the counters for the next launch using this slot
+					if (atomicAdd(P.sched + 1, 1) == num_clusters - 1) { P.sched[0] = 0; P.sched[1] = 0; __threadfence(); }
+					break;
+				}
+			}
 		}
 		__syncwarp();   // reconverge before the .aligned teardown barrier
-	} else if (warp < 8) {
+	} else if (warp < 4 + 4 * XF_GROUPS) {
 		// ================= transform warps: write the "small" operand copies =================
 		reg_dec<64>();
-		const int t = threadIdx.x - 128;
+		const int grp = (warp - 4) >> 2;                 // this warpgroup takes k-blocks with it % XF_GROUPS == grp
+		const int t = (threadIdx.x - 128) & 127;
 		int it = 0;
 		long long w_full = 0, t_work = 0, t_fence = 0; const long long t_begin = clock64();
-		for (int tile = cluster_id; tile < P.num_tiles && !(P.flags & 64); tile += num_clusters) {
-			for (int kb = 0; kb < nkb; kb++, it++) {
+		int nt = 0;
+		while (next_tile<CG>(bar_base, nt, true, lane, P.diag) >= 0) {
+			for (int kb = 0; kb < nkb && !(P.flags & 64); kb++, it++) {
+				if (it % XF_GROUPS != grp) continue;
 				const int s = it % STAGES;
 				const uint32_t ph = (it / STAGES) & 1;
 				const long long t0 = clock64();
@@ -290,17 +353,18 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				w_full += t1 - t0; t_work += t2 - t1; t_fence += t3 - t2;
 			}
 		}
-		if (prof && t == 0) { prof[5] = w_full; prof[6] = t_work; prof[7] = t_fence; prof[8] = clock64() - t_begin; }
+		if (prof && threadIdx.x == 128) { prof[5] = w_full; prof[6] = t_work; prof[7] = t_fence; prof[8] = clock64() - t_begin; }
 	} else {
 		// ================= epilogue warps =================
-		reg_inc<200>();
-		const int e = warp - 8;
+		reg_inc<152>();
+		const int e = warp - (4 + 4 * XF_GROUPS);
 		const int q = e & 3;        // TMEM lane quarter (must equal warp % 4)
 		const int h = e >> 2;       // column half
 		const float alpha = P.alpha, beta = P.beta;
 		int ci = 0;
 		long long w_tf = 0, t_drain = 0, t_store = 0; const long long t_begin = clock64();
-		for (int tile = cluster_id; tile < P.num_tiles; tile += num_clusters) {
+		int nt = 0;
+		for (int tile; (tile = next_tile<CG>(bar_base, nt, true, lane, P.diag)) >= 0;) {
 			int tm, tn;
 			decode_tile(tile, P.tiles_m, P.tiles_n, tm, tn);
 			float acc[NG][32];
@@ -317,11 +381,11 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				tc_fence_after();
 				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * (BN / 2));
 #pragma unroll
-				for (int g = 0; g < NG; g++) {
-					float v[32];
-					tmem_ld_32x32b_x32(taddr + g * 32, v);
+				for (int g = 0; g < 2 * NG; g++) {
+					float v[16];
+					tmem_ld_32x32b_x16(taddr + g * 16, v);
 #pragma unroll
-					for (int i = 0; i < 32; i++) acc[g][i] += v[i];   // fp32 round-to-nearest promotion
+					for (int i = 0; i < 16; i++) acc[g >> 1][(g & 1) * 16 + i] += v[i];   // fp32 round-to-nearest promotion
 				}
 				tc_fence_before();
 				__syncwarp();
@@ -368,7 +432,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			}
 			t_store += clock64() - ts0;
 		}
-		if (prof && threadIdx.x == 256) { prof[9] = w_tf; prof[10] = t_drain; prof[11] = t_store; prof[12] = clock64() - t_begin; }
+		if (prof && threadIdx.x == 32 * (4 + 4 * XF_GROUPS)) { prof[9] = w_tf; prof[10] = t_drain; prof[11] = t_store; prof[12] = clock64() - t_begin; }
 	}
 
 	// ---- teardown: everyone (both CTAs of a pair) done before TMEM is returned ------------------------------
@@ -499,6 +563,15 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	P.flags = t.flags;
 	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0) ? 1 : 0;
 	P.diag = diag_dev();
+	// dynamic-scheduler counters: a small pool so launches on different streams do not share a slot
+	static int *sched_pool = nullptr;
+	static unsigned sched_next = 0;
+	constexpr unsigned SCHED_POOL = 64;
+	if (!sched_pool) {
+		if (cudaMalloc(&sched_pool, SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return cudaErrorMemoryAllocation;
+		cudaMemset(sched_pool, 0, SCHED_POOL * 2 * sizeof(int));
+	}
+	P.sched = sched_pool + 2 * (sched_next++ % SCHED_POOL);
 	P.prof = nullptr;
 	static long long *prof_dev = nullptr;
 	if (t.flags & 32) {

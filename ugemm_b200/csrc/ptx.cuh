@@ -65,6 +65,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, uint
 	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// same with an L2 eviction-priority hint (createpolicy encodings: evict_first / evict_last)
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull, L2_EVICT_NORMAL = 0x1000000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1, uint64_t hint)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
+}
+
 // ---- tensor memory --------------------------------------------------------------------------------------
 template <int CG> __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
 {

@@ -97,12 +97,16 @@ class CudaOps:
     def empty(self, n):
         return self.torch.empty(n, dtype=self.torch.float32, device=self.device)
 
+    def _stream(self):
+        # the C ABI reads a NULL stream as "the backend's own stream"; torch's default stream has handle 0, which
+        # must be passed as cudaStreamLegacy (0x1) so the launch is ordered with torch's work and NCCL waits
+        return self.torch.cuda.current_stream().cuda_stream or 1
+
     def fill_window(self, t, rows, cols, seed, offset, gld, lo, hi):
-        self.be.fill_uniform_dev_2d(t.data_ptr(), rows, cols, cols, seed, offset, gld, lo, hi,
-                                    stream=self.torch.cuda.current_stream().cuda_stream)
+        self.be.fill_uniform_dev_2d(t.data_ptr(), rows, cols, cols, seed, offset, gld, lo, hi, stream=self._stream())
 
     def gemm(self, M, N, K, A, lda, B, ldb, beta, Cm, ldc):
-        self.be.sgemm_cuda_dev(self.mode, self.torch.cuda.current_stream().cuda_stream, "R", "N", "N", M, N, K, 1.0,
+        self.be.sgemm_cuda_dev(self.mode, self._stream(), "R", "N", "N", M, N, K, 1.0,
                                A.data_ptr(), lda, B.data_ptr(), ldb, beta, Cm.data_ptr(), ldc)
 
     def sync(self):
