@@ -239,6 +239,9 @@ def run_multi(args, wl_name):
     from ugemm_b200.dist import CudaOps, ShardedGemm, SlabPlan
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    # the panel broadcasts only have to keep up with the GEMM of the previous slab, not saturate NVLink: a few CTAs
+    # per communicator are enough and fit in the SMs the sharded driver leaves free (ugemm_b200/dist.py)
+    os.environ.setdefault("NCCL_MAX_CTAS", "4")
     torch.cuda.set_device(local)
     u.sgemm_cuda_init(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))

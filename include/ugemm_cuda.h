@@ -95,6 +95,11 @@ int  ugemm_cuda_device_info(int *sm_count, int *sm_clock_khz, size_t *hbm_bytes,
  * cta_group: 1 or 2 CTAs per MMA. */
 void sgemm_cuda_set_k1_tuning(int kc_blocks, int split, int cta_group);
 
+/* Cap the number of SMs K1's persistent grid occupies (0 = all).  Used by the sharded driver while NCCL panel
+ * broadcasts are in flight: a persistent CTA fills an SM's registers and shared memory, so a few SMs are left
+ * free for the collective's own CTAs instead of serialising the transfer behind the GEMM. */
+void sgemm_cuda_set_sm_limit(int sms);
+
 /* ---- memory helpers (replace oclKernelArgs/oclWrite/oclRead buffer plumbing, ocl.h:227-293) */
 void *ugemm_cuda_malloc(size_t bytes);            /* device memory */
 void  ugemm_cuda_free(void *dptr);

@@ -72,6 +72,8 @@ def lib():
     L.ugemm_cuda_device_info.restype = C.c_int
     L.sgemm_cuda_set_k1_tuning.argtypes = [C.c_int, C.c_int, C.c_int]
     L.sgemm_cuda_set_k1_tuning.restype = None
+    L.sgemm_cuda_set_sm_limit.argtypes = [C.c_int]
+    L.sgemm_cuda_set_sm_limit.restype = None
     L.ugemm_cuda_malloc.argtypes = [C.c_size_t]
     L.ugemm_cuda_malloc.restype = C.c_void_p
     L.ugemm_cuda_free.argtypes = [C.c_void_p]
@@ -103,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "sgemm_cuda_init", "sgemm_cuda_finish", "sgemm_cuda", "sgemm_cuda_3xtf32", "sgemm_cuda_simt",
     "sgemm_cuda_dev", "sgemm_cuda_k1_eligible", "sgemm_cuda_time_dev", "sgemm_cuda_last_error",
     "sgemm_cuda_clear_error", "sgemm_cuda_last_kernel", "sgemm_cuda_launch_count", "ugemm_cuda_device_info",
-    "sgemm_cuda_set_k1_tuning", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
+    "sgemm_cuda_set_k1_tuning", "sgemm_cuda_set_sm_limit", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
     "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
     "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
     "ugemm_cuda_probe_tf32",
@@ -180,6 +182,10 @@ def k1_eligible(major, ta, tb, M, N, K, dA, lda, dB, ldb, dC, ldc):
 
 def set_k1_tuning(kc_blocks=-1, split=-1, cta_group=-1):
     lib().sgemm_cuda_set_k1_tuning(kc_blocks, split, cta_group)
+
+
+def set_sm_limit(sms=0):
+    lib().sgemm_cuda_set_sm_limit(int(sms))
 
 
 def last_kernel():

@@ -27,11 +27,14 @@ struct State {
 	char name[128] = {0};
 	cudaStream_t stream = nullptr;   // compute + H2D
 	cudaStream_t stream_d2h = nullptr;
+	cudaStream_t stream_h2d = nullptr;
+	cudaEvent_t ev_up[16] = {0}, ev_done[16] = {0};
 	// staging arena of the host-pointer entry points (one buffer like the OpenCL backend's `gm`)
 	char *arena = nullptr;
 	size_t arena_bytes = 0;
 	K1Tuning tuning = {4, 0, 2, 0};   // promote every 4 k-blocks (128 k), truncation split, 2-CTA pairs
 	int last_kernel = 0;
+	int sm_limit = 0;                // 0 = all SMs; otherwise K1's persistent grid is capped (leaves SMs to NCCL)
 	unsigned long long launches = 0;
 } g;
 
@@ -114,7 +117,7 @@ int run_dev(int mode, cudaStream_t stream, const Problem &p)
 	if (use == UGEMM_MODE_3XTF32) {
 		const char *why = nullptr;
 		if (!k1_eligible(p, &why)) { set_error("3xTF32 kernel not applicable: %s", why); return 1; }
-		CU_TRY(launch_k1_3xtf32(p, g.tuning, stream, g.sm_count), "K1 (3xTF32 tcgen05) launch");
+		CU_TRY(launch_k1_3xtf32(p, g.tuning, stream, (g.sm_limit > 0 && g.sm_limit < g.sm_count) ? g.sm_limit : g.sm_count), "K1 (3xTF32 tcgen05) launch");
 	} else if (use == UGEMM_MODE_SIMT) {
 		CU_TRY(launch_k2_simt(p, stream, g.sm_count), "K2 (SIMT FFMA) launch");
 	} else {
@@ -139,6 +142,59 @@ int ensure_arena(size_t bytes)
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+cudaError_t copy2d(float *dst, const float *src, long long ld, long long lines, long long cols, cudaMemcpyKind kind, cudaStream_t st)
+{
+	if (lines <= 0 || cols <= 0) return cudaSuccess;
+	if (ld == cols) return cudaMemcpyAsync(dst, src, (size_t)lines * cols * 4, kind, st);
+	return cudaMemcpy2DAsync(dst, (size_t)ld * 4, src, (size_t)ld * 4, (size_t)cols * 4, (size_t)lines, kind, st);
+}
+
+// Large problems: the reference's OpenCL path uploads everything, runs, downloads (sgemm_ocl2.h:175-217) and its
+// timed region is dominated by the two PCIe transfers.  Here op(B) goes up first, then row panels of op(A) (and of C
+// when beta != 0) stream up on one stream while the GEMM of the previous panel runs on a second and the finished C
+// panel streams down on a third (PCIe is full duplex).  Same device layout and leading dimensions as the one-shot
+// path, so kernel choice and results are identical.  Host buffers should be pinned (ugemm_cuda_malloc_host) for the
+// copies to be truly asynchronous; pageable memory still works, just without the overlap.
+void run_host_pipelined(int mode, const Problem &p, float *dA, float *dB, float *dC)
+{
+	const long long b_lines = p.b_kmajor ? p.N : p.K, b_cols = p.b_kmajor ? p.K : p.N;
+	int panels = (int)((p.M + 1023) / 1024);
+	if (panels > 16) panels = 16;
+	long long mb = ((p.M + panels - 1) / panels + 255) / 256 * 256;
+	panels = (int)((p.M + mb - 1) / mb);
+	cudaStream_t s_up = g.stream_h2d, s_cmp = g.stream, s_dn = g.stream_d2h;
+	cudaError_t e = copy2d(dB, p.B, p.ldb, b_lines, b_cols, cudaMemcpyHostToDevice, s_up);
+	int rc = 0;
+	for (int i = 0; i < panels && e == cudaSuccess && !rc; i++) {
+		const long long m0 = i * mb, mm = (p.M - m0 < mb) ? p.M - m0 : mb;
+		// panel i of op(A): rows m0.. of an M x K array (k-major) or columns m0.. of a K x M array
+		if (p.a_kmajor) e = copy2d(dA + m0 * p.lda, p.A + m0 * p.lda, p.lda, mm, p.K, cudaMemcpyHostToDevice, s_up);
+		else e = cudaMemcpy2DAsync(dA + m0, (size_t)p.lda * 4, p.A + m0, (size_t)p.lda * 4, (size_t)mm * 4, (size_t)p.K, cudaMemcpyHostToDevice, s_up);
+		if (e == cudaSuccess && p.beta != 0.f)
+			e = copy2d(dC + m0 * p.ldc, p.C + m0 * p.ldc, p.ldc, mm, p.N, cudaMemcpyHostToDevice, s_up);
+		if (e != cudaSuccess) break;
+		cudaEventRecord(g.ev_up[i], s_up);
+		cudaStreamWaitEvent(s_cmp, g.ev_up[i], 0);
+		Problem d = p;
+		d.M = (int)mm;
+		d.A = p.a_kmajor ? dA + m0 * p.lda : dA + m0;
+		d.B = dB;
+		d.C = dC + m0 * p.ldc;
+		rc = run_dev(mode, s_cmp, d);
+		if (rc) break;
+		cudaEventRecord(g.ev_done[i], s_cmp);
+		cudaStreamWaitEvent(s_dn, g.ev_done[i], 0);
+		e = copy2d(p.C + m0 * p.ldc, dC + m0 * p.ldc, p.ldc, mm, p.N, cudaMemcpyDeviceToHost, s_dn);
+	}
+	cudaError_t e1 = cudaStreamSynchronize(s_up), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_dn);
+	if (e == cudaSuccess) e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+	if (e != cudaSuccess && !rc) {
+		const unsigned *dg = k1_diag_host();
+		if (dg && dg[0]) set_error("pipelined GEMM failed: %s (K1 watchdog code %u, block %u, thread %u)", cudaGetErrorString(e), dg[0], dg[1], dg[2]);
+		else set_error("pipelined GEMM failed: %s", cudaGetErrorString(e));
+	}
+}
+
 // Host-pointer GEMM: stage operands into the arena, run, copy C back.  Blocking, like sgemm_ocl.
 void run_host(int mode, char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda,
               const float *B, int ldb, float beta, float *C, int ldc)
@@ -161,6 +217,16 @@ void run_host(int mode, char major, char ta, char tb, int M, int N, int K, float
 	if (ensure_arena(offC + c_bytes)) return;
 	float *dA = reinterpret_cast<float *>(g.arena + offA), *dB = reinterpret_cast<float *>(g.arena + offB);
 	float *dC = reinterpret_cast<float *>(g.arena + offC);
+
+	if (need_ab && p.M >= 2048 && !getenv("UGEMM_CUDA_NO_PIPELINE")) {
+		if (mode == UGEMM_MODE_3XTF32) {
+			Problem chk = p; chk.A = dA; chk.B = dB; chk.C = dC;
+			const char *why = nullptr;
+			if (!k1_eligible(chk, &why)) { set_error("3xTF32 kernel not applicable: %s", why); return; }
+		}
+		run_host_pipelined(mode, p, dA, dB, dC);
+		return;
+	}
 
 	cudaError_t e = cudaSuccess;
 	auto up2d = [&](float *d, const float *h, long long ld, long long lines, long long cols) {
@@ -244,6 +310,11 @@ int sgemm_cuda_init(int device, size_t arena_bytes)
 	strncpy(g.name, prop.name, sizeof g.name - 1);
 	CU_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate");
 	CU_TRY(cudaStreamCreateWithFlags(&g.stream_d2h, cudaStreamNonBlocking), "cudaStreamCreate");
+	CU_TRY(cudaStreamCreateWithFlags(&g.stream_h2d, cudaStreamNonBlocking), "cudaStreamCreate");
+	for (int i = 0; i < 16; i++) {
+		CU_TRY(cudaEventCreateWithFlags(&g.ev_up[i], cudaEventDisableTiming), "cudaEventCreate");
+		CU_TRY(cudaEventCreateWithFlags(&g.ev_done[i], cudaEventDisableTiming), "cudaEventCreate");
+	}
 	if (const char *f = getenv("UGEMM_K1_FLAGS")) g.tuning.flags = atoi(f);   // debug / ablation, see common.cuh
 	g.ready = true;
 	if (arena_bytes && ensure_arena(arena_bytes)) { g.ready = false; return 1; }
@@ -258,7 +329,9 @@ void sgemm_cuda_finish(void)
 	g.arena = nullptr; g.arena_bytes = 0;
 	cudaStreamDestroy(g.stream);
 	cudaStreamDestroy(g.stream_d2h);
-	g.stream = g.stream_d2h = nullptr;
+	cudaStreamDestroy(g.stream_h2d);
+	for (int i = 0; i < 16; i++) { cudaEventDestroy(g.ev_up[i]); cudaEventDestroy(g.ev_done[i]); }
+	g.stream = g.stream_d2h = g.stream_h2d = nullptr;
 	g.ready = false;
 }
 
@@ -367,6 +440,8 @@ void sgemm_cuda_set_k1_tuning(int kc_blocks, int split, int cta_group)
 	if (split >= 0) g.tuning.split = split ? 1 : 0;
 	if (cta_group == 1 || cta_group == 2) g.tuning.cta_group = cta_group;
 }
+
+void sgemm_cuda_set_sm_limit(int sms) { g.sm_limit = sms > 0 ? sms : 0; }
 
 void *ugemm_cuda_malloc(size_t bytes)
 {

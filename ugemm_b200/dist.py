@@ -87,12 +87,18 @@ class SlabPlan:
 class CudaOps:
     """Device plumbing for the real thing: torch CUDA tensors for memory/streams/NCCL, C ABI for compute."""
 
-    def __init__(self, mode="auto"):
+    def __init__(self, mode="auto", comm_sms=8):
         import torch
 
         from . import backend
         self.torch, self.be, self.mode = torch, backend, mode
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self.sm_count = backend.device_info()["sm_count"]
+        self.comm_sms = comm_sms
+
+    def reserve_for_comm(self, on):
+        """While panel broadcasts are in flight leave `comm_sms` SMs to NCCL (a persistent K1 CTA fills an SM)."""
+        self.be.set_sm_limit(self.sm_count - self.comm_sms if on else 0)
 
     def empty(self, n):
         return self.torch.empty(n, dtype=self.torch.float32, device=self.device)
@@ -162,10 +168,17 @@ class ShardedGemm:
                 if p.pr > 1:
                     wb = self.dist.broadcast(self.b[t], src=p.b_owner(t), group=self.col_group, async_op=True)
                 works[t] = (wa, wb)
+        overlapped = distribute and p.world > 1 and hasattr(self.ops, "reserve_for_comm")
+        if overlapped:
+            self.ops.reserve_for_comm(True)
         for t in range(p.L):
             if works[t] is not None:
                 for w in works[t]:
                     if w is not None:
                         w.wait()   # NCCL: makes the current stream wait for the collective; gloo: blocks
+            if overlapped and t == p.L - 1:
+                self.ops.reserve_for_comm(False)   # nothing left in flight behind the last slab
             self.ops.gemm(p.mloc, p.nloc, p.kw, self.a[t], p.kw, self.b[t], p.nloc, 0.0 if t == 0 else 1.0, self.c, p.nloc)
+        if overlapped:
+            self.ops.reserve_for_comm(False)
         return self.c
