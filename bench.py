@@ -236,7 +236,7 @@ def run_multi(args, wl_name):
     import torch.distributed as dist
 
     import ugemm_b200 as u
-    from ugemm_b200.dist import CudaOps, ShardedGemm, SlabPlan
+    from ugemm_b200.dist import CudaOps, CudaP2POps, ShardedGemm, SlabPlan
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     # the panel broadcasts only have to keep up with the GEMM of the previous slab, not saturate NVLink: a few CTAs
@@ -248,7 +248,8 @@ def run_multi(args, wl_name):
     wl = WORKLOADS[wl_name]
     M, N, K = wl["M"], wl["N"], wl["K"]
     plan = SlabPlan(world, rank, M, N, K)
-    sg = ShardedGemm(plan, CudaOps("auto"), dist)
+    ops = CudaP2POps("auto") if args.dist == "p2p" else CudaOps("auto")
+    sg = ShardedGemm(plan, ops, dist)
     sg.generate_owned(seed_a=1, seed_b=2)
     flops = 2.0 * M * N * K
 
@@ -278,19 +279,29 @@ def run_multi(args, wl_name):
     # ---- e2e: owned slabs come from pinned host memory every step, the C block goes back to pinned host memory
     own_a = [t for t in range(plan.L) if plan.a_owner(t) == rank]
     own_b = [t for t in range(plan.L) if plan.b_owner(t) == rank]
-    h_a = [sg.a[t].to("cpu").pin_memory() for t in own_a]
-    h_b = [sg.b[t].to("cpu").pin_memory() for t in own_b]
+    def stream_handle():
+        return torch.cuda.current_stream().cuda_stream or 1
+
+    def pinned_copy_of(buf, n):
+        h = torch.empty(n, dtype=torch.float32).pin_memory()
+        u.backend.memcpy_async(h.data_ptr(), buf.data_ptr(), 4 * n, stream_handle())
+        return h
+
+    h_a = [pinned_copy_of(sg.a[t], plan.mloc * plan.kw) for t in own_a]
+    h_b = [pinned_copy_of(sg.b[t], plan.kw * plan.nloc) for t in own_b]
     h_c = torch.empty(plan.mloc * plan.nloc, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
     h2d = sum(x.numel() for x in h_a + h_b) * 4
     d2h = h_c.numel() * 4
 
     def e2e_step():
+        sh = stream_handle()
         for t, h in zip(own_a, h_a):
-            sg.a[t].copy_(h, non_blocking=True)
+            u.backend.memcpy_async(sg.a[t].data_ptr(), h.data_ptr(), 4 * h.numel(), sh)
         for t, h in zip(own_b, h_b):
-            sg.b[t].copy_(h, non_blocking=True)
+            u.backend.memcpy_async(sg.b[t].data_ptr(), h.data_ptr(), 4 * h.numel(), sh)
         sg.run(True)
-        h_c.copy_(sg.c, non_blocking=True)
+        u.backend.memcpy_async(h_c.data_ptr(), sg.c.data_ptr(), 4 * h_c.numel(), stream_handle())
 
     e2e_step()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -313,7 +324,10 @@ def run_multi(args, wl_name):
     r0, c0, rows, cols = plan.c_window()
     rs = np.linspace(0, rows - 1, 6).astype(int)
     cs = np.linspace(0, cols - 1, 48).astype(int)
-    cblk = sg.c.view(rows, cols)[torch.as_tensor(rs, device="cuda")][:, torch.as_tensor(cs, device="cuda")].cpu().numpy()
+    full_rows = np.empty((len(rs), cols), np.float32)
+    for i, r in enumerate(rs):
+        u.backend.lib().ugemm_cuda_memcpy_d2h(full_rows[i].ctypes.data, sg.c.data_ptr() + 4 * int(r) * cols, 4 * cols)
+    cblk = full_rows[:, cs]
     a_rows = np.stack([u.fill_uniform_host_2d(1, K, 1, (r0 + int(r)) * K, K) for r in rs]).astype(np.float64)
     b_cols = np.stack([u.fill_uniform_host_2d(K, 1, 2, c0 + int(c), N) for c in cs], axis=1).astype(np.float64)
     ref = a_rows @ b_cols
@@ -332,7 +346,9 @@ def run_multi(args, wl_name):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "grid": f"{plan.pr}x{plan.pc}", "k_slabs": plan.L,
-                       "timed_region": "owner-rooted NCCL panel broadcast + local GEMMs (distribution included), max over ranks",
+                       "transport": sg.transport,
+                       "timed_region": "owner-rooted panel distribution (%s) + local GEMMs, distribution included, max over ranks"
+                                       % ("NCCL broadcast" if sg.transport == "nccl" else "copy-engine peer pull over NVLink"),
                        "compute_only_tflops": flops / ms_compute / 1e9, "compute_only_ms": ms_compute,
                        "recv_bytes_per_rank": plan.recv_bytes(), "verified_sampled_relerr_max_over_ranks": verr,
                        "l2_policy": "inputs larger than L2 (per-GPU panels %.1f GB)" % ((plan.mloc * K + K * plan.nloc) * 4 / 1e9)},
@@ -357,6 +373,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None] + list(WORKLOADS))
+    ap.add_argument("--dist", default=os.environ.get("UGEMM_BENCH_DIST", "nccl"), choices=["nccl", "p2p"],
+                    help="panel transport for --gpus N > 1: NCCL broadcast or copy-engine peer pull")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -108,6 +108,14 @@ void  ugemm_cuda_free_host(void *hptr);
 int   ugemm_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int   ugemm_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes);
 int   ugemm_cuda_sync(void);
+/* stream-ordered copy between any two pointers of the unified address space (device<->device across GPUs included) */
+int   ugemm_cuda_memcpy_async(void *dst, const void *src, size_t bytes, void *stream);
+/* Peer-to-peer plumbing for the sharded driver (one process per GPU): export a ugemm_cuda_malloc'ed buffer as a
+ * 64-byte CUDA IPC handle, map a peer's handle into this process (peer access enabled lazily), unmap it.  Copies
+ * from a mapped peer buffer run on the copy engines over NVLink and take no SMs from the GEMM. */
+int   ugemm_cuda_ipc_export(void *dptr, void *handle64);
+void *ugemm_cuda_ipc_import(const void *handle64);
+int   ugemm_cuda_ipc_close(void *mapped);
 
 /* ---- counter-based uniform stream, identical on host and device (so a 32768^2 operand can be generated
  * on the GPU and any sampled row regenerated on the host for verification):

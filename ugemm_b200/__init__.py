@@ -4,6 +4,7 @@ Only what the hot path needs: `csrc/` (hand-written CUDA kernels + the extern "C
 include/ugemm_cuda.h), `build.py` (nvcc recipe) and `backend.py` (ctypes binding that mirrors the
 reference's `sgemm_*` entry points), plus `dist.py` (2-D C-tile sharding across GPUs).
 """
+from . import backend  # noqa: F401
 from .backend import (  # noqa: F401
     MODE_3XTF32, MODE_AUTO, MODE_SIMT, DeviceBuffer, UgemmCudaError, check, device_info, fill_uniform_host,
     fill_uniform_dev_2d, fill_uniform_host_2d,

@@ -85,6 +85,14 @@ def lib():
     L.ugemm_cuda_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.ugemm_cuda_memcpy_d2h.restype = C.c_int
     L.ugemm_cuda_sync.restype = C.c_int
+    L.ugemm_cuda_memcpy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.ugemm_cuda_memcpy_async.restype = C.c_int
+    L.ugemm_cuda_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.ugemm_cuda_ipc_export.restype = C.c_int
+    L.ugemm_cuda_ipc_import.argtypes = [C.c_void_p]
+    L.ugemm_cuda_ipc_import.restype = C.c_void_p
+    L.ugemm_cuda_ipc_close.argtypes = [C.c_void_p]
+    L.ugemm_cuda_ipc_close.restype = C.c_int
     L.ugemm_fill_uniform_host.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_float, C.c_float]
     L.ugemm_fill_uniform_host.restype = None
     L.ugemm_fill_uniform_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_float, C.c_float, C.c_void_p]
@@ -107,6 +115,7 @@ EXPORTED_SYMBOLS = [
     "sgemm_cuda_clear_error", "sgemm_cuda_last_kernel", "sgemm_cuda_launch_count", "ugemm_cuda_device_info",
     "sgemm_cuda_set_k1_tuning", "sgemm_cuda_set_sm_limit", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
     "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
+    "ugemm_cuda_memcpy_async", "ugemm_cuda_ipc_export", "ugemm_cuda_ipc_import", "ugemm_cuda_ipc_close",
     "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
     "ugemm_cuda_probe_tf32",
 ]
@@ -266,6 +275,31 @@ def fill_uniform_host_2d(rows, cols, seed, offset, gld, lo=0.0, hi=1.0, ld=None,
 def fill_uniform_dev_2d(dptr, rows, cols, ld, seed, offset, gld, lo=0.0, hi=1.0, stream=None):
     if lib().ugemm_fill_uniform_dev_2d(_ptr(dptr), rows, cols, ld, seed, offset, gld, lo, hi, C.c_void_p(stream or 0)):
         check()
+
+
+def memcpy_async(dst, src, nbytes, stream=None):
+    if lib().ugemm_cuda_memcpy_async(_ptr(dst), _ptr(src), nbytes, C.c_void_p(stream or 0)):
+        check()
+
+
+def ipc_export(dptr):
+    """64-byte CUDA IPC handle (bytes) of a buffer allocated with ugemm_cuda_malloc / DeviceBuffer."""
+    h = C.create_string_buffer(64)
+    if lib().ugemm_cuda_ipc_export(_ptr(dptr), h):
+        check()
+    return h.raw
+
+
+def ipc_import(handle):
+    p = lib().ugemm_cuda_ipc_import(C.c_char_p(handle))
+    if not p:
+        check()
+        raise UgemmCudaError("ugemm_cuda_ipc_import failed")
+    return p
+
+
+def ipc_close(ptr):
+    lib().ugemm_cuda_ipc_close(C.c_void_p(ptr))
 
 
 def sync():

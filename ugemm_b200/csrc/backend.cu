@@ -475,6 +475,36 @@ int ugemm_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes)
 	CU_TRY(cudaStreamSynchronize(g.stream), "D2H sync");
 	return 0;
 }
+int ugemm_cuda_memcpy_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+	if (ensure_init()) return 1;
+	CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream ? static_cast<cudaStream_t>(stream) : g.stream), "async copy");
+	return 0;
+}
+int ugemm_cuda_ipc_export(void *dptr, void *handle64)
+{
+	if (ensure_init()) return 1;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	CU_TRY(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(handle64), dptr), "cudaIpcGetMemHandle");
+	return 0;
+}
+void *ugemm_cuda_ipc_import(const void *handle64)
+{
+	if (ensure_init()) return nullptr;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof h);
+	void *p = nullptr;
+	cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+	if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); return nullptr; }
+	return p;
+}
+int ugemm_cuda_ipc_close(void *p)
+{
+	if (!p) return 0;
+	CU_TRY(cudaIpcCloseMemHandle(p), "cudaIpcCloseMemHandle");
+	return 0;
+}
+
 int ugemm_cuda_sync(void)
 {
 	if (ensure_init()) return 1;

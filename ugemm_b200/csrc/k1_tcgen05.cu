@@ -262,6 +262,25 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 							const uint64_t dBs = smem_desc(sBs + k4 * b_kstep, b_lbo, b_sbo, b_lay);
 							const uint32_t first = (kb > kb0 || k4 > 0) ? 1u : 0u;
 							if (P.flags & 8) { mma_tf32_ss<CG>(d_tmem, dAb, dBb, idesc, first); continue; }
+							if (P.flags & 2048) {   // timing experiment only: A operand from (aliased) tensor memory
+								const uint32_t a_t = tmem_base + (uint32_t)((acc ^ 1) * BN) + k4 * 8;
+								if (P.flags & 4096) {   // two N=128 halves per product
+									const uint32_t idh = idesc_tf32(UMMA_M, BN / 2, 0, P.b_kmajor ? 0 : 1);
+									for (int hh = 0; hh < 2; hh++) {
+										mma_tf32_ts<CG>(d_tmem + hh * (BN / 2), a_t, dBb, idh, first);
+										mma_tf32_ts<CG>(d_tmem + hh * (BN / 2), a_t + 32, dBs, idh, 1u);
+										mma_tf32_ts<CG>(d_tmem + hh * (BN / 2), a_t, dBb, idh, 1u);
+									}
+								} else {
+									// bits 13..15: experimental N = 256 - 16*x (timing only)
+									const int nexp = BN - 16 * ((P.flags >> 13) & 7);
+									const uint32_t idn = idesc_tf32(UMMA_M, nexp, 0, P.b_kmajor ? 0 : 1);
+									mma_tf32_ts<CG>(d_tmem, a_t, dBb, idn, first);
+									mma_tf32_ts<CG>(d_tmem, a_t + 32, dBs, idn, 1u);
+									mma_tf32_ts<CG>(d_tmem, a_t, dBb, idn, 1u);
+								}
+								continue;
+							}
 							mma_tf32_ss<CG>(d_tmem, dAs, dBb, idesc, first);
 							if (P.flags & 1) {
 								mma_tf32_ss_coll<CG, 1>(d_tmem, dAb, dBs, idesc, 1u);
@@ -360,7 +379,9 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		const int e = warp - (4 + 4 * XF_GROUPS);
 		const int q = e & 3;        // TMEM lane quarter (must equal warp % 4)
 		const int h = e >> 2;       // column half
-		const float alpha = P.alpha, beta = P.beta;
+		const float alpha = P.alpha;
+		const float bs = P.beta / P.alpha;                 // alpha != 0 here (alpha == 0 never reaches a GEMM kernel)
+		const bool preload_c = P.beta != 0.f && fabsf(bs) < 1e18f && fabsf(bs) > 1e-18f;
 		int ci = 0;
 		long long w_tf = 0, t_drain = 0, t_store = 0; const long long t_begin = clock64();
 		int nt = 0;
@@ -368,10 +389,32 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			int tm, tn;
 			decode_tile(tile, P.tiles_m, P.tiles_n, tm, tn);
 			float acc[NG][32];
+			const long long row = (long long)tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane;
+			float *crow = P.C + row * P.ldc;
+			// beta != 0: the old C is folded in UP FRONT -- the running sums start at (beta/alpha)*C, loaded while the
+			// tile's first MMAs run and the epilogue warps would idle anyway -- so the tile end is store-only and
+			// never stalls the accumulator hand-over on a global-load round trip.
+			if (preload_c && row < P.M) {
 #pragma unroll
-			for (int g = 0; g < NG; g++)
+				for (int g = 0; g < NG; g++) {
+					const long long col0 = (long long)tn * BN + h * (BN / 2) + g * 32;
+					if (P.vecC && col0 + 31 < P.N) {
 #pragma unroll
-				for (int i = 0; i < 32; i++) acc[g][i] = 0.f;
+						for (int i = 0; i < 32; i += 4) {
+							const float4 cv = *reinterpret_cast<const float4 *>(crow + col0 + i);
+							acc[g][i + 0] = bs * cv.x; acc[g][i + 1] = bs * cv.y; acc[g][i + 2] = bs * cv.z; acc[g][i + 3] = bs * cv.w;
+						}
+					} else {
+#pragma unroll
+						for (int i = 0; i < 32; i++) acc[g][i] = (col0 + i < P.N) ? bs * crow[col0 + i] : 0.f;
+					}
+				}
+			} else {
+#pragma unroll
+				for (int g = 0; g < NG; g++)
+#pragma unroll
+					for (int i = 0; i < 32; i++) acc[g][i] = 0.f;
+			}
 			for (int kb0 = 0; kb0 < nkb; kb0 += kc, ci++) {
 				const int ab = ci & 1;
 				const uint32_t aph = (ci >> 1) & 1;
@@ -397,9 +440,8 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			}
 			const long long ts0 = clock64();
 			// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
-			const long long row = (long long)tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane;
+			const float beta = preload_c ? 0.f : P.beta;   // already folded into acc when preloaded
 			if (row < P.M && !(P.flags & 16)) {
-				float *crow = P.C + row * P.ldc;
 #pragma unroll
 				for (int g = 0; g < NG; g++) {
 					const long long col0 = (long long)tn * BN + h * (BN / 2) + g * 32;

@@ -103,6 +103,18 @@ template <int CG> __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, u
 		             "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
 		             ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (K-major only): D[tmem] (+)= A[tmem] * B[smem desc]
+template <int CG> __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+	if (CG == 1)
+		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+		             "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+		             ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+	else
+		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+		             "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+		             ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // Same with the A-operand collector: KEEP = latch this A in the tensor core's collector after reading it from
 // shared memory (.collector::a::fill), REUSE = take A from the collector instead of shared memory and release it
 // (.collector::a::lastuse).  Lets big*small and big*big of one k-step share a single shared-memory read of A_big.

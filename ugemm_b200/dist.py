@@ -14,6 +14,14 @@ step and no reduction:
     issued asynchronously for all slabs up front; the local GEMM of slab t (beta = 1 after the first slab) starts
     as soon as ITS two broadcasts have landed, so panel distribution overlaps the tensor-core work slab by slab.
 
+Two transports move the slabs (both over NVLink, selected by the ops object):
+  * "nccl": `torch.distributed.broadcast` from the owner inside the grid-row / grid-column communicator.  NCCL's
+    CTAs need SMs, and a persistent K1 CTA fills an SM, so a few SMs are left free while broadcasts are in flight
+    (sgemm_cuda_set_sm_limit) and NCCL is asked for few CTAs (NCCL_MAX_CTAS).
+  * "p2p": every rank exports its owned-slab buffer as a CUDA IPC handle once; receivers PULL each slab with a
+    stream-ordered peer copy, which runs on the copy engines and takes no SM from the GEMM.  NCCL is then only used
+    for the handle exchange and for two one-element all-reduces per step that order the pulls across processes.
+
 The local GEMM is the C-ABI device entry point (sgemm_cuda_dev); this module contains no arithmetic.  The
 `ops` object isolates everything device-specific so the same schedule runs on CPU tensors under gloo in tests
 (tests/test_dist_cpu.py injects its own CPU-checker ops object there; the product default is CudaOps).
@@ -119,6 +127,35 @@ class CudaOps:
         self.torch.cuda.synchronize()
 
 
+class RawBuf:
+    """A window of a ugemm_cuda_malloc'ed allocation (what the p2p transport shares between processes)."""
+
+    def __init__(self, ptr, n):
+        self.ptr, self.n = ptr, n
+
+    def data_ptr(self):
+        return self.ptr
+
+
+class CudaP2POps(CudaOps):
+    """Copy-engine pull transport: buffers come from the C ABI (cudaMalloc) so they can be IPC-exported."""
+    transport = "p2p"
+
+    def __init__(self, mode="auto"):
+        super().__init__(mode, comm_sms=0)
+        self.copy_stream = self.torch.cuda.Stream()
+        self._keep = []
+
+    def alloc(self, n):
+        buf = self.be.DeviceBuffer(n)
+        self._keep.append(buf)
+        return buf
+
+    def empty(self, n):
+        b = self.alloc(n)
+        return RawBuf(b.ptr, n)
+
+
 class ShardedGemm:
     """C_ij = A_i * B_j on this rank, with slab-wise owner-rooted panel broadcast overlapped with compute."""
 
@@ -139,9 +176,61 @@ class ShardedGemm:
                 g = dist.new_group([ii * p.pc + jj for ii in range(p.pr)])
                 if jj == p.j:
                     self.col_group = g
-        self.a = [ops.empty(p.mloc * p.kw) for _ in range(p.L)]
-        self.b = [ops.empty(p.kw * p.nloc) for _ in range(p.L)]
+        self.transport = getattr(ops, "transport", "nccl") if p.world > 1 else "local"
+        if self.transport == "p2p":
+            self._init_p2p()
+        else:
+            self.a = [ops.empty(p.mloc * p.kw) for _ in range(p.L)]
+            self.b = [ops.empty(p.kw * p.nloc) for _ in range(p.L)]
         self.c = ops.empty(p.mloc * p.nloc)
+
+    def _init_p2p(self):
+        """Owned slabs live in ONE exported allocation; peers' allocations are mapped once."""
+        p, ops, be = self.plan, self.ops, self.ops.be
+        an, bn = p.mloc * p.kw, p.kw * p.nloc
+        table, off = {}, 0
+        for t in range(p.L):
+            if p.a_owner(t) == p.rank:
+                table[("a", t)] = off
+                off += an
+            if p.b_owner(t) == p.rank:
+                table[("b", t)] = off
+                off += bn
+        own = ops.alloc(max(off, 1))
+        gathered = [None] * p.world
+        self.dist.all_gather_object(gathered, (be.ipc_export(own.ptr), table))
+        peers = (set(p.row_ranks) | set(p.col_ranks)) - {p.rank}
+        self._peer_base = {r: be.ipc_import(gathered[r][0]) for r in sorted(peers)}
+        self.a, self.b, self._pull = [], [], []
+        for t in range(p.L):
+            for kind, owner, n, lst in (("a", p.a_owner(t), an, self.a), ("b", p.b_owner(t), bn, self.b)):
+                if owner == p.rank:
+                    lst.append(RawBuf(own.ptr + 4 * table[(kind, t)], n))
+                else:
+                    dst = ops.empty(n)
+                    lst.append(dst)
+                    self._pull.append((t, dst.ptr, self._peer_base[owner] + 4 * gathered[owner][1][(kind, t)], 4 * n))
+        self._flag = ops.torch.zeros(1, device=ops.device)
+        self._events = [ops.torch.cuda.Event() for _ in range(p.L)]
+
+    def _run_p2p(self):
+        p, ops, torch = self.plan, self.ops, self.ops.torch
+        cur = torch.cuda.current_stream()
+        self.dist.all_reduce(self._flag)            # stream-ordered: every owner's slabs are final before anyone pulls
+        ops.copy_stream.wait_stream(cur)
+        cs = ops.copy_stream.cuda_stream
+        pulls = {}
+        for t, dst, src, nbytes in self._pull:
+            pulls.setdefault(t, []).append((dst, src, nbytes))
+        for t in range(p.L):
+            for dst, src, nbytes in pulls.get(t, ()):
+                ops.be.memcpy_async(dst, src, nbytes, cs)
+            self._events[t].record(ops.copy_stream)
+        for t in range(p.L):
+            cur.wait_event(self._events[t])
+            ops.gemm(p.mloc, p.nloc, p.kw, self.a[t], p.kw, self.b[t], p.nloc, 0.0 if t == 0 else 1.0, self.c, p.nloc)
+        self.dist.all_reduce(self._flag)            # nobody overwrites its owned slabs while a peer may still be pulling
+        return self.c
 
     def generate_owned(self, seed_a, seed_b, lo=0.0, hi=1.0):
         """Each rank synthesises ONLY the slabs it owns, as windows of the global A (M x K) and B (K x N) streams."""
@@ -159,6 +248,8 @@ class ShardedGemm:
         """Distribution (optional: panels may already be resident from a previous run) + local GEMMs.
         Asynchronous w.r.t. the host on the GPU path; callers bracket it with events / synchronize."""
         p = self.plan
+        if distribute and self.transport == "p2p":
+            return self._run_p2p()
         works = [None] * p.L
         if distribute and p.world > 1:
             for t in range(p.L):
