@@ -373,7 +373,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None] + list(WORKLOADS))
-    ap.add_argument("--dist", default=os.environ.get("UGEMM_BENCH_DIST", "nccl"), choices=["nccl", "p2p"],
+    ap.add_argument("--dist", default=os.environ.get("UGEMM_BENCH_DIST", "p2p"), choices=["nccl", "p2p"],
                     help="panel transport for --gpus N > 1: NCCL broadcast or copy-engine peer pull")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
