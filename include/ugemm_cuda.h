@@ -133,6 +133,26 @@ void ugemm_fill_uniform_host_2d(float *x, size_t rows, size_t cols, size_t ld, u
 int  ugemm_fill_uniform_dev_2d(float *dx, size_t rows, size_t cols, size_t ld, uint64_t seed, uint64_t offset,
                                uint64_t gld, float lo, float hi, void *stream);
 
+/* ---- convolution callers of the GEMM (the producer of BASELINE config 4's big operand).
+ * Layouts are the reference's: planar C x H x W image, weights ch x (ich*k*k) row-major with column index
+ * c*k*k + ki*k + kj, column matrix (ich*k*k) x (Ho*Wo), output ch x (Ho*Wo); square kernel / pad / stride.
+ *   im2col_cuda            replaces the OpenCL `im2col` kernel + ocl_im2col (sgemm_ocl1.h:81-119,255-270) and the CPU
+ *                          im2col (sgemm_gl1.h:166-190); host pointers, blocking.
+ *   convolution_cuda       replaces ocl_convolution (sgemm_ocl1.h:271-300): outputs = weights . im2col(inputs).
+ *   convolution_cuda_LReLU replaces gl_convolution_LReLU (sgemm_gl1.h:192-218) / the disabled ocl_convolution_LReLU
+ *                          (sgemm_ocl1.h:301-338): + bias[ch] and LeakyReLU(0.1), FUSED into the GEMM epilogue instead of
+ *                          the reference's separate host loop (sgemm_gl1.h:210-217).
+ *   *_dev                  device pointers, asynchronous; d_workspace holds ich*k*k*Ho*Wo floats; d_bias may be NULL;
+ *                          slope = 1 means no activation.  Returns 0 on success. */
+void im2col_cuda(const float *im, int channels, int height, int width, int k, int pad, int stride, float *col);
+int  im2col_cuda_dev(const float *d_im, int channels, int height, int width, int k, int pad, int stride, float *d_col, void *stream);
+void convolution_cuda(const float *inputs, int ich, int w, int h, const float *weights, int k, int pad, int stride,
+                      float *outputs, int ch);
+void convolution_cuda_LReLU(const float *inputs, int ich, int w, int h, const float *weights, int k, int pad, int stride,
+                            float *outputs, int ch, const float *bias);
+int  convolution_cuda_dev(int mode, void *stream, const float *d_inputs, int ich, int w, int h, const float *d_weights, int k,
+                          int pad, int stride, float *d_outputs, int ch, const float *d_bias, float slope, float *d_workspace);
+
 /* ---- hardware probe used by tests/DESIGN.md: runs one 128 x 16 x (8*ksteps) TF32 tcgen05 product
  * chain on raw fp32 bit patterns and returns the 128x16 fp32 accumulator, so the rounding behaviour of
  * the tensor core (operand truncation, accumulator rounding) can be pinned.  A: 128 x 8*ksteps row-major,

@@ -47,6 +47,11 @@ def oracle():
         lib.oracle_fill_uniform.argtypes = [_f32p, C.c_size_t, C.c_uint64, C.c_float, C.c_float]
         lib.oracle_fill_uniform.restype = None
         lib.oracle_max_threads.restype = C.c_int
+        lib.oracle_im2col.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
+        lib.oracle_im2col.restype = None
+        lib.oracle_convolution.argtypes = [C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p,
+                                           C.c_int, C.c_void_p, C.c_float, _f32p]
+        lib.oracle_convolution.restype = None
         _oracle = lib
     return _oracle
 

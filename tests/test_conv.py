@@ -1,0 +1,101 @@
+"""Convolution callers of the GEMM: im2col and convolution(+bias+LeakyReLU).
+
+CPU part: the oracle's restatement of the reference's im2col / gl_convolution_LReLU (sgemm_gl1.h:166-218) is pinned
+against a definition-level direct convolution (the headers that hold the reference versions need GLFW/OpenCL and do
+not compile here).  GPU part (-m gpu): the CUDA entry points against that oracle, bit-exact for im2col (pure data
+movement), normwise relerr <= 1e-5 for the convolutions."""
+import numpy as np
+import pytest
+
+import _oracle as O
+
+GEOMS = [  # ich, h, w, k, pad, stride, ch
+    (1, 5, 5, 3, 1, 1, 2),
+    (3, 8, 10, 3, 0, 1, 4),
+    (4, 9, 7, 2, 1, 2, 5),
+    (8, 14, 14, 3, 1, 1, 16),
+    (2, 6, 6, 5, 2, 1, 3),
+    (3, 12, 9, 4, 2, 2, 6),
+]
+
+
+def direct_conv(x, wgt, k, pad, stride):
+    """outputs[co, io, jo] = sum_{c,ki,kj} wgt[co, c, ki, kj] * x_padded[c, io*stride+ki, jo*stride+kj]   (fp64)"""
+    ich, h, w = x.shape
+    ch = wgt.shape[0]
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    xp = np.zeros((ich, h + 2 * pad, w + 2 * pad))
+    xp[:, pad:pad + h, pad:pad + w] = x
+    out = np.zeros((ch, ho, wo))
+    for ki in range(k):
+        for kj in range(k):
+            patch = xp[:, ki:ki + stride * ho:stride, kj:kj + stride * wo:stride]      # ich, ho, wo
+            out += np.einsum("oc,chw->ohw", wgt[:, :, ki, kj].astype(np.float64), patch)
+    return out
+
+
+def make_conv(ich, h, w, k, ch, seed):
+    x = O.fill_uniform(ich * h * w, seed, -0.5, 0.5)
+    wgt = O.fill_uniform(ch * ich * k * k, seed + 1, -0.5, 0.5)
+    bias = O.fill_uniform(ch, seed + 2, -0.5, 0.5)
+    return x, wgt, bias
+
+
+def oracle_conv(x, ich, w, h, wgt, k, pad, stride, ch, bias, slope):
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    out = np.zeros(ch * ho * wo, np.float32)
+    ws = np.zeros(ich * k * k * ho * wo, np.float32)
+    O.oracle().oracle_convolution(2, x, ich, w, h, wgt, k, pad, stride, out, ch,
+                                  None if bias is None else bias.ctypes.data, slope, ws)
+    return out, ws
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_oracle_im2col_and_convolution_match_the_definition(geom):
+    ich, h, w, k, pad, stride, ch = geom
+    x, wgt, bias = make_conv(ich, h, w, k, ch, seed=50)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    out, col = oracle_conv(x, ich, w, h, wgt, k, pad, stride, ch, None, 1.0)
+    # im2col: every entry is either an image pixel or a padding zero, at the documented position
+    xp = np.zeros((ich, h + 2 * pad, w + 2 * pad), np.float32)
+    xp[:, pad:pad + h, pad:pad + w] = x.reshape(ich, h, w)
+    colm = col.reshape(ich, k, k, ho, wo)
+    for ki in range(k):
+        for kj in range(k):
+            assert np.array_equal(colm[:, ki, kj], xp[:, ki:ki + stride * ho:stride, kj:kj + stride * wo:stride])
+    ref = direct_conv(x.reshape(ich, h, w), wgt.reshape(ch, ich, k, k), k, pad, stride).reshape(-1)
+    assert np.linalg.norm(out - ref) / np.linalg.norm(ref) <= 1e-6
+    # + bias + LeakyReLU(0.1), sgemm_gl1.h:210-217
+    out2, _ = oracle_conv(x, ich, w, h, wgt, k, pad, stride, ch, bias, 0.1)
+    r2 = ref.reshape(ch, -1) + bias[:, None].astype(np.float64)
+    r2 = np.where(r2 > 0, r2, 0.1 * r2).reshape(-1)
+    assert np.linalg.norm(out2 - r2) / np.linalg.norm(r2) <= 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", GEOMS + [(128, 56, 56, 3, 1, 1, 256), (64, 57, 41, 3, 1, 2, 96)])
+def test_gpu_im2col_and_convolution(u, geom):
+    """(128,56,56,3,1,1,256) is one image of BASELINE config 4: M=256, N=3136, K=1152 -> K1 (3xTF32)."""
+    ich, h, w, k, pad, stride, ch = geom
+    x, wgt, bias = make_conv(ich, h, w, k, ch, seed=70)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    want, want_col = oracle_conv(x, ich, w, h, wgt, k, pad, stride, ch, None, 1.0)
+    col = np.full(ich * k * k * ho * wo, np.nan, np.float32)
+    u.im2col_cuda(x, ich, h, w, k, pad, stride, col)
+    assert np.array_equal(col, want_col), "im2col is pure data movement: must be bit-exact"
+    out = np.full(ch * ho * wo, np.nan, np.float32)
+    u.convolution_cuda(x, ich, w, h, wgt, k, pad, stride, out, ch)
+    e = np.linalg.norm(out.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64))
+    assert e <= 1e-5, e
+    big = ch >= 128 and ho * wo >= 128 and (ho * wo) % 4 == 0 and (ich * k * k) % 4 == 0 and ich * k * k >= 32
+    assert u.last_kernel() == ("3xtf32" if big else "simt")
+    want2, _ = oracle_conv(x, ich, w, h, wgt, k, pad, stride, ch, bias, 0.1)
+    out2 = np.full(ch * ho * wo, np.nan, np.float32)
+    u.convolution_cuda_LReLU(x, ich, w, h, wgt, k, pad, stride, out2, ch, bias)
+    e2 = np.linalg.norm(out2.astype(np.float64) - want2) / np.linalg.norm(want2.astype(np.float64))
+    assert e2 <= 1e-5, e2
+    # the activation really happened: negatives are scaled by 0.1 relative to the plain result + bias
+    plain = out.reshape(ch, -1) + bias[:, None]
+    neg = plain < -1e-3
+    if neg.any():
+        assert np.allclose(out2.reshape(ch, -1)[neg], 0.1 * plain[neg], rtol=1e-3, atol=1e-5)

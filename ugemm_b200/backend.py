@@ -103,6 +103,17 @@ def lib():
     L.ugemm_fill_uniform_dev_2d.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, C.c_uint64,
                                             C.c_uint64, C.c_float, C.c_float, C.c_void_p]
     L.ugemm_fill_uniform_dev_2d.restype = C.c_int
+    L.im2col_cuda.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.im2col_cuda.restype = None
+    L.im2col_cuda_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.im2col_cuda_dev.restype = C.c_int
+    conv10 = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.convolution_cuda.argtypes = conv10
+    L.convolution_cuda.restype = None
+    L.convolution_cuda_LReLU.argtypes = conv10 + [C.c_void_p]
+    L.convolution_cuda_LReLU.restype = None
+    L.convolution_cuda_dev.argtypes = [C.c_int, C.c_void_p] + conv10 + [C.c_void_p, C.c_float, C.c_void_p]
+    L.convolution_cuda_dev.restype = C.c_int
     L.ugemm_cuda_probe_tf32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.ugemm_cuda_probe_tf32.restype = C.c_int
     _lib = L
@@ -117,7 +128,8 @@ EXPORTED_SYMBOLS = [
     "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
     "ugemm_cuda_memcpy_async", "ugemm_cuda_ipc_export", "ugemm_cuda_ipc_import", "ugemm_cuda_ipc_close",
     "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
-    "ugemm_cuda_probe_tf32",
+    "ugemm_cuda_probe_tf32", "im2col_cuda", "im2col_cuda_dev", "convolution_cuda", "convolution_cuda_LReLU",
+    "convolution_cuda_dev",
 ]
 
 
@@ -317,6 +329,30 @@ def probe_tf32(A, B, ksteps):
         check()
         raise UgemmCudaError("probe failed")
     return D
+
+
+# ---- convolution callers (argument order of ocl_convolution, sgemm_ocl1.h:271, and gl_convolution_LReLU, sgemm_gl1.h:192)
+def im2col_cuda(im, channels, height, width, k, pad, stride, col):
+    lib().im2col_cuda(_ptr(im), channels, height, width, k, pad, stride, _ptr(col))
+    check()
+
+
+def convolution_cuda(inputs, ich, w, h, weights, k, pad, stride, outputs, ch):
+    lib().convolution_cuda(_ptr(inputs), ich, w, h, _ptr(weights), k, pad, stride, _ptr(outputs), ch)
+    check()
+
+
+def convolution_cuda_LReLU(inputs, ich, w, h, weights, k, pad, stride, outputs, ch, bias):
+    lib().convolution_cuda_LReLU(_ptr(inputs), ich, w, h, _ptr(weights), k, pad, stride, _ptr(outputs), ch, _ptr(bias))
+    check()
+
+
+def convolution_cuda_dev(mode, stream, d_inputs, ich, w, h, d_weights, k, pad, stride, d_outputs, ch, d_bias, slope, d_workspace):
+    rc = lib().convolution_cuda_dev(_MODES[mode], C.c_void_p(stream or 0), _ptr(d_inputs), ich, w, h, _ptr(d_weights), k, pad, stride,
+                                    _ptr(d_outputs), ch, _ptr(d_bias), slope, _ptr(d_workspace))
+    if rc:
+        check()
+        raise UgemmCudaError("convolution_cuda_dev failed")
 
 
 # ---- the macro API of the reference's GPU harness (sgemm_test.c:19-33): tight row-major, no ld ----------

@@ -32,7 +32,7 @@ struct State {
 	// staging arena of the host-pointer entry points (one buffer like the OpenCL backend's `gm`)
 	char *arena = nullptr;
 	size_t arena_bytes = 0;
-	K1Tuning tuning = {4, 0, 2, 0};   // promote every 4 k-blocks (128 k), truncation split, 2-CTA pairs
+	K1Tuning tuning = {4, 0, 2, 1};   // promote every 4 k-blocks (128 k), truncation split, 2-CTA pairs
 	int last_kernel = 0;
 	int sm_limit = 0;                // 0 = all SMs; otherwise K1's persistent grid is capped (leaves SMs to NCCL)
 	unsigned long long launches = 0;
@@ -315,7 +315,7 @@ int sgemm_cuda_init(int device, size_t arena_bytes)
 		CU_TRY(cudaEventCreateWithFlags(&g.ev_up[i], cudaEventDisableTiming), "cudaEventCreate");
 		CU_TRY(cudaEventCreateWithFlags(&g.ev_done[i], cudaEventDisableTiming), "cudaEventCreate");
 	}
-	if (const char *f = getenv("UGEMM_K1_FLAGS")) g.tuning.flags = atoi(f);   // debug / ablation, see common.cuh
+	if (const char *f = getenv("UGEMM_K1_FLAGS")) g.tuning.flags = atoi(f);   // overrides the default (bit0 = A collector on)   // debug / ablation, see common.cuh
 	g.ready = true;
 	if (arena_bytes && ensure_arena(arena_bytes)) { g.ready = false; return 1; }
 	return 0;
@@ -564,6 +564,81 @@ int ugemm_fill_uniform_dev_2d(float *dx, size_t rows, size_t cols, size_t ld, ui
 	g.launches++;
 	return 0;
 }
+
+// ---- convolution callers of the GEMM -------------------------------------------------
+int im2col_cuda_dev(const float *d_im, int channels, int height, int width, int k, int pad, int stride, float *d_col, void *stream)
+{
+	if (ensure_init()) return 1;
+	if (channels < 0 || height <= 0 || width <= 0 || k <= 0 || stride <= 0 || pad < 0 || height + 2 * pad < k || width + 2 * pad < k) {
+		set_error("im2col: bad geometry (C=%d H=%d W=%d k=%d pad=%d stride=%d)", channels, height, width, k, pad, stride);
+		return 1;
+	}
+	CU_TRY(launch_im2col(d_im, channels, height, width, k, pad, stride, d_col, stream ? static_cast<cudaStream_t>(stream) : g.stream), "im2col launch");
+	g.launches++;
+	return 0;
+}
+
+int convolution_cuda_dev(int mode, void *stream, const float *d_inputs, int ich, int w, int h, const float *d_weights, int k,
+                         int pad, int stride, float *d_outputs, int ch, const float *d_bias, float slope, float *d_workspace)
+{
+	if (im2col_cuda_dev(d_inputs, ich, h, w, k, pad, stride, d_workspace, stream)) return 1;
+	const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+	const long long npix = (long long)ho * wo, kk = (long long)ich * k * k;
+	if (npix > 0x7fffffffLL || kk > 0x7fffffffLL) { set_error("convolution: problem too large for int dimensions"); return 1; }
+	Problem p;
+	if (normalise('R', 'N', 'N', ch, (int)npix, (int)kk, 1.f, d_weights, (int)kk, d_workspace, (int)npix, 0.f, d_outputs, (int)npix, &p)) return 1;
+	p.bias = d_bias;
+	p.slope = slope;
+	return run_dev(mode, stream ? static_cast<cudaStream_t>(stream) : g.stream, p);
+}
+
+static void conv_host(const float *inputs, int ich, int w, int h, const float *weights, int k, int pad, int stride, float *outputs,
+                      int ch, const float *bias, float slope)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (ensure_init()) return;
+	if (ich <= 0 || ch <= 0 || k <= 0 || stride <= 0 || pad < 0 || h + 2 * pad < k || w + 2 * pad < k) { set_error("convolution: bad geometry"); return; }
+	const long long ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1, npix = ho * wo, kk = (long long)ich * k * k;
+	const size_t in_b = (size_t)ich * h * w * 4, w_b = (size_t)ch * kk * 4, col_b = (size_t)kk * npix * 4, out_b = (size_t)ch * npix * 4, bias_b = bias ? (size_t)ch * 4 : 0;
+	const size_t o_in = 0, o_w = align_up(o_in + in_b, 256), o_col = align_up(o_w + w_b, 256), o_out = align_up(o_col + col_b, 256), o_bias = align_up(o_out + out_b, 256);
+	if (ensure_arena(o_bias + bias_b + 256)) return;
+	float *d_in = reinterpret_cast<float *>(g.arena + o_in), *d_w = reinterpret_cast<float *>(g.arena + o_w);
+	float *d_col = reinterpret_cast<float *>(g.arena + o_col), *d_out = reinterpret_cast<float *>(g.arena + o_out);
+	float *d_bias = bias ? reinterpret_cast<float *>(g.arena + o_bias) : nullptr;
+	cudaError_t e = cudaMemcpyAsync(d_in, inputs, in_b, cudaMemcpyHostToDevice, g.stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_w, weights, w_b, cudaMemcpyHostToDevice, g.stream);
+	if (e == cudaSuccess && bias) e = cudaMemcpyAsync(d_bias, bias, bias_b, cudaMemcpyHostToDevice, g.stream);
+	if (e != cudaSuccess) { set_error("convolution H2D failed: %s", cudaGetErrorString(e)); return; }
+	if (convolution_cuda_dev(UGEMM_MODE_AUTO, g.stream, d_in, ich, w, h, d_w, k, pad, stride, d_out, ch, d_bias, slope, d_col)) return;
+	e = cudaMemcpyAsync(outputs, d_out, out_b, cudaMemcpyDeviceToHost, g.stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+	if (e != cudaSuccess) set_error("convolution failed: %s", cudaGetErrorString(e));
+}
+
+void im2col_cuda(const float *im, int channels, int height, int width, int k, int pad, int stride, float *col)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (ensure_init()) return;
+	if (k <= 0 || stride <= 0 || pad < 0 || height + 2 * pad < k || width + 2 * pad < k) { set_error("im2col: bad geometry"); return; }
+	const long long ho = (height + 2 * pad - k) / stride + 1, wo = (width + 2 * pad - k) / stride + 1;
+	const size_t in_b = (size_t)channels * height * width * 4, col_b = (size_t)channels * k * k * ho * wo * 4;
+	const size_t o_col = align_up(in_b, 256);
+	if (ensure_arena(o_col + col_b)) return;
+	float *d_in = reinterpret_cast<float *>(g.arena), *d_col = reinterpret_cast<float *>(g.arena + o_col);
+	cudaError_t e = cudaMemcpyAsync(d_in, im, in_b, cudaMemcpyHostToDevice, g.stream);
+	if (e != cudaSuccess) { set_error("im2col H2D failed: %s", cudaGetErrorString(e)); return; }
+	if (im2col_cuda_dev(d_in, channels, height, width, k, pad, stride, d_col, g.stream)) return;
+	e = cudaMemcpyAsync(col, d_col, col_b, cudaMemcpyDeviceToHost, g.stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+	if (e != cudaSuccess) set_error("im2col failed: %s", cudaGetErrorString(e));
+}
+
+void convolution_cuda(const float *inputs, int ich, int w, int h, const float *weights, int k, int pad, int stride, float *outputs, int ch)
+{ conv_host(inputs, ich, w, h, weights, k, pad, stride, outputs, ch, nullptr, 1.f); }
+
+void convolution_cuda_LReLU(const float *inputs, int ich, int w, int h, const float *weights, int k, int pad, int stride, float *outputs,
+                            int ch, const float *bias)
+{ conv_host(inputs, ich, w, h, weights, k, pad, stride, outputs, ch, bias, 0.1f); }
 
 int ugemm_cuda_probe_tf32(const float *A, const float *B, float *D, int ksteps)
 {

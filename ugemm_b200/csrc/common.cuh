@@ -15,6 +15,10 @@ struct Problem {
 	const float *A; long long lda; bool a_kmajor;
 	const float *B; long long ldb; bool b_kmajor;
 	float *C; long long ldc;
+	// optional fused epilogue of the convolution callers (sgemm_gl1.h:210-217): out = act(alpha*acc + beta*C + bias[m]),
+	// act(x) = x > 0 ? x : slope*x.  bias == nullptr and slope == 1 (the default) mean a plain GEMM.
+	const float *bias = nullptr;
+	float slope = 1.f;
 };
 
 // flags: bit0 = share one shared-memory read of A_big between big*small and big*big (A collector);
@@ -30,6 +34,8 @@ bool        k1_eligible(const Problem &p, const char **why);
 cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count);
 // C <- beta*C over the M x N region (alpha==0 or K==0 path)
 cudaError_t launch_scale_c(const Problem &p, cudaStream_t stream);
+// im2col of a planar C x H x W image into the (C*k*k) x (Ho*Wo) column matrix (k2_simt.cu)
+cudaError_t launch_im2col(const float *im, int channels, int height, int width, int k, int pad, int stride, float *col, cudaStream_t stream);
 // probe (k1_tcgen05.cu)
 cudaError_t launch_probe_tf32(const float *dA, const float *dB, float *dD, int ksteps, cudaStream_t stream);
 // last diagnostic record written by a K1 watchdog (host-mapped memory), 0 if none

@@ -52,6 +52,8 @@ struct K1Params {
 	float alpha, beta;
 	float *C;
 	long long ldc;
+	const float *bias;
+	float slope;
 	int a_kmajor, b_kmajor;
 	int tiles_m, tiles_n, num_tiles;
 	int num_k_blocks, kc_blocks, split, vecC, flags;
@@ -442,6 +444,10 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
 			const float beta = preload_c ? 0.f : P.beta;   // already folded into acc when preloaded
 			if (row < P.M && !(P.flags & 16)) {
+				const float slope = P.slope;
+				const bool post = P.bias != nullptr || slope != 1.f;   // bias[row] + LeakyReLU (convolution callers)
+				const float bm = P.bias ? __ldg(P.bias + row) : 0.f;
+				auto act = [&](float x) { x += bm; return x > 0.f ? x : x * slope; };
 #pragma unroll
 				for (int g = 0; g < NG; g++) {
 					const long long col0 = (long long)tn * BN + h * (BN / 2) + g * 32;
@@ -458,6 +464,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 								o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1];
 								o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
 							}
+							if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
 							*cp = o;
 						}
 					} else {
@@ -466,7 +473,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 							if (col0 + i < P.N) {
 								float o = alpha * acc[g][i];
 								if (beta != 0.f) o = fmaf(alpha, acc[g][i], beta * crow[col0 + i]);
-								crow[col0 + i] = o;
+								crow[col0 + i] = post ? act(o) : o;
 							}
 						}
 					}
@@ -592,6 +599,7 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	if (!make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.b_kmajor)) return cudaErrorInvalidValue;
 	K1Params P;
 	P.M = p.M; P.N = p.N; P.K = p.K; P.alpha = p.alpha; P.beta = p.beta; P.C = p.C; P.ldc = p.ldc;
+	P.bias = p.bias; P.slope = p.slope;
 	P.a_kmajor = p.a_kmajor; P.b_kmajor = p.b_kmajor;
 	const int tile_m = 128 * CG, tile_n = 128 * CG;
 	P.tiles_m = (p.M + tile_m - 1) / tile_m;

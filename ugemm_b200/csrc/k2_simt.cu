@@ -148,12 +148,15 @@ k2_simt_kernel(const Problem p, const int tiles_m, const int tiles_n, const bool
 	}
 
 	// fused epilogue: C = alpha*acc + beta*C (C never read when beta == 0), ld padding never touched
-	const float alpha = p.alpha, beta = p.beta;
+	const float alpha = p.alpha, beta = p.beta, slope = p.slope;
+	const bool post = p.bias != nullptr || slope != 1.f;   // bias[m] + LeakyReLU of the convolution callers
 #pragma unroll
 	for (int i = 0; i < TM; i++) {
 		const long long m = m0 + (i < HM ? ty * HM + i : BM / 2 + ty * HM + (i - HM));
 		if (m >= p.M) continue;
 		float *crow = p.C + m * p.ldc;
+		const float bm = p.bias ? __ldg(p.bias + m) : 0.f;
+		auto act = [&](float x) { x += bm; return x > 0.f ? x : x * slope; };
 #pragma unroll
 		for (int h = 0; h < 2; h++) {
 			const long long n = n0 + h * (BN / 2) + tx * HN;
@@ -170,6 +173,7 @@ k2_simt_kernel(const Problem p, const int tiles_m, const int tiles_n, const bool
 					o.x = alpha * acc[i][h * HN + 0]; o.y = alpha * acc[i][h * HN + 1];
 					o.z = alpha * acc[i][h * HN + 2]; o.w = alpha * acc[i][h * HN + 3];
 				}
+				if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
 				*cp = o;
 			} else {
 #pragma unroll
@@ -177,7 +181,7 @@ k2_simt_kernel(const Problem p, const int tiles_m, const int tiles_n, const bool
 					if (n + j < p.N) {
 						float v = alpha * acc[i][h * HN + j];
 						if (beta != 0.f) v = fmaf(alpha, acc[i][h * HN + j], beta * crow[n + j]);
-						crow[n + j] = v;
+						crow[n + j] = post ? act(v) : v;
 					}
 				}
 			}
@@ -193,6 +197,23 @@ __global__ void scale_c_kernel(float *C, long long ldc, int M, int N, float beta
 	for (; m < M; m += gridDim.y) {
 		float *c = C + m * ldc + n;
 		*c = (beta == 0.f) ? 0.f : beta * *c;
+	}
+}
+
+// col[(c*k*k + ki*k + kj) * (Ho*Wo) + (io*Wo + jo)] = im[c][io*stride - pad + ki][jo*stride - pad + kj] (0 outside the image):
+// the layout of the reference's im2col (sgemm_ocl1.h:81-119, sgemm_gl1.h:166-190).  One thread per column-matrix
+// element, pixels fastest, so both the writes and (for stride 1) the reads are coalesced; HBM-bound by the
+// 4*C*k*k*Ho*Wo bytes it writes.
+__global__ void im2col_kernel(const float *__restrict__ im, int channels, int height, int width, int k, int pad, int stride,
+                              int ho, int wo, float *__restrict__ col)
+{
+	const long long npix = (long long)ho * wo, total = (long long)channels * k * k * npix;
+	for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+		const long long row = idx / npix, pix = idx - row * npix;
+		const int kj = (int)(row % k), ki = (int)((row / k) % k), c = (int)(row / ((long long)k * k));
+		const int io = (int)(pix / wo), jo = (int)(pix - (long long)io * wo);
+		const int i = io * stride - pad + ki, j = jo * stride - pad + kj;
+		col[idx] = (i >= 0 && j >= 0 && i < height && j < width) ? __ldg(im + ((long long)c * height + i) * width + j) : 0.f;
 	}
 }
 
@@ -224,6 +245,17 @@ cudaError_t launch_k2_simt(const Problem &p, cudaStream_t stream, int sm_count)
 	const long long big_tiles = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128);
 	if (big_tiles >= sm_count) return launch_cfg<128, 128, 8, 8>(p, stream);
 	return launch_cfg<64, 64, 4, 4>(p, stream);
+}
+
+cudaError_t launch_im2col(const float *im, int channels, int height, int width, int k, int pad, int stride, float *col, cudaStream_t stream)
+{
+	const int ho = (height + 2 * pad - k) / stride + 1, wo = (width + 2 * pad - k) / stride + 1;
+	const long long total = (long long)channels * k * k * ho * wo;
+	if (total <= 0) return cudaSuccess;
+	long long blocks = (total + 255) / 256;
+	if (blocks > 148LL * 64) blocks = 148LL * 64;
+	im2col_kernel<<<(unsigned)blocks, 256, 0, stream>>>(im, channels, height, width, k, pad, stride, ho, wo, col);
+	return cudaGetLastError();
 }
 
 cudaError_t launch_scale_c(const Problem &p, cudaStream_t stream)
