@@ -41,8 +41,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build.needs_build():
+    path = os.environ.get("UGEMM_CUDA_LIB") or _build.LIB   # override: A/B-test another build of the same ABI
+    if path == _build.LIB and _build.needs_build():
         try:
             _build.build()
         except Exception as e:  # stale-but-present library is still usable on a box without nvcc

@@ -121,6 +121,8 @@ __device__ __forceinline__ int next_tile(uint32_t bar_base, int &n, bool warp_co
 	return tile;
 }
 
+template <bool PROF> __device__ __forceinline__ long long tick() { return PROF ? clock64() : 0LL; }
+
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float tf32_rna(float x)
 {
@@ -129,7 +131,9 @@ __device__ __forceinline__ float tf32_rna(float x)
 	return __uint_as_float(r);
 }
 
-template <int CG>
+// PROF compiles the per-role cycle counters in (UGEMM_K1_FLAGS bit 5); the production instantiation has none, which
+// keeps ~10 registers out of the epilogue's hot drain loop.
+template <int CG, bool PROF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const K1Params P)
 {
@@ -157,7 +161,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 	const int num_clusters = (CG == 2) ? (int)num_clusters_x() : (int)gridDim.x;
 	const int nkb = P.num_k_blocks;
 	const int kc = P.kc_blocks;
-	long long *prof = (P.prof && blockIdx.x < 4) ? P.prof + 16 * blockIdx.x : nullptr;
+	long long *prof = (PROF && P.prof && blockIdx.x < 4) ? P.prof + 16 * blockIdx.x : nullptr;
 
 	// ---- one-time setup --------------------------------------------------------------------------------
 	if (warp == 0 && lane == 0) {
@@ -190,11 +194,11 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 	const uint32_t tmem_base = *tmem_slot_ptr;
 
 	if (warp < 4) {
-		reg_dec<40>();
+		reg_dec<48>();
 		if (warp == 0 && lane == 0) {
 			// ================= TMA producer =================
 			int it = 0;
-			long long w_empty = 0; const long long t_begin = clock64();
+			long long w_empty = 0; const long long t_begin = tick<PROF>();
 			const uint64_t hintA = (P.flags & 128) ? L2_EVICT_LAST : (P.flags & 1024) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
 			const uint64_t hintB = (P.flags & 512) ? L2_EVICT_LAST : (P.flags & 256) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
 			int nt = 0;
@@ -206,9 +210,9 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				for (int kb = 0; kb < nkb && !(P.flags & 64); kb++, it++) {
 					const int s = it % STAGES;
 					const uint32_t ph = (it / STAGES) & 1;
-					const long long tw = clock64();
+					const long long tw = tick<PROF>();
 					mbar_wait(empty_bar(s), ph ^ 1u, P.diag, 1);
-					w_empty += clock64() - tw;
+					w_empty += tick<PROF>() - tw;
 					mbar_arrive_expect_tx(full_bar(s), RAW_BYTES);
 					const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + OPER_BYTES;
 					const int k0 = kb * BK;
@@ -220,7 +224,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 						for (int j = 0; j < ROWS / 32; j++) tma_load_2d_hint(sB + j * 4096, &tmB, full_bar(s), b_row0 + 32 * j, k0, hintB);
 				}
 			}
-			if (prof) { prof[0] = w_empty; prof[1] = clock64() - t_begin; }
+			if (prof) { prof[0] = w_empty; prof[1] = tick<PROF>() - t_begin; }
 		} else if (warp == 1 && lane == 0 && cta_rank == 0) {
 			// ================= MMA issuer (leader CTA) =================
 			const uint32_t idesc = idesc_tf32(UMMA_M, BN, P.a_kmajor ? 0 : 1, P.b_kmajor ? 0 : 1);
@@ -231,28 +235,28 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			const uint32_t b_lbo = P.b_kmajor ? 1u : 256u, b_sbo = P.b_kmajor ? 64u : 32u, b_lay = P.b_kmajor ? 2u : 1u;
 			const uint32_t a_kstep = P.a_kmajor ? 32u : 1024u, b_kstep = P.b_kmajor ? 32u : 1024u;
 			int it = 0, ci = 0;
-			long long w_xf = 0, w_te = 0; const long long t_begin = clock64();
+			long long w_xf = 0, w_te = 0; const long long t_begin = tick<PROF>();
 			int nt = 0;
 			while (next_tile<CG>(bar_base, nt, false, 0, P.diag) >= 0) {
 				for (int kb0 = 0; kb0 < nkb; kb0 += kc, ci++) {
 					const int acc = ci & 1;
 					const uint32_t aph = (ci >> 1) & 1;
-					long long tw = clock64();
+					long long tw = tick<PROF>();
 					if (CG == 2) mbar_wait_cluster(tempty_bar(acc), aph ^ 1u, P.diag, 2);
 					else mbar_wait(tempty_bar(acc), aph ^ 1u, P.diag, 2);
-					w_te += clock64() - tw;
+					w_te += tick<PROF>() - tw;
 					tc_fence_after();
 					const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
 					const int kb1 = min(kb0 + kc, nkb);
 					for (int kb = kb0; kb < kb1; kb++, it++) {
 						const int s = it % STAGES;
 						const uint32_t ph = (it / STAGES) & 1;
-						tw = clock64();
+						tw = tick<PROF>();
 						if (!(P.flags & 64)) {
 							if (CG == 2) mbar_wait_cluster(xf_bar(s), ph, P.diag, 3);
 							else mbar_wait(xf_bar(s), ph, P.diag, 3);
 						}
-						w_xf += clock64() - tw;
+						w_xf += tick<PROF>() - tw;
 						tc_fence_after();
 						const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + OPER_BYTES;
 						const uint32_t sAs = sA + RAW_BYTES, sBs = sB + RAW_BYTES;
@@ -264,25 +268,6 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 							const uint64_t dBs = smem_desc(sBs + k4 * b_kstep, b_lbo, b_sbo, b_lay);
 							const uint32_t first = (kb > kb0 || k4 > 0) ? 1u : 0u;
 							if (P.flags & 8) { mma_tf32_ss<CG>(d_tmem, dAb, dBb, idesc, first); continue; }
-							if (P.flags & 2048) {   // timing experiment only: A operand from (aliased) tensor memory
-								const uint32_t a_t = tmem_base + (uint32_t)((acc ^ 1) * BN) + k4 * 8;
-								if (P.flags & 4096) {   // two N=128 halves per product
-									const uint32_t idh = idesc_tf32(UMMA_M, BN / 2, 0, P.b_kmajor ? 0 : 1);
-									for (int hh = 0; hh < 2; hh++) {
-										mma_tf32_ts<CG>(d_tmem + hh * (BN / 2), a_t, dBb, idh, first);
-										mma_tf32_ts<CG>(d_tmem + hh * (BN / 2), a_t + 32, dBs, idh, 1u);
-										mma_tf32_ts<CG>(d_tmem + hh * (BN / 2), a_t, dBb, idh, 1u);
-									}
-								} else {
-									// bits 13..15: experimental N = 256 - 16*x (timing only)
-									const int nexp = BN - 16 * ((P.flags >> 13) & 7);
-									const uint32_t idn = idesc_tf32(UMMA_M, nexp, 0, P.b_kmajor ? 0 : 1);
-									mma_tf32_ts<CG>(d_tmem, a_t, dBb, idn, first);
-									mma_tf32_ts<CG>(d_tmem, a_t + 32, dBs, idn, 1u);
-									mma_tf32_ts<CG>(d_tmem, a_t, dBb, idn, 1u);
-								}
-								continue;
-							}
 							mma_tf32_ss<CG>(d_tmem, dAs, dBb, idesc, first);
 							if (P.flags & 1) {
 								mma_tf32_ss_coll<CG, 1>(d_tmem, dAb, dBs, idesc, 1u);
@@ -297,7 +282,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					mma_commit<CG>(tfull_bar(acc));     // accumulator chunk complete
 				}
 			}
-			if (prof) { prof[2] = w_xf; prof[3] = w_te; prof[4] = clock64() - t_begin; }
+			if (prof) { prof[2] = w_xf; prof[3] = w_te; prof[4] = tick<PROF>() - t_begin; }
 		} else if (warp == 2 && lane == 0 && cta_rank == 0) {
 			// ================= tile scheduler (leader CTA) =================
 			const uint32_t slots = bar_base + 8u * (14 + 2 * SCHED_SLOTS);
@@ -327,20 +312,20 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		__syncwarp();   // reconverge before the .aligned teardown barrier
 	} else if (warp < 4 + 4 * XF_GROUPS) {
 		// ================= transform warps: write the "small" operand copies =================
-		reg_dec<64>();
+		reg_dec<56>();
 		const int grp = (warp - 4) >> 2;                 // this warpgroup takes k-blocks with it % XF_GROUPS == grp
 		const int t = (threadIdx.x - 128) & 127;
 		int it = 0;
-		long long w_full = 0, t_work = 0, t_fence = 0; const long long t_begin = clock64();
+		long long w_full = 0, t_work = 0, t_fence = 0; const long long t_begin = tick<PROF>();
 		int nt = 0;
 		while (next_tile<CG>(bar_base, nt, true, lane, P.diag) >= 0) {
 			for (int kb = 0; kb < nkb && !(P.flags & 64); kb++, it++) {
 				if (it % XF_GROUPS != grp) continue;
 				const int s = it % STAGES;
 				const uint32_t ph = (it / STAGES) & 1;
-				const long long t0 = clock64();
+				const long long t0 = tick<PROF>();
 				mbar_wait(full_bar(s), ph, P.diag, 4);
-				const long long t1 = clock64();
+				const long long t1 = tick<PROF>();
 				const uint32_t raw = smem_base + s * STAGE_BYTES;
 #pragma unroll
 				for (int half = 0; half < 2; half++) {
@@ -363,21 +348,21 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 						if (P.split != 0) sts128(raw + off, b);
 					}
 				}
-				const long long t2 = clock64();
+				const long long t2 = tick<PROF>();
 				fence_proxy_async_smem();
 				__syncwarp();
 				if (lane == 0) {
 					if (CG == 2) mbar_arrive_cluster(xf_bar(s), 0);
 					else mbar_arrive(xf_bar(s));
 				}
-				const long long t3 = clock64();
+				const long long t3 = tick<PROF>();
 				w_full += t1 - t0; t_work += t2 - t1; t_fence += t3 - t2;
 			}
 		}
-		if (prof && threadIdx.x == 128) { prof[5] = w_full; prof[6] = t_work; prof[7] = t_fence; prof[8] = clock64() - t_begin; }
+		if (prof && threadIdx.x == 128) { prof[5] = w_full; prof[6] = t_work; prof[7] = t_fence; prof[8] = tick<PROF>() - t_begin; }
 	} else {
 		// ================= epilogue warps =================
-		reg_inc<152>();
+		reg_inc<160>();
 		const int e = warp - (4 + 4 * XF_GROUPS);
 		const int q = e & 3;        // TMEM lane quarter (must equal warp % 4)
 		const int h = e >> 2;       // column half
@@ -385,7 +370,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		const float bs = P.beta / P.alpha;                 // alpha != 0 here (alpha == 0 never reaches a GEMM kernel)
 		const bool preload_c = P.beta != 0.f && fabsf(bs) < 1e18f && fabsf(bs) > 1e-18f;
 		int ci = 0;
-		long long w_tf = 0, t_drain = 0, t_store = 0; const long long t_begin = clock64();
+		long long w_tf = 0, t_drain = 0, t_store = 0; const long long t_begin = tick<PROF>();
 		int nt = 0;
 		for (int tile; (tile = next_tile<CG>(bar_base, nt, true, lane, P.diag)) >= 0;) {
 			int tm, tn;
@@ -420,9 +405,9 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			for (int kb0 = 0; kb0 < nkb; kb0 += kc, ci++) {
 				const int ab = ci & 1;
 				const uint32_t aph = (ci >> 1) & 1;
-				const long long t0 = clock64();
+				const long long t0 = tick<PROF>();
 				mbar_wait(tfull_bar(ab), aph, P.diag, 5);
-				const long long t1 = clock64();
+				const long long t1 = tick<PROF>();
 				tc_fence_after();
 				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * (BN / 2));
 #pragma unroll
@@ -438,9 +423,9 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					if (CG == 2) mbar_arrive_cluster(tempty_bar(ab), 0);
 					else mbar_arrive(tempty_bar(ab));
 				}
-				w_tf += t1 - t0; t_drain += clock64() - t1;
+				w_tf += t1 - t0; t_drain += tick<PROF>() - t1;
 			}
-			const long long ts0 = clock64();
+			const long long ts0 = tick<PROF>();
 			// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
 			const float beta = preload_c ? 0.f : P.beta;   // already folded into acc when preloaded
 			if (row < P.M && !(P.flags & 16)) {
@@ -479,9 +464,9 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					}
 				}
 			}
-			t_store += clock64() - ts0;
+			t_store += tick<PROF>() - ts0;
 		}
-		if (prof && threadIdx.x == 32 * (4 + 4 * XF_GROUPS)) { prof[9] = w_tf; prof[10] = t_drain; prof[11] = t_store; prof[12] = clock64() - t_begin; }
+		if (prof && threadIdx.x == 32 * (4 + 4 * XF_GROUPS)) { prof[9] = w_tf; prof[10] = t_drain; prof[11] = t_store; prof[12] = tick<PROF>() - t_begin; }
 	}
 
 	// ---- teardown: everyone (both CTAs of a pair) done before TMEM is returned ------------------------------
@@ -632,7 +617,9 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 
 	static bool attr_set[3] = {false, false, false};
 	if (!attr_set[CG]) {
-		cudaError_t e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+		cudaError_t e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+		if (e != cudaSuccess) return e;
+		e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 		if (e != cudaSuccess) return e;
 		attr_set[CG] = true;
 	}
@@ -647,7 +634,8 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr; cfg.numAttrs = 1;
-	cudaError_t le = cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG>, tmA, tmB, P);
+	cudaError_t le = (t.flags & 32) ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true>, tmA, tmB, P)
+	                                : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false>, tmA, tmB, P);
 	if (le == cudaSuccess && (t.flags & 32)) {   // debug: per-role cycle breakdown of CTAs 0..3 on stderr
 		long long h[64];
 		if (cudaStreamSynchronize(stream) == cudaSuccess && cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
