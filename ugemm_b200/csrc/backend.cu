@@ -32,7 +32,7 @@ struct State {
 	// staging arena of the host-pointer entry points (one buffer like the OpenCL backend's `gm`)
 	char *arena = nullptr;
 	size_t arena_bytes = 0;
-	K1Tuning tuning = {4, 0, 2, 1};   // promote every 4 k-blocks (128 k), truncation split, 2-CTA pairs
+	K1Tuning tuning = {4, 0, 2, 1};   // promote every 4 k-blocks (128 k), truncation split, 2-CTA pairs, A collector
 	int last_kernel = 0;
 	int sm_limit = 0;                // 0 = all SMs; otherwise K1's persistent grid is capped (leaves SMs to NCCL)
 	unsigned long long launches = 0;

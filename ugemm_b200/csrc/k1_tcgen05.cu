@@ -41,7 +41,8 @@ constexpr int RAW_BYTES = 2 * OPER_BYTES;     // A raw | B raw
 constexpr int STAGE_BYTES = 2 * RAW_BYTES;    // A raw | B raw | A small | B small = 64 KiB
 constexpr int STAGES = 3;
 constexpr int NUM_THREADS = 640;              // 20 warps, see role map above
-constexpr int XF_GROUPS = 2;                  // transform warpgroups, alternating k-blocks
+constexpr int XF_GROUPS = 2;                  // transform warpgroups
+constexpr bool XF_SPLIT_STAGE = true;         // true: both groups share every stage (half each); false: groups alternate k-blocks
 constexpr int BAR_BYTES = 256;
 constexpr int SCHED_SLOTS = 4;               // depth of the dynamic tile-index ring
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024; // + slack for 1024-B alignment
@@ -169,7 +170,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		prefetch_tmap(&tmB);
 		for (int s = 0; s < STAGES; s++) {
 			mbar_init(full_bar(s), 1);
-			mbar_init(xf_bar(s), 4 * CG);     // 4 transform warps per CTA of the pair
+			mbar_init(xf_bar(s), (XF_SPLIT_STAGE ? 4 * XF_GROUPS : 4) * CG);   // transform warps that publish one stage
 			mbar_init(empty_bar(s), 1);
 		}
 		for (int a = 0; a < 2; a++) {
@@ -320,7 +321,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		int nt = 0;
 		while (next_tile<CG>(bar_base, nt, true, lane, P.diag) >= 0) {
 			for (int kb = 0; kb < nkb && !(P.flags & 64); kb++, it++) {
-				if (it % XF_GROUPS != grp) continue;
+				if (!XF_SPLIT_STAGE && it % XF_GROUPS != grp) continue;
 				const int s = it % STAGES;
 				const uint32_t ph = (it / STAGES) & 1;
 				const long long t0 = tick<PROF>();
@@ -328,7 +329,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				const long long t1 = tick<PROF>();
 				const uint32_t raw = smem_base + s * STAGE_BYTES;
 #pragma unroll
-				for (int half = 0; half < 2; half++) {
+				for (int half = (XF_SPLIT_STAGE ? grp : 0); half < (XF_SPLIT_STAGE ? grp + 1 : 2); half++) {
 					if (P.flags & 4) break;
 					float4 v[8];
 #pragma unroll
