@@ -89,10 +89,10 @@ void        sgemm_cuda_clear_error(void);
 int                sgemm_cuda_last_kernel(void);   /* UGEMM_MODE_3XTF32 or UGEMM_MODE_SIMT of the last GEMM launch, 0 if none */
 unsigned long long sgemm_cuda_launch_count(void);  /* number of GEMM/fill/scale kernels launched by this library so far */
 int  ugemm_cuda_device_info(int *sm_count, int *sm_clock_khz, size_t *hbm_bytes, char *name, int name_len);
-/* Tunables of K1 (0/negative = keep).  kc_blocks: number of 32-wide k-blocks accumulated inside TMEM
+/* Tunables of K1 (negative = keep).  kc_blocks: number of 32-wide k-blocks accumulated inside TMEM
  * before the partial sums are promoted to fp32 registers with round-to-nearest adds;
  * split: 0 = truncation split, raw tile is the "big" operand; 1 = round-to-nearest split, big rewritten.
- * cta_group: 1 or 2 CTAs per MMA. */
+ * cta_group: 1 or 2 CTAs per MMA, 0 = by problem size (pairs once >= ~3/4 of the SM pairs have a 256x256 tile). */
 void sgemm_cuda_set_k1_tuning(int kc_blocks, int split, int cta_group);
 
 /* Cap the number of SMs K1's persistent grid occupies (0 = all).  Used by the sharded driver while NCCL panel

@@ -32,7 +32,7 @@ struct State {
 	// staging arena of the host-pointer entry points (one buffer like the OpenCL backend's `gm`)
 	char *arena = nullptr;
 	size_t arena_bytes = 0;
-	K1Tuning tuning = {4, 0, 2, 1};   // promote every 4 k-blocks (128 k), truncation split, 2-CTA pairs, A collector
+	K1Tuning tuning = {4, 0, 0, 1};   // promote every 4 k-blocks (128 k), truncation split, CTA pairing by problem size, A collector
 	int last_kernel = 0;
 	int sm_limit = 0;                // 0 = all SMs; otherwise K1's persistent grid is capped (leaves SMs to NCCL)
 	unsigned long long launches = 0;
@@ -438,7 +438,7 @@ void sgemm_cuda_set_k1_tuning(int kc_blocks, int split, int cta_group)
 {
 	if (kc_blocks >= 0) g.tuning.kc_blocks = kc_blocks;
 	if (split >= 0) g.tuning.split = split ? 1 : 0;
-	if (cta_group == 1 || cta_group == 2) g.tuning.cta_group = cta_group;
+	if (cta_group >= 0 && cta_group <= 2) g.tuning.cta_group = cta_group;   // 0 = choose by problem size
 }
 
 void sgemm_cuda_set_sm_limit(int sms) { g.sm_limit = sms > 0 ? sms : 0; }

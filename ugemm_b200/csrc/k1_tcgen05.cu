@@ -665,7 +665,15 @@ bool k1_eligible(const Problem &p, const char **why)
 
 cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
-	if (t.cta_group == 1) return launch_cg<1>(p, t, stream, sm_count);
+	int cg = t.cta_group;
+	if (cg != 1 && cg != 2) {
+		// auto: 2-CTA pairs (256x256 tiles, half the shared-memory operand traffic per flop) once there are enough
+		// such tiles to occupy ~3/4 of the SM pairs; below that 128x128 single-CTA tiles spread the problem over more
+		// SMs (measured cross-over between 1536^3 = 36 pair tiles and 2048^3 = 64, profiles/r1_sizes.txt)
+		const long long pair_tiles = (long long)((p.M + 255) / 256) * ((p.N + 255) / 256);
+		cg = (pair_tiles * 8 >= (long long)(sm_count / 2) * 6) ? 2 : 1;
+	}
+	if (cg == 1) return launch_cg<1>(p, t, stream, sm_count);
 	return launch_cg<2>(p, t, stream, sm_count);
 }
 
