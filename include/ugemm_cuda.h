@@ -67,8 +67,11 @@ int sgemm_cuda_dev(int mode, void *stream, char major, char transA, char transB,
                    float alpha, const float *dA, int lda, const float *dB, int ldb,
                    float beta, float *dC, int ldc);
 
-/* 1 if UGEMM_MODE_AUTO would pick K1 for this problem: A, B 16-byte aligned, lda and ldb multiples
- * of 4 (TMA global-stride rule), M,N >= 128 and K >= 32 (at least one full tile of tensor work). */
+/* 1 if UGEMM_MODE_AUTO would pick K1 DIRECTLY for this problem: A, B 16-byte aligned, lda and ldb multiples
+ * of 4 (TMA global-stride rule), M,N >= 128 and K >= 32 (at least one full tile of tensor work).
+ * The complete auto rule: (1) that -> K1; (2) else, if M,N >= 256 and K >= 64, the operand(s) TMA cannot take are
+ * first copied to a stream-ordered scratch buffer with an aligned leading dimension (one HBM pass, reported by
+ * sgemm_cuda_last_repacked) and K1 runs on the copy; (3) else K2.  Forced modes never repack. */
 int sgemm_cuda_k1_eligible(char major, char transA, char transB, int M, int N, int K,
                            const float *dA, int lda, const float *dB, int ldb, const float *dC, int ldc);
 
@@ -86,6 +89,7 @@ const char *sgemm_cuda_last_error(void);
 void        sgemm_cuda_clear_error(void);
 
 /* ---- introspection used by the harnesses / bench */
+int                sgemm_cuda_last_repacked(void);  /* 1 if the last auto launch went through rule (2) above */
 int                sgemm_cuda_last_kernel(void);   /* UGEMM_MODE_3XTF32 or UGEMM_MODE_SIMT of the last GEMM launch, 0 if none */
 unsigned long long sgemm_cuda_launch_count(void);  /* number of GEMM/fill/scale kernels launched by this library so far */
 int  ugemm_cuda_device_info(int *sm_count, int *sm_clock_khz, size_t *hbm_bytes, char *name, int name_len);

@@ -182,11 +182,15 @@ def test_k1_vs_k2_agree(u):
 
 
 def test_auto_dispatch_rule(u):
-    """mode=auto: K1 iff A,B 16-B aligned, lda/ldb % 4 == 0, M,N >= 128, K >= 32; otherwise K2."""
-    for (M, N, K, pad, want) in ((256, 256, 64, (0, 0, 0), "3xtf32"), (256, 256, 64, (1, 0, 0), "simt"),
-                                 (64, 256, 64, (0, 0, 0), "simt"), (256, 256, 16, (0, 0, 0), "simt")):
-        check_case(u, "auto", "R", "N", "N", M, N, K, 1.0, 0.0, pad, seed=2)
+    """mode=auto: (1) K1 iff A,B 16-B aligned, lda/ldb % 4 == 0, M,N >= 128, K >= 32; (2) else, M,N >= 256 and K >= 64:
+    repack the TMA-ineligible operand(s) to an aligned ld, then K1; (3) else K2."""
+    for (M, N, K, pad, want, repacked) in ((256, 256, 64, (0, 0, 0), "3xtf32", False), (256, 256, 64, (1, 0, 0), "3xtf32", True),
+                                           (256, 256, 64, (0, 3, 5), "3xtf32", True), (200, 256, 64, (1, 0, 0), "simt", False),
+                                           (64, 256, 64, (0, 0, 0), "simt", False), (256, 256, 16, (0, 0, 0), "simt", False),
+                                           (300, 257, 100, (1, 2, 3), "3xtf32", True)):
+        check_case(u, "auto", "R", "N", "N", M, N, K, 1.5, 0.5, pad, seed=2)
         assert u.last_kernel() == want, (M, N, K, pad)
+        assert u.last_repacked() == repacked, (M, N, K, pad)
 
 
 def test_golden_fixtures(u):
@@ -226,20 +230,22 @@ def test_config1_1024_cube_vs_reference_avx(u):
 @pytest.mark.parametrize("ta,tb", [("N", "T"), ("T", "N"), ("T", "T"), ("N", "N")])
 def test_config3_ragged_transposed(u, ta, tb):
     """BASELINE config 3: 4095 x 3001 x 2047, alpha=1.5 beta=0.5, (i) ld padded to multiples of 4 -> K1,
-    (ii) odd padding -> K2; padding untouched.  Oracle: reference sgemm_sse when _ref ships, else 35-band."""
+    (ii) odd padding -> auto repacks to an aligned ld and runs K1, forced simt runs K2; padding untouched.  Oracle: reference sgemm_sse when _ref ships, else 35-band."""
     M, N, K = 4095, 3001, 2047
     r = O.ref()
     (ar, ac), (br, bc), _ = O.stored_shapes("R", ta, tb, M, N, K)
     odd = lambda w, p: p if (w + p) % 4 else p + 1   # a pad that leaves the leading dimension NOT a multiple of 4
-    for label, pad, want_kernel in (("ld%4==0", ((-ac) % 4, (-bc) % 4, (-N) % 4), "3xtf32"),
-                                    ("odd ld", (odd(ac, 5), odd(bc, 3), odd(N, 7)), "simt")):
+    for label, pad, mode, want_kernel in (("ld%4==0", ((-ac) % 4, (-bc) % 4, (-N) % 4), "auto", "3xtf32"),
+                                          ("odd ld, auto (repack + K1)", (odd(ac, 5), odd(bc, 3), odd(N, 7)), "auto", "3xtf32"),
+                                          ("odd ld, forced K2", (odd(ac, 5), odd(bc, 3), odd(N, 7)), "simt", "simt")):
         A, lda, B, ldb, Cm, ldc = O.make_problem("R", ta, tb, M, N, K, pad=pad, seed=33, sentinel=-9.0)
         if r is not None:
             want = O.run14(r.ref_sgemm_sse, "R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
         else:
             want = oracle14("R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
-        got = gpu14(u, "auto", "R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+        got = gpu14(u, mode, "R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
         assert u.last_kernel() == want_kernel
+        assert u.last_repacked() == label.startswith("odd ld, auto")
         e = O.relerr("R", M, N, want, got, ldc)
         print(f"c3 {ta}{tb} {label} -> {want_kernel}: relerr {e:.3e} ({bounds(K)})")
         assert e <= TOL

@@ -67,6 +67,7 @@ def lib():
     L.sgemm_cuda_last_error.restype = C.c_char_p
     L.sgemm_cuda_clear_error.restype = None
     L.sgemm_cuda_last_kernel.restype = C.c_int
+    L.sgemm_cuda_last_repacked.restype = C.c_int
     L.sgemm_cuda_launch_count.restype = C.c_ulonglong
     L.ugemm_cuda_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.c_char_p, C.c_int]
     L.ugemm_cuda_device_info.restype = C.c_int
@@ -123,7 +124,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "sgemm_cuda_init", "sgemm_cuda_finish", "sgemm_cuda", "sgemm_cuda_3xtf32", "sgemm_cuda_simt",
     "sgemm_cuda_dev", "sgemm_cuda_k1_eligible", "sgemm_cuda_time_dev", "sgemm_cuda_last_error",
-    "sgemm_cuda_clear_error", "sgemm_cuda_last_kernel", "sgemm_cuda_launch_count", "ugemm_cuda_device_info",
+    "sgemm_cuda_clear_error", "sgemm_cuda_last_kernel", "sgemm_cuda_last_repacked", "sgemm_cuda_launch_count", "ugemm_cuda_device_info",
     "sgemm_cuda_set_k1_tuning", "sgemm_cuda_set_sm_limit", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
     "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
     "ugemm_cuda_memcpy_async", "ugemm_cuda_ipc_export", "ugemm_cuda_ipc_import", "ugemm_cuda_ipc_close",
@@ -211,6 +212,10 @@ def set_sm_limit(sms=0):
 
 def last_kernel():
     return {0: None, 1: "3xtf32", 2: "simt"}[lib().sgemm_cuda_last_kernel()]
+
+
+def last_repacked():
+    return bool(lib().sgemm_cuda_last_repacked())
 
 
 def launch_count():

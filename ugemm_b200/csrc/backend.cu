@@ -34,6 +34,7 @@ struct State {
 	size_t arena_bytes = 0;
 	K1Tuning tuning = {4, 0, 0, 1};   // promote every 4 k-blocks (128 k), truncation split, CTA pairing by problem size, A collector
 	int last_kernel = 0;
+	int last_repacked = 0;           // last auto launch copied an operand to an aligned leading dimension first
 	int sm_limit = 0;                // 0 = all SMs; otherwise K1's persistent grid is capped (leaves SMs to NCCL)
 	unsigned long long launches = 0;
 } g;
@@ -66,6 +67,8 @@ int ensure_init()
 	if (g.ready) return 0;
 	return sgemm_cuda_init(-1, 0);
 }
+
+size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int upper(char c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
 
@@ -101,6 +104,43 @@ bool auto_prefers_k1(const Problem &p)
 	return k1_eligible(p, nullptr) && p.M >= 128 && p.N >= 128 && p.K >= 32;
 }
 
+bool tma_ok(const float *ptr, long long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 4 == 0; }
+
+// mode=auto, operand layout TMA cannot take (ld not a multiple of 4 or a misaligned base) but a problem big enough
+// that the tensor cores pay for a copy: repack the offending operand(s) into a stream-ordered scratch buffer with an
+// aligned leading dimension (one HBM pass over that operand, 2*4*rows*cols bytes, ~1 % of the GEMM time at the
+// sizes this triggers for) and run K1 on the copy.  C needs no repacking: K1's epilogue stores through any ldc.
+bool auto_wants_repack(const Problem &p)
+{
+	return !(tma_ok(p.A, p.lda) && tma_ok(p.B, p.ldb)) && p.M >= 256 && p.N >= 256 && p.K >= 64;
+}
+
+// returns 0 on success with *q the problem to launch and *scratch the buffer to cudaFreeAsync afterwards (or null);
+// returns 1 if the scratch allocation is not available (caller falls back to K2, which is not an error)
+int repack_for_tma(const Problem &p, cudaStream_t stream, Problem *q, void **scratch)
+{
+	*q = p; *scratch = nullptr;
+	const long long a_lines = p.a_kmajor ? p.M : p.K, a_cols = p.a_kmajor ? p.K : p.M;
+	const long long b_lines = p.b_kmajor ? p.N : p.K, b_cols = p.b_kmajor ? p.K : p.N;
+	const bool ra = !tma_ok(p.A, p.lda), rb = !tma_ok(p.B, p.ldb);
+	const long long lda2 = (a_cols + 3) / 4 * 4, ldb2 = (b_cols + 3) / 4 * 4;
+	const size_t a_bytes = ra ? align_up_sz((size_t)a_lines * lda2 * 4, 256) : 0, b_bytes = rb ? (size_t)b_lines * ldb2 * 4 : 0;
+	char *ws = nullptr;
+	if (cudaMallocAsync(reinterpret_cast<void **>(&ws), a_bytes + b_bytes + 256, stream) != cudaSuccess) { cudaGetLastError(); return 1; }
+	cudaError_t e = cudaSuccess;
+	if (ra) {
+		e = cudaMemcpy2DAsync(ws, (size_t)lda2 * 4, p.A, (size_t)p.lda * 4, (size_t)a_cols * 4, (size_t)a_lines, cudaMemcpyDeviceToDevice, stream);
+		q->A = reinterpret_cast<const float *>(ws); q->lda = lda2;
+	}
+	if (rb && e == cudaSuccess) {
+		e = cudaMemcpy2DAsync(ws + a_bytes, (size_t)ldb2 * 4, p.B, (size_t)p.ldb * 4, (size_t)b_cols * 4, (size_t)b_lines, cudaMemcpyDeviceToDevice, stream);
+		q->B = reinterpret_cast<const float *>(ws + a_bytes); q->ldb = ldb2;
+	}
+	if (e != cudaSuccess) { cudaFreeAsync(ws, stream); cudaGetLastError(); return 1; }
+	*scratch = ws;
+	return 0;
+}
+
 // device-pointer GEMM on `stream`
 int run_dev(int mode, cudaStream_t stream, const Problem &p)
 {
@@ -114,6 +154,19 @@ int run_dev(int mode, cudaStream_t stream, const Problem &p)
 	}
 	int use = mode;
 	if (mode == UGEMM_MODE_AUTO) use = auto_prefers_k1(p) ? UGEMM_MODE_3XTF32 : UGEMM_MODE_SIMT;
+	if (mode == UGEMM_MODE_AUTO && use == UGEMM_MODE_SIMT && auto_wants_repack(p)) {
+		Problem q; void *scratch = nullptr;
+		if (repack_for_tma(p, stream, &q, &scratch) == 0 && k1_eligible(q, nullptr)) {
+			cudaError_t e = launch_k1_3xtf32(q, g.tuning, stream, (g.sm_limit > 0 && g.sm_limit < g.sm_count) ? g.sm_limit : g.sm_count);
+			if (scratch) cudaFreeAsync(scratch, stream);
+			CU_TRY(e, "K1 (3xTF32 tcgen05, repacked operands) launch");
+			g.last_kernel = UGEMM_MODE_3XTF32; g.last_repacked = 1;
+			g.launches++;
+			return 0;
+		}
+		if (scratch) cudaFreeAsync(scratch, stream);
+	}
+	g.last_repacked = 0;
 	if (use == UGEMM_MODE_3XTF32) {
 		const char *why = nullptr;
 		if (!k1_eligible(p, &why)) { set_error("3xTF32 kernel not applicable: %s", why); return 1; }
@@ -315,6 +368,14 @@ int sgemm_cuda_init(int device, size_t arena_bytes)
 		CU_TRY(cudaEventCreateWithFlags(&g.ev_up[i], cudaEventDisableTiming), "cudaEventCreate");
 		CU_TRY(cudaEventCreateWithFlags(&g.ev_done[i], cudaEventDisableTiming), "cudaEventCreate");
 	}
+	{   // keep stream-ordered scratch (the repack path) cached in the pool instead of returning it to the OS at every sync
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+			unsigned long long keep = ~0ull;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+		cudaGetLastError();
+	}
 	if (const char *f = getenv("UGEMM_K1_FLAGS")) g.tuning.flags = atoi(f);   // overrides the default (bit0 = A collector on)   // debug / ablation, see common.cuh
 	g.ready = true;
 	if (arena_bytes && ensure_arena(arena_bytes)) { g.ready = false; return 1; }
@@ -422,6 +483,7 @@ int sgemm_cuda_time_dev(int mode, int iters, int warmup, char major, char ta, ch
 const char *sgemm_cuda_last_error(void) { return g_has_err ? g_err : nullptr; }
 void sgemm_cuda_clear_error(void) { g_has_err = false; g_err[0] = 0; }
 int sgemm_cuda_last_kernel(void) { return g.last_kernel; }
+int sgemm_cuda_last_repacked(void) { return g.last_repacked; }
 unsigned long long sgemm_cuda_launch_count(void) { return g.launches; }
 
 int ugemm_cuda_device_info(int *sm_count, int *sm_clock_khz, size_t *hbm_bytes, char *name, int name_len)
