@@ -211,7 +211,8 @@ cudaError_t copy2d(float *dst, const float *src, long long ld, long long lines, 
 void run_host_pipelined(int mode, const Problem &p, float *dA, float *dB, float *dC)
 {
 	const long long b_lines = p.b_kmajor ? p.N : p.K, b_cols = p.b_kmajor ? p.K : p.N;
-	int panels = (int)((p.M + 1023) / 1024);
+	int panels = (int)((p.M + 511) / 512);     // small panels shorten the un-overlapped tail (last GEMM + last download)
+	if (const char *e = getenv("UGEMM_CUDA_PANELS")) panels = atoi(e) > 0 ? atoi(e) : panels;
 	if (panels > 16) panels = 16;
 	long long mb = ((p.M + panels - 1) / panels + 255) / 256 * 256;
 	panels = (int)((p.M + mb - 1) / mb);
