@@ -67,6 +67,17 @@ int sgemm_cuda_dev(int mode, void *stream, char major, char transA, char transB,
                    float alpha, const float *dA, int lda, const float *dB, int ldb,
                    float beta, float *dC, int ldc);
 
+/* ---- strided batch: `batch` problems of one shape in ONE launch; instance b uses A + b*strideA, B + b*strideB,
+ * C + b*strideC (strides in elements).  This is the stacked-instance layout of the reference's test_sgemm (11 instances,
+ * a is (11*M) x lda etc., check_sgemm.c:111-124,242-246), which the reference walks one call at a time.  K1 needs
+ * strideA and strideB to be multiples of 4 in addition to the usual rule; otherwise K2.  No operand repacking here. */
+void sgemm_cuda_batched(char major, char transA, char transB, int M, int N, int K, float alpha,
+                        const float *A, int lda, long long strideA, const float *B, int ldb, long long strideB,
+                        float beta, float *C, int ldc, long long strideC, int batch);             /* host pointers, blocking */
+int  sgemm_cuda_batched_dev(int mode, void *stream, char major, char transA, char transB, int M, int N, int K, float alpha,
+                            const float *dA, int lda, long long strideA, const float *dB, int ldb, long long strideB,
+                            float beta, float *dC, int ldc, long long strideC, int batch);        /* device pointers, async */
+
 /* 1 if UGEMM_MODE_AUTO would pick K1 DIRECTLY for this problem: A, B 16-byte aligned, lda and ldb multiples
  * of 4 (TMA global-stride rule), M,N >= 128 and K >= 32 (at least one full tile of tensor work).
  * The complete auto rule: (1) that -> K1; (2) else, if M,N >= 256 and K >= 64, the operand(s) TMA cannot take are

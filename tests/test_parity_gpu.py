@@ -319,3 +319,31 @@ def test_full_size_linearity_property(u):
     assert e <= TOL
     for x in (dA, dB1, dB2, dB12, dC, dD):
         x.free()
+
+
+@pytest.mark.parametrize("case", [
+    ("R", "N", "N", 128, 361, 1152, 11, (0, 0, 0), "simt"),      # the reference's default check_sgemm problem: 11 stacked instances
+    ("R", "N", "N", 128, 360, 1152, 11, (0, 0, 0), "3xtf32"),    # same with a TMA-eligible ldb -> one K1 launch over 11 x 3 tiles
+    ("R", "T", "N", 256, 384, 200, 5, (0, 0, 4), "3xtf32"),
+    ("R", "N", "T", 300, 260, 100, 3, (4, 4, 0), "3xtf32"),
+    ("C", "N", "N", 130, 140, 70, 4, (2, 0, 1), "simt"),
+])
+def test_batched_stacked_instances(u, case):
+    """sgemm_cuda_batched == the reference's loop over stacked instances (check_sgemm.c:111-124), one launch."""
+    maj, ta, tb, M, N, K, batch, pad, want_kernel = case
+    (ar, ac), (br, bc), (cr, cc) = O.stored_shapes(maj, ta, tb, M, N, K)
+    lda, ldb, ldc = ac + pad[0], bc + pad[1], cc + pad[2]
+    sA, sB, sC = ar * lda, br * ldb, cr * ldc
+    A = O.fill_uniform(batch * sA, 901, -0.5, 0.5)
+    B = O.fill_uniform(batch * sB, 902, -0.5, 0.5)
+    C0 = O.fill_uniform(batch * sC, 903, -0.5, 0.5)
+    got = C0.copy()
+    u.sgemm_cuda_batched(maj, ta, tb, M, N, K, 1.5, A, lda, sA, B, ldb, sB, 0.5, got, ldc, sC, batch)
+    assert u.last_kernel() == want_kernel
+    for b in range(batch):
+        want = oracle14(maj, ta, tb, M, N, K, 1.5, A[b * sA:(b + 1) * sA], lda, B[b * sB:(b + 1) * sB], ldb, 0.5,
+                        C0[b * sC:(b + 1) * sC], ldc)
+        e = O.relerr("R", cr, cc, want, got[b * sC:(b + 1) * sC], ldc)
+        assert e <= TOL, (b, e)
+        if pad[2]:
+            assert np.array_equal(got[b * sC:(b + 1) * sC].reshape(cr, ldc)[:, cc:], C0[b * sC:(b + 1) * sC].reshape(cr, ldc)[:, cc:])

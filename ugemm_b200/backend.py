@@ -59,6 +59,12 @@ def lib():
         getattr(L, n).restype = None
     L.sgemm_cuda_dev.argtypes = [C.c_int, C.c_void_p] + sig14
     L.sgemm_cuda_dev.restype = C.c_int
+    bat = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_longlong,
+           C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_void_p, C.c_int, C.c_longlong, C.c_int]
+    L.sgemm_cuda_batched.argtypes = bat
+    L.sgemm_cuda_batched.restype = None
+    L.sgemm_cuda_batched_dev.argtypes = [C.c_int, C.c_void_p] + bat
+    L.sgemm_cuda_batched_dev.restype = C.c_int
     L.sgemm_cuda_k1_eligible.argtypes = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.sgemm_cuda_k1_eligible.restype = C.c_int
@@ -123,7 +129,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "sgemm_cuda_init", "sgemm_cuda_finish", "sgemm_cuda", "sgemm_cuda_3xtf32", "sgemm_cuda_simt",
-    "sgemm_cuda_dev", "sgemm_cuda_k1_eligible", "sgemm_cuda_time_dev", "sgemm_cuda_last_error",
+    "sgemm_cuda_dev", "sgemm_cuda_batched", "sgemm_cuda_batched_dev", "sgemm_cuda_k1_eligible", "sgemm_cuda_time_dev", "sgemm_cuda_last_error",
     "sgemm_cuda_clear_error", "sgemm_cuda_last_kernel", "sgemm_cuda_last_repacked", "sgemm_cuda_launch_count", "ugemm_cuda_device_info",
     "sgemm_cuda_set_k1_tuning", "sgemm_cuda_set_sm_limit", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
     "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
@@ -185,6 +191,21 @@ def sgemm_cuda_dev(mode, stream, major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb
     if rc:
         check()
         raise UgemmCudaError("sgemm_cuda_dev failed")
+
+
+def sgemm_cuda_batched(major, ta, tb, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, Cm, ldc, strideC, batch):
+    """`batch` stacked instances in one launch (host buffers, blocking)."""
+    lib().sgemm_cuda_batched(_b(major), _b(ta), _b(tb), M, N, K, alpha, _ptr(A), lda, strideA, _ptr(B), ldb, strideB, beta,
+                             _ptr(Cm), ldc, strideC, batch)
+    check()
+
+
+def sgemm_cuda_batched_dev(mode, stream, major, ta, tb, M, N, K, alpha, dA, lda, strideA, dB, ldb, strideB, beta, dC, ldc, strideC, batch):
+    rc = lib().sgemm_cuda_batched_dev(_MODES[mode], C.c_void_p(stream or 0), _b(major), _b(ta), _b(tb), M, N, K, alpha,
+                                      _ptr(dA), lda, strideA, _ptr(dB), ldb, strideB, beta, _ptr(dC), ldc, strideC, batch)
+    if rc:
+        check()
+        raise UgemmCudaError("sgemm_cuda_batched_dev failed")
 
 
 def sgemm_cuda_time_dev(mode, iters, warmup, major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, total=False):

@@ -112,7 +112,7 @@ bool tma_ok(const float *ptr, long long ld) { return (reinterpret_cast<uintptr_t
 // sizes this triggers for) and run K1 on the copy.  C needs no repacking: K1's epilogue stores through any ldc.
 bool auto_wants_repack(const Problem &p)
 {
-	return !(tma_ok(p.A, p.lda) && tma_ok(p.B, p.ldb)) && p.M >= 256 && p.N >= 256 && p.K >= 64;
+	return p.batch <= 1 && !(tma_ok(p.A, p.lda) && tma_ok(p.B, p.ldb)) && p.M >= 256 && p.N >= 256 && p.K >= 64;
 }
 
 // returns 0 on success with *q the problem to launch and *scratch the buffer to cudaFreeAsync afterwards (or null);
@@ -416,6 +416,62 @@ int sgemm_cuda_dev(int mode, void *stream, char major, char ta, char tb, int M, 
 	Problem p;
 	if (normalise(major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, &p)) return 1;
 	return run_dev(mode, stream ? static_cast<cudaStream_t>(stream) : g.stream, p);
+}
+
+// Strided batch: `batch` independent problems of identical shape, instance b at A + b*strideA, B + b*strideB,
+// C + b*strideC -- the stacked layout test_sgemm walks one call at a time (check_sgemm.c:111-124), done in ONE launch
+// so that small instances still fill the machine.  Device pointers, asynchronous.
+int sgemm_cuda_batched_dev(int mode, void *stream, char major, char ta, char tb, int M, int N, int K, float alpha,
+                           const float *dA, int lda, long long strideA, const float *dB, int ldb, long long strideB,
+                           float beta, float *dC, int ldc, long long strideC, int batch)
+{
+	if (ensure_init()) return 1;
+	if (batch < 0) { set_error("negative batch count"); return 1; }
+	if (batch == 0) return 0;
+	Problem p;
+	if (normalise(major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, &p)) return 1;
+	const bool swapped = (major == 'C' || major == 'c');
+	p.batch = batch;
+	p.strideA = swapped ? strideB : strideA;     // normalise() swapped the operands for column-major
+	p.strideB = swapped ? strideA : strideB;
+	p.strideC = strideC;
+	if (batch > 1 && (p.strideA < 0 || p.strideB < 0 || p.strideC < (long long)(p.M - 1) * p.ldc + p.N)) {
+		set_error("batch strides must be non-negative and strideC must not make instances of C overlap");
+		return 1;
+	}
+	return run_dev(mode, stream ? static_cast<cudaStream_t>(stream) : g.stream, p);
+}
+
+// host-pointer version: whole stacked buffers go up, one launch, the stacked C comes back (blocking)
+void sgemm_cuda_batched(char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda, long long strideA,
+                        const float *B, int ldb, long long strideB, float beta, float *C, int ldc, long long strideC, int batch)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (ensure_init() || batch <= 0) return;
+	Problem p;
+	if (normalise(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, &p)) return;
+	if (p.M == 0 || p.N == 0) return;
+	const bool swapped = (major == 'C' || major == 'c');
+	const long long sA = swapped ? strideB : strideA, sB = swapped ? strideA : strideB;
+	const long long a_lines = p.a_kmajor ? p.M : p.K, a_cols = p.a_kmajor ? p.K : p.M;
+	const long long b_lines = p.b_kmajor ? p.N : p.K, b_cols = p.b_kmajor ? p.K : p.N;
+	const size_t a_n = (size_t)((batch - 1) * sA + (a_lines - 1) * p.lda + a_cols);
+	const size_t b_n = (size_t)((batch - 1) * sB + (b_lines - 1) * p.ldb + b_cols);
+	const size_t c_n = (size_t)((batch - 1) * strideC + (long long)(p.M - 1) * p.ldc + p.N);
+	const size_t offB = align_up(a_n * 4, 256), offC = align_up(offB + b_n * 4, 256);
+	if (ensure_arena(offC + c_n * 4)) return;
+	float *dA = reinterpret_cast<float *>(g.arena), *dB = reinterpret_cast<float *>(g.arena + offB), *dC = reinterpret_cast<float *>(g.arena + offC);
+	cudaError_t e = cudaMemcpyAsync(dA, p.A, a_n * 4, cudaMemcpyHostToDevice, g.stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(dB, p.B, b_n * 4, cudaMemcpyHostToDevice, g.stream);
+	// C travels whole (padding included, so the download restores it bit for bit); needed up front when beta != 0
+	if (e == cudaSuccess) e = cudaMemcpyAsync(dC, p.C, c_n * 4, cudaMemcpyHostToDevice, g.stream);
+	if (e != cudaSuccess) { set_error("batched H2D failed: %s", cudaGetErrorString(e)); return; }
+	Problem d = p;
+	d.A = dA; d.B = dB; d.C = dC; d.batch = batch; d.strideA = sA; d.strideB = sB; d.strideC = strideC;
+	if (run_dev(UGEMM_MODE_AUTO, g.stream, d)) return;
+	e = cudaMemcpyAsync(p.C, dC, c_n * 4, cudaMemcpyDeviceToHost, g.stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+	if (e != cudaSuccess) set_error("batched GEMM failed: %s", cudaGetErrorString(e));
 }
 
 int sgemm_cuda_k1_eligible(char major, char ta, char tb, int M, int N, int K, const float *dA, int lda,

@@ -19,6 +19,10 @@ struct Problem {
 	// act(x) = x > 0 ? x : slope*x.  bias == nullptr and slope == 1 (the default) mean a plain GEMM.
 	const float *bias = nullptr;
 	float slope = 1.f;
+	// strided batch (the stacked-instance layout of test_sgemm, check_sgemm.c:116-120): instance b uses
+	// A + b*strideA, B + b*strideB, C + b*strideC (elements); batch == 1 is a plain GEMM.
+	int batch = 1;
+	long long strideA = 0, strideB = 0, strideC = 0;
 };
 
 // flags: bit0 = share one shared-memory read of A_big between big*small and big*big (A collector);

@@ -55,6 +55,8 @@ struct K1Params {
 	long long ldc;
 	const float *bias;
 	float slope;
+	long long strideC;          // elements between batch instances of C
+	int tiles_per_batch;        // tiles_m * tiles_n; tile index = instance * tiles_per_batch + tile within the instance
 	int a_kmajor, b_kmajor;
 	int tiles_m, tiles_n, num_tiles;
 	int num_k_blocks, kc_blocks, split, vecC, flags;
@@ -205,7 +207,8 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			int nt = 0;
 			for (int tile; (tile = next_tile<CG>(bar_base, nt, false, 0, P.diag)) >= 0;) {
 				int tm, tn;
-				decode_tile(tile, P.tiles_m, P.tiles_n, tm, tn);
+				const int inst = tile / P.tiles_per_batch;
+				decode_tile(tile - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
 				const int a_row0 = tm * UMMA_M + (int)cta_rank * ROWS;
 				const int b_row0 = tn * BN + (int)cta_rank * ROWS;
 				for (int kb = 0; kb < nkb && !(P.flags & 64); kb++, it++) {
@@ -217,12 +220,12 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					mbar_arrive_expect_tx(full_bar(s), RAW_BYTES);
 					const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + OPER_BYTES;
 					const int k0 = kb * BK;
-					if (P.a_kmajor) tma_load_2d_hint(sA, &tmA, full_bar(s), k0, a_row0, hintA);
+					if (P.a_kmajor) tma_load_3d_hint(sA, &tmA, full_bar(s), k0, a_row0, inst, hintA);
 					else
-						for (int j = 0; j < ROWS / 32; j++) tma_load_2d_hint(sA + j * 4096, &tmA, full_bar(s), a_row0 + 32 * j, k0, hintA);
-					if (P.b_kmajor) tma_load_2d_hint(sB, &tmB, full_bar(s), k0, b_row0, hintB);
+						for (int j = 0; j < ROWS / 32; j++) tma_load_3d_hint(sA + j * 4096, &tmA, full_bar(s), a_row0 + 32 * j, k0, inst, hintA);
+					if (P.b_kmajor) tma_load_3d_hint(sB, &tmB, full_bar(s), k0, b_row0, inst, hintB);
 					else
-						for (int j = 0; j < ROWS / 32; j++) tma_load_2d_hint(sB + j * 4096, &tmB, full_bar(s), b_row0 + 32 * j, k0, hintB);
+						for (int j = 0; j < ROWS / 32; j++) tma_load_3d_hint(sB + j * 4096, &tmB, full_bar(s), b_row0 + 32 * j, k0, inst, hintB);
 				}
 			}
 			if (prof) { prof[0] = w_empty; prof[1] = tick<PROF>() - t_begin; }
@@ -375,10 +378,11 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		int nt = 0;
 		for (int tile; (tile = next_tile<CG>(bar_base, nt, true, lane, P.diag)) >= 0;) {
 			int tm, tn;
-			decode_tile(tile, P.tiles_m, P.tiles_n, tm, tn);
+			const int inst = tile / P.tiles_per_batch;
+			decode_tile(tile - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
 			float acc[NG][32];
 			const long long row = (long long)tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane;
-			float *crow = P.C + row * P.ldc;
+			float *crow = P.C + (long long)inst * P.strideC + row * P.ldc;
 			// beta != 0: the old C is folded in UP FRONT -- the running sums start at (beta/alpha)*C, loaded while the
 			// tile's first MMAs run and the epilogue warps would idle anyway -- so the tile end is store-only and
 			// never stalls the accumulator hand-over on a global-load round trip.
@@ -547,19 +551,24 @@ EncodeTiledFn encode_fn()
 	return fn;
 }
 
-// K-major operand: `rows` lines of `K` contiguous fp32, pitch ld  -> dims {K, rows}, box {32, 128}, SWIZZLE_128B
-// MN-major operand: `K` lines of `rows` contiguous fp32, pitch ld -> dims {rows, K}, box {32, 32}, SWIZZLE_128B_ATOM_32B
-bool make_operand_map(CUtensorMap *map, const float *base, long long rows, long long K, long long ld, bool kmajor)
+// K-major operand: `rows` lines of `K` contiguous fp32, pitch ld  -> dims {K, rows, batch}, box {32, 128, 1}, SWIZZLE_128B
+// MN-major operand: `K` lines of `rows` contiguous fp32, pitch ld -> dims {rows, K, batch}, box {32, 32, 1}, SWIZZLE_128B_ATOM_32B
+// The third dimension walks the strided batch (extent 1 for a plain GEMM).
+bool make_operand_map(CUtensorMap *map, const float *base, long long rows, long long K, long long ld, bool kmajor,
+                      int batch, long long stride)
 {
 	EncodeTiledFn fn = encode_fn();
 	if (!fn) return false;
-	cuuint64_t gdim[2], gstride[1];
-	cuuint32_t box[2], estr[2] = {1, 1};
+	cuuint64_t gdim[3], gstride[2];
+	cuuint32_t box[3], estr[3] = {1, 1, 1};
 	CUtensorMapSwizzle sw;
 	if (kmajor) { gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows; box[0] = BK; box[1] = ROWS; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
 	else        { gdim[0] = (cuuint64_t)rows; gdim[1] = (cuuint64_t)K; box[0] = 32; box[1] = BK; sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; }
+	gdim[2] = (cuuint64_t)(batch > 0 ? batch : 1);
+	box[2] = 1;
 	gstride[0] = (cuuint64_t)ld * 4;
-	CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
+	gstride[1] = (batch > 1) ? (cuuint64_t)stride * 4 : gstride[0] * gdim[1];   // any legal value when there is one instance
+	CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), gdim, gstride, box, estr,
 	                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	return r == CUDA_SUCCESS;
 }
@@ -581,8 +590,8 @@ template <int CG>
 cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
 	CUtensorMap tmA, tmB;
-	if (!make_operand_map(&tmA, p.A, p.M, p.K, p.lda, p.a_kmajor)) return cudaErrorInvalidValue;
-	if (!make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.b_kmajor)) return cudaErrorInvalidValue;
+	if (!make_operand_map(&tmA, p.A, p.M, p.K, p.lda, p.a_kmajor, p.batch, p.strideA)) return cudaErrorInvalidValue;
+	if (!make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.b_kmajor, p.batch, p.strideB)) return cudaErrorInvalidValue;
 	K1Params P;
 	P.M = p.M; P.N = p.N; P.K = p.K; P.alpha = p.alpha; P.beta = p.beta; P.C = p.C; P.ldc = p.ldc;
 	P.bias = p.bias; P.slope = p.slope;
@@ -590,7 +599,9 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	const int tile_m = 128 * CG, tile_n = 128 * CG;
 	P.tiles_m = (p.M + tile_m - 1) / tile_m;
 	P.tiles_n = (p.N + tile_n - 1) / tile_n;
-	const long long nt = (long long)P.tiles_m * P.tiles_n;
+	P.tiles_per_batch = P.tiles_m * P.tiles_n;
+	P.strideC = p.strideC;
+	const long long nt = (long long)P.tiles_m * P.tiles_n * (p.batch > 0 ? p.batch : 1);
 	if (nt > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
 	P.num_tiles = (int)nt;
 	P.num_k_blocks = (p.K + BK - 1) / BK;
@@ -657,6 +668,7 @@ bool k1_eligible(const Problem &p, const char **why)
 	const char *w = nullptr;
 	if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.B) & 15)) w = "A or B not 16-byte aligned (TMA base rule)";
 	else if (p.lda % 4 || p.ldb % 4) w = "lda or ldb not a multiple of 4 (TMA global stride must be a multiple of 16 bytes)";
+	else if (p.batch > 1 && (p.strideA % 4 || p.strideB % 4)) w = "batch strides of A or B not multiples of 4 (TMA global stride rule)";
 	else if (p.M < 1 || p.N < 1 || p.K < 1) w = "empty problem";
 	else if (!encode_fn()) w = "cuTensorMapEncodeTiled unavailable";
 	if (why) *why = w;
@@ -670,7 +682,7 @@ cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t s
 		// auto: 2-CTA pairs (256x256 tiles, half the shared-memory operand traffic per flop) once there are enough
 		// such tiles to occupy ~3/4 of the SM pairs; below that 128x128 single-CTA tiles spread the problem over more
 		// SMs (measured cross-over between 1536^3 = 36 pair tiles and 2048^3 = 64, profiles/r1_sizes.txt)
-		const long long pair_tiles = (long long)((p.M + 255) / 256) * ((p.N + 255) / 256);
+		const long long pair_tiles = (long long)((p.M + 255) / 256) * ((p.N + 255) / 256) * (p.batch > 0 ? p.batch : 1);
 		cg = (pair_tiles * 8 >= (long long)(sm_count / 2) * 6) ? 2 : 1;
 	}
 	if (cg == 1) return launch_cg<1>(p, t, stream, sm_count);

@@ -79,8 +79,12 @@ struct Stager {
 
 template <int BM, int BN, int TM, int TN, bool AK, bool BKM>
 __global__ void __launch_bounds__(K2_THREADS, (BM >= 128 ? 2 : 3))
-k2_simt_kernel(const Problem p, const int tiles_m, const int tiles_n, const bool vecA, const bool vecB, const bool vecC)
+k2_simt_kernel(Problem p, const int tiles_m, const int tiles_n, const bool vecA, const bool vecB, const bool vecC)
 {
+	// strided batch: one grid.y slice per instance
+	p.A += (long long)blockIdx.y * p.strideA;
+	p.B += (long long)blockIdx.y * p.strideB;
+	p.C += (long long)blockIdx.y * p.strideC;
 	static_assert((BM / TM) * (BN / TN) == K2_THREADS, "thread tile must cover the CTA tile");
 	constexpr int HM = TM / 2, HN = TN / 2;
 	__shared__ __align__(16) float As[2][K2_BK][BM + K2_PAD];
@@ -224,10 +228,12 @@ cudaError_t launch_cfg(const Problem &p, cudaStream_t stream)
 	const long long tiles = (long long)tiles_m * tiles_n;
 	if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
 	auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-	const bool vecA = al16(p.A) && (p.lda % 4 == 0);
-	const bool vecB = al16(p.B) && (p.ldb % 4 == 0);
-	const bool vecC = al16(p.C) && (p.ldc % 4 == 0);
-	dim3 grid((unsigned)tiles), block(K2_THREADS);
+	const bool multi = p.batch > 1;
+	const bool vecA = al16(p.A) && (p.lda % 4 == 0) && (!multi || p.strideA % 4 == 0);
+	const bool vecB = al16(p.B) && (p.ldb % 4 == 0) && (!multi || p.strideB % 4 == 0);
+	const bool vecC = al16(p.C) && (p.ldc % 4 == 0) && (!multi || p.strideC % 4 == 0);
+	if (p.batch > 65535) return cudaErrorInvalidConfiguration;
+	dim3 grid((unsigned)tiles, (unsigned)(multi ? p.batch : 1)), block(K2_THREADS);
 #define K2_LAUNCH(AK, BKM) \
 	k2_simt_kernel<BM, BN, TM, TN, AK, BKM><<<grid, block, 0, stream>>>(p, tiles_m, tiles_n, vecA, vecB, vecC)
 	if (p.a_kmajor) { if (p.b_kmajor) K2_LAUNCH(true, true); else K2_LAUNCH(true, false); }
@@ -242,7 +248,7 @@ cudaError_t launch_k2_simt(const Problem &p, cudaStream_t stream, int sm_count)
 {
 	// 128x128 tiles once they fill the machine (>= one CTA per SM); 64x64 below that so that small and
 	// skinny problems still spread over the 148 SMs.
-	const long long big_tiles = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128);
+	const long long big_tiles = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128) * (p.batch > 0 ? p.batch : 1);
 	if (big_tiles >= sm_count) return launch_cfg<128, 128, 8, 8>(p, stream);
 	return launch_cfg<64, 64, 4, 4>(p, stream);
 }
@@ -262,8 +268,12 @@ cudaError_t launch_scale_c(const Problem &p, cudaStream_t stream)
 {
 	if (p.M <= 0 || p.N <= 0) return cudaSuccess;
 	dim3 block(256), grid((unsigned)((p.N + 255) / 256), (unsigned)min(p.M, 65535));
-	scale_c_kernel<<<grid, block, 0, stream>>>(p.C, p.ldc, p.M, p.N, p.beta);
-	return cudaGetLastError();
+	for (int b = 0; b < (p.batch > 0 ? p.batch : 1); b++) {
+		scale_c_kernel<<<grid, block, 0, stream>>>(p.C + (long long)b * p.strideC, p.ldc, p.M, p.N, p.beta);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) return e;
+	}
+	return cudaSuccess;
 }
 
 } // namespace ugemm
