@@ -248,8 +248,21 @@ def run_multi(args, wl_name):
     wl = WORKLOADS[wl_name]
     M, N, K = wl["M"], wl["N"], wl["K"]
     plan = SlabPlan(world, rank, M, N, K)
-    ops = CudaP2POps("auto") if args.dist == "p2p" else CudaOps("auto")
-    sg = ShardedGemm(plan, ops, dist)
+    sg = None
+    if args.dist == "p2p":
+        # CUDA IPC / peer access can be unavailable on a box; all ranks must then agree to fall back to NCCL broadcast
+        ok = 1
+        try:
+            sg = ShardedGemm(plan, CudaP2POps("auto"), dist)
+        except Exception as ex:  # noqa: BLE001
+            ok, sg = 0, None
+            print(f"[rank {rank}] p2p transport unavailable ({ex}); falling back to NCCL broadcast", file=sys.stderr, flush=True)
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            sg = None
+    if sg is None:
+        sg = ShardedGemm(plan, CudaOps("auto"), dist)
     sg.generate_owned(seed_a=1, seed_b=2)
     flops = 2.0 * M * N * K
 
