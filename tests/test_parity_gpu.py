@@ -347,3 +347,18 @@ def test_batched_stacked_instances(u, case):
         assert e <= TOL, (b, e)
         if pad[2]:
             assert np.array_equal(got[b * sC:(b + 1) * sC].reshape(cr, ldc)[:, cc:], C0[b * sC:(b + 1) * sC].reshape(cr, ldc)[:, cc:])
+
+
+@pytest.mark.parametrize("ta", ["N", "T"])
+@pytest.mark.parametrize("tb", ["N", "T"])
+def test_k2_narrow_n_tiles(u, ta, tb):
+    """Tall-skinny shapes (N <= 32, M >= 256) take K2's 256x16 / 256x32 tiles; ragged edges, odd ld, both majors."""
+    for i, (M, N, K) in enumerate([(300, 16, 70), (257, 7, 33), (1000, 32, 129), (512, 24, 64), (4096, 1, 100), (777, 31, 1)]):
+        for maj in ("R", "C"):
+            pad = (0, 0, 0) if i % 2 == 0 else (3, 1, 5)
+            mm, nn = (M, N) if maj == "R" else (N, M)   # column-major swaps the roles, so keep the skinny side on N after the swap
+            check_case(u, "simt", maj, ta, tb, mm, nn, K, 1.5, 0.5, pad, seed=60 + i, naive=True)
+    # the memory-bound corner at size: 200704 x 16 x 1152 through auto (N < 128 -> K2)
+    e = sampled_rows_check(u, "auto", 200704, 16, 1152, [(0, 32), (200672, 32)], 0.0, 1.0)
+    assert u.last_kernel() == "simt"
+    assert e <= TOL

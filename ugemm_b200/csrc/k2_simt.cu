@@ -40,7 +40,8 @@ __device__ __forceinline__ float4 load_quad(const float *__restrict__ line, long
 //   else   : global lines run along m/n (row-major 'T' A, or 'N' B): line index = k, column = m (or n)
 template <int BMN, bool KCONTIG>
 struct Stager {
-	static constexpr int QUADS = BMN * K2_BK / 4 / K2_THREADS;
+	static constexpr int NQ = BMN * K2_BK / 4;                              // quads in the tile
+	static constexpr int QUADS = (NQ + K2_THREADS - 1) / K2_THREADS;        // per thread (narrow tiles: some threads idle)
 	float4 r[QUADS];
 
 	__device__ __forceinline__ void load(const float *__restrict__ base, long long ld, long long mn0, long long mn_max,
@@ -49,6 +50,7 @@ struct Stager {
 #pragma unroll
 		for (int i = 0; i < QUADS; i++) {
 			int f = tid + i * K2_THREADS;
+			if (NQ % K2_THREADS != 0 && f >= NQ) continue;
 			if (KCONTIG) {
 				int line = f / (K2_BK / 4), kq = (f % (K2_BK / 4)) * 4;
 				long long mn = mn0 + line;
@@ -65,6 +67,7 @@ struct Stager {
 #pragma unroll
 		for (int i = 0; i < QUADS; i++) {
 			int f = tid + i * K2_THREADS;
+			if (NQ % K2_THREADS != 0 && f >= NQ) continue;
 			if (KCONTIG) {
 				int line = f / (K2_BK / 4), kq = (f % (K2_BK / 4)) * 4;
 				s[kq + 0][line] = r[i].x; s[kq + 1][line] = r[i].y;
@@ -248,6 +251,10 @@ cudaError_t launch_k2_simt(const Problem &p, cudaStream_t stream, int sm_count)
 {
 	// 128x128 tiles once they fill the machine (>= one CTA per SM); 64x64 below that so that small and
 	// skinny problems still spread over the 148 SMs.
+	// narrow N (the tall-skinny, HBM-bound corner): 256-row tiles that are only as wide as the problem, so the FMA work
+	// wasted on columns >= N does not turn a memory-bound shape into a compute-bound one
+	if (p.N <= 16 && p.M >= 256) return launch_cfg<256, 16, 8, 2>(p, stream);
+	if (p.N <= 32 && p.M >= 256) return launch_cfg<256, 32, 8, 4>(p, stream);
 	const long long big_tiles = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128) * (p.batch > 0 ? p.batch : 1);
 	if (big_tiles >= sm_count) return launch_cfg<128, 128, 8, 8>(p, stream);
 	return launch_cfg<64, 64, 4, 4>(p, stream);
