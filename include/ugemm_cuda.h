@@ -168,6 +168,24 @@ void convolution_cuda_LReLU(const float *inputs, int ich, int w, int h, const fl
 int  convolution_cuda_dev(int mode, void *stream, const float *d_inputs, int ich, int w, int h, const float *d_weights, int k,
                           int pad, int stride, float *d_outputs, int ch, const float *d_bias, float slope, float *d_workspace);
 
+/* ---- level-1 / level-2 companions, HBM-bound.
+ *   saxpy_cuda   replaces saxpy_cpu (ugemm.h:75-86; also saxpy_avx ugemm.h:58-73 and the OpenCL Xaxpy kernel of
+ *                saxpy_ocl.c:129-157, whose host code uploads x and y, runs, downloads y):  y[i*incy] += alpha * x[i*incx],
+ *                one fused multiply-add per element.  Host pointers, blocking.  incx, incy >= 1.
+ *   sgemv_cuda   replaces sgemv_cpu (ugemm.h:124-150), argument for argument:  y[m*incy] = alpha * sum_n a(m,n) * x[n*incx] + beta * y[m*incy]
+ *                for m < M, n < N, where a(m,n) = A[m + n*lda] when trans == 'N' (lda >= M) and A[n + m*lda] otherwise
+ *                ('T', lda >= N) -- M is the length of y and N the length of x in BOTH cases, as in the reference.
+ *                Deliberate differences: x is strided by incx (the reference strides x by incy, ugemm.h:140,147 -- a typo
+ *                that only shows when incx != incy); beta == 0 overwrites y without reading it (consistent with sgemm_cuda);
+ *                trans letters other than N/T (either case) are an error instead of meaning 'T'.
+ *   *_dev        device pointers, asynchronous on `stream`.  Return 0 on success. */
+void saxpy_cuda(int N, float alpha, const float *x, int incx, float *y, int incy);
+int  saxpy_cuda_dev(void *stream, int N, float alpha, const float *dx, int incx, float *dy, int incy);
+void sgemv_cuda(char trans, int M, int N, float alpha, const float *A, int lda, const float *x, int incx,
+                float beta, float *y, int incy);
+int  sgemv_cuda_dev(void *stream, char trans, int M, int N, float alpha, const float *dA, int lda, const float *dx, int incx,
+                    float beta, float *dy, int incy);
+
 /* ---- hardware probe used by tests/DESIGN.md: runs one 128 x 16 x (8*ksteps) TF32 tcgen05 product
  * chain on raw fp32 bit patterns and returns the 128x16 fp32 accumulator, so the rounding behaviour of
  * the tensor core (operand truncation, accumulator rounding) can be pinned.  A: 128 x 8*ksteps row-major,

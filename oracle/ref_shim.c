@@ -12,6 +12,8 @@
  *   ref_sgemm_c    -> sgemm_c     gemm_cpu.h:284    Goto-blocked scalar 4x4
  *   ref_sgemm_avx  -> sgemm_avx   sgemm_avx256.h:392  AVX "noncblas", row-major NN only
  *   ref_sgemm_sse  -> sgemm_sse   sgemm_sse.h:365   AVX 8x8 Goto (static in the header)
+ *   ref_saxpy_cpu  -> saxpy_cpu   ugemm.h:75        y += alpha*x
+ *   ref_sgemv_cpu  -> sgemv_cpu   ugemm.h:124       naive gemv
  *   ref_sgemm_avx_mt: harness-level wrapper, sgemm_avx on disjoint row slabs of
  *                  A/C from `threads` OpenMP threads.  Legal because all state of
  *                  avx256_noncblas_sgemm lives in the stack-allocated
@@ -33,6 +35,11 @@ void ref_sgemm_cpu(SIG) { sgemm_cpu(ARGS); }
 void ref_sgemm_c  (SIG) { sgemm_c(ARGS); }
 void ref_sgemm_avx(SIG) { sgemm_avx(ARGS); }
 void ref_sgemm_sse(SIG) { sgemm_sse(ARGS); }
+
+void ref_saxpy_cpu(int N, float alpha, const float *x, int incx, float *y, int incy) { saxpy_cpu(N, alpha, x, incx, y, incy); }
+void ref_sgemv_cpu(char trans, int M, int N, float alpha, const float *A, int lda, const float *x, int incx,
+                   float beta, float *y, int incy)
+{ sgemv_cpu(trans, M, N, alpha, A, lda, x, incx, beta, y, incy); }
 
 int ref_max_threads(void)
 {

@@ -18,11 +18,17 @@ _SIG14 = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_float,
           _f32p, C.c_int, _f32p, C.c_int, C.c_float, _f32p, C.c_int]
 
 
+_AXPY = [C.c_int, C.c_float, _f32p, C.c_int, _f32p, C.c_int]
+_GEMV = [C.c_char, C.c_int, C.c_int, C.c_float, _f32p, C.c_int, _f32p, C.c_int, C.c_float, _f32p, C.c_int]
+
+
 def build_oracle(force=False):
     """Compile oracle/liboracle.so (and oracle/_ref when /root/reference exists)."""
-    if force or not os.path.exists(ORACLE_SO):
+    src = os.path.join(ORACLE_DIR, "sgemm_oracle.c")
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(src) > os.path.getmtime(ORACLE_SO):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.exists(os.environ.get("UGEMM_REF", "/root/reference") + "/ugemm.h") and (force or not os.path.exists(REF_SO)):
+    if os.path.exists(os.environ.get("UGEMM_REF", "/root/reference") + "/ugemm.h") and (
+            force or not os.path.exists(REF_SO) or os.path.getmtime(os.path.join(ORACLE_DIR, "ref_shim.c")) > os.path.getmtime(REF_SO)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -52,6 +58,10 @@ def oracle():
         lib.oracle_convolution.argtypes = [C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p,
                                            C.c_int, C.c_void_p, C.c_float, _f32p]
         lib.oracle_convolution.restype = None
+        lib.oracle_saxpy.argtypes = _AXPY
+        lib.oracle_saxpy.restype = None
+        lib.oracle_sgemv.argtypes = _GEMV
+        lib.oracle_sgemv.restype = None
         _oracle = lib
     return _oracle
 
@@ -70,6 +80,11 @@ def ref():
         lib.ref_sgemm_avx_mt.argtypes = [C.c_int] + _SIG14
         lib.ref_sgemm_avx_mt.restype = None
         lib.ref_max_threads.restype = C.c_int
+        if hasattr(lib, "ref_saxpy_cpu"):   # a prebuilt _ref from before these exports existed still serves the GEMM tests
+            lib.ref_saxpy_cpu.argtypes = _AXPY
+            lib.ref_saxpy_cpu.restype = None
+            lib.ref_sgemv_cpu.argtypes = _GEMV
+            lib.ref_sgemv_cpu.restype = None
         _ref = lib
     return _ref
 

@@ -121,6 +121,14 @@ def lib():
     L.convolution_cuda_LReLU.restype = None
     L.convolution_cuda_dev.argtypes = [C.c_int, C.c_void_p] + conv10 + [C.c_void_p, C.c_float, C.c_void_p]
     L.convolution_cuda_dev.restype = C.c_int
+    L.saxpy_cuda.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.saxpy_cuda.restype = None
+    L.saxpy_cuda_dev.argtypes = [C.c_void_p] + L.saxpy_cuda.argtypes
+    L.saxpy_cuda_dev.restype = C.c_int
+    L.sgemv_cuda.argtypes = [C.c_char, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int]
+    L.sgemv_cuda.restype = None
+    L.sgemv_cuda_dev.argtypes = [C.c_void_p] + L.sgemv_cuda.argtypes
+    L.sgemv_cuda_dev.restype = C.c_int
     L.ugemm_cuda_probe_tf32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.ugemm_cuda_probe_tf32.restype = C.c_int
     _lib = L
@@ -136,7 +144,7 @@ EXPORTED_SYMBOLS = [
     "ugemm_cuda_memcpy_async", "ugemm_cuda_ipc_export", "ugemm_cuda_ipc_import", "ugemm_cuda_ipc_close",
     "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
     "ugemm_cuda_probe_tf32", "im2col_cuda", "im2col_cuda_dev", "convolution_cuda", "convolution_cuda_LReLU",
-    "convolution_cuda_dev",
+    "convolution_cuda_dev", "saxpy_cuda", "saxpy_cuda_dev", "sgemv_cuda", "sgemv_cuda_dev",
 ]
 
 
@@ -379,6 +387,29 @@ def convolution_cuda_dev(mode, stream, d_inputs, ich, w, h, d_weights, k, pad, s
     if rc:
         check()
         raise UgemmCudaError("convolution_cuda_dev failed")
+
+
+# ---- level 1 / level 2 (argument order of saxpy_cpu ugemm.h:75 and sgemv_cpu ugemm.h:124) ----------------
+def saxpy_cuda(N, alpha, x, incx, y, incy):
+    lib().saxpy_cuda(N, alpha, _ptr(x), incx, _ptr(y), incy)
+    check()
+
+
+def saxpy_cuda_dev(stream, N, alpha, dx, incx, dy, incy):
+    if lib().saxpy_cuda_dev(C.c_void_p(stream or 0), N, alpha, _ptr(dx), incx, _ptr(dy), incy):
+        check()
+        raise UgemmCudaError("saxpy_cuda_dev failed")
+
+
+def sgemv_cuda(trans, M, N, alpha, A, lda, x, incx, beta, y, incy):
+    lib().sgemv_cuda(_b(trans), M, N, alpha, _ptr(A), lda, _ptr(x), incx, beta, _ptr(y), incy)
+    check()
+
+
+def sgemv_cuda_dev(stream, trans, M, N, alpha, dA, lda, dx, incx, beta, dy, incy):
+    if lib().sgemv_cuda_dev(C.c_void_p(stream or 0), _b(trans), M, N, alpha, _ptr(dA), lda, _ptr(dx), incx, beta, _ptr(dy), incy):
+        check()
+        raise UgemmCudaError("sgemv_cuda_dev failed")
 
 
 # ---- the macro API of the reference's GPU harness (sgemm_test.c:19-33): tight row-major, no ld ----------

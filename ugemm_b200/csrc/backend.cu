@@ -759,6 +759,87 @@ void convolution_cuda_LReLU(const float *inputs, int ich, int w, int h, const fl
                             int ch, const float *bias)
 { conv_host(inputs, ich, w, h, weights, k, pad, stride, outputs, ch, bias, 0.1f); }
 
+// ---- level 1 / level 2 -------------------------------------------------------------------
+int saxpy_cuda_dev(void *stream, int N, float alpha, const float *dx, int incx, float *dy, int incy)
+{
+	if (ensure_init()) return 1;
+	if (N < 0 || incx < 1 || incy < 1) { set_error("saxpy: N must be >= 0 and incx, incy >= 1 (N=%d incx=%d incy=%d)", N, incx, incy); return 1; }
+	if (N == 0 || alpha == 0.f) return 0;
+	CU_TRY(launch_saxpy(N, alpha, dx, incx, dy, incy, stream ? static_cast<cudaStream_t>(stream) : g.stream, g.sm_count), "saxpy launch");
+	g.launches++;
+	return 0;
+}
+
+void saxpy_cuda(int N, float alpha, const float *x, int incx, float *y, int incy)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (ensure_init()) return;
+	if (N < 0 || incx < 1 || incy < 1) { set_error("saxpy: N must be >= 0 and incx, incy >= 1 (N=%d incx=%d incy=%d)", N, incx, incy); return; }
+	if (N == 0 || alpha == 0.f) return;
+	const size_t xn = (size_t)(N - 1) * incx + 1, yn = (size_t)(N - 1) * incy + 1;
+	const size_t offY = align_up(xn * 4, 256);
+	if (ensure_arena(offY + yn * 4)) return;
+	float *dx = reinterpret_cast<float *>(g.arena), *dy = reinterpret_cast<float *>(g.arena + offY);
+	cudaError_t e = cudaMemcpyAsync(dx, x, xn * 4, cudaMemcpyHostToDevice, g.stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y, yn * 4, cudaMemcpyHostToDevice, g.stream);
+	if (e != cudaSuccess) { set_error("saxpy H2D failed: %s", cudaGetErrorString(e)); return; }
+	if (saxpy_cuda_dev(g.stream, N, alpha, dx, incx, dy, incy)) return;
+	// the whole strided span travels both ways, so the gaps between elements come back bit for bit
+	e = cudaMemcpyAsync(y, dy, yn * 4, cudaMemcpyDeviceToHost, g.stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+	if (e != cudaSuccess) set_error("saxpy failed: %s", cudaGetErrorString(e));
+}
+
+static int gemv_check(char *trans, int M, int N, int lda, int incx, int incy)
+{
+	*trans = (char)upper(*trans);
+	if (*trans != 'N' && *trans != 'T') { set_error("sgemv: trans must be 'N' or 'T'"); return 1; }
+	if (M < 0 || N < 0 || incx < 1 || incy < 1) { set_error("sgemv: M, N must be >= 0 and incx, incy >= 1"); return 1; }
+	const int need = *trans == 'N' ? M : N;
+	if (lda < (need > 1 ? need : 1)) { set_error("sgemv: lda=%d too small for trans='%c' (needs >= %d)", lda, *trans, need); return 1; }
+	return 0;
+}
+
+int sgemv_cuda_dev(void *stream, char trans, int M, int N, float alpha, const float *dA, int lda, const float *dx, int incx,
+                   float beta, float *dy, int incy)
+{
+	if (ensure_init()) return 1;
+	if (gemv_check(&trans, M, N, lda, incx, incy)) return 1;
+	if (M == 0) return 0;
+	if ((alpha == 0.f || N == 0) && beta == 1.f) return 0;
+	// alpha == 0 or N == 0: the sum is empty, y <- beta*y; an N of 0 makes the kernels' loops do exactly that
+	CU_TRY(launch_sgemv(trans == 'T', M, alpha == 0.f ? 0 : N, alpha, dA, lda, dx, incx, beta, dy, incy,
+	                    stream ? static_cast<cudaStream_t>(stream) : g.stream, g.sm_count), "sgemv launch");
+	g.launches++;
+	return 0;
+}
+
+void sgemv_cuda(char trans, int M, int N, float alpha, const float *A, int lda, const float *x, int incx, float beta, float *y, int incy)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (ensure_init()) return;
+	if (gemv_check(&trans, M, N, lda, incx, incy)) return;
+	if (M == 0) return;
+	if ((alpha == 0.f || N == 0) && beta == 1.f) return;
+	const bool need_ax = alpha != 0.f && N > 0;
+	const long long lines = trans == 'N' ? N : M, cols = trans == 'N' ? M : N;
+	const size_t a_n = need_ax ? (size_t)((lines - 1) * lda + cols) : 0, xn = need_ax ? (size_t)(N - 1) * incx + 1 : 0, yn = (size_t)(M - 1) * incy + 1;
+	const size_t offX = align_up(a_n * 4, 256), offY = align_up(offX + xn * 4, 256);
+	if (ensure_arena(offY + yn * 4)) return;
+	float *dA = reinterpret_cast<float *>(g.arena), *dx = reinterpret_cast<float *>(g.arena + offX), *dy = reinterpret_cast<float *>(g.arena + offY);
+	cudaError_t e = cudaSuccess;
+	if (need_ax) {
+		e = copy2d(dA, A, lda, lines, cols, cudaMemcpyHostToDevice, g.stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, xn * 4, cudaMemcpyHostToDevice, g.stream);
+	}
+	if (e == cudaSuccess && (beta != 0.f || incy != 1)) e = cudaMemcpyAsync(dy, y, yn * 4, cudaMemcpyHostToDevice, g.stream);
+	if (e != cudaSuccess) { set_error("sgemv H2D failed: %s", cudaGetErrorString(e)); return; }
+	if (sgemv_cuda_dev(g.stream, trans, M, N, alpha, dA, lda, dx, incx, beta, dy, incy)) return;
+	e = cudaMemcpyAsync(y, dy, yn * 4, cudaMemcpyDeviceToHost, g.stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+	if (e != cudaSuccess) set_error("sgemv failed: %s", cudaGetErrorString(e));
+}
+
 int ugemm_cuda_probe_tf32(const float *A, const float *B, float *D, int ksteps)
 {
 	if (ensure_init()) return 1;

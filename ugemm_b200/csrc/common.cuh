@@ -40,6 +40,10 @@ cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t s
 cudaError_t launch_scale_c(const Problem &p, cudaStream_t stream);
 // im2col of a planar C x H x W image into the (C*k*k) x (Ho*Wo) column matrix (k2_simt.cu)
 cudaError_t launch_im2col(const float *im, int channels, int height, int width, int k, int pad, int stride, float *col, cudaStream_t stream);
+// level 1 / level 2 companions (k3_level12.cu): y += alpha*x;  y = alpha*op(A)*x + beta*y
+cudaError_t launch_saxpy(long long n, float alpha, const float *x, long long incx, float *y, long long incy, cudaStream_t stream, int sm_count);
+cudaError_t launch_sgemv(bool rows_contiguous, int M, int N, float alpha, const float *A, long long lda, const float *x, long long incx,
+                         float beta, float *y, long long incy, cudaStream_t stream, int sm_count);
 // probe (k1_tcgen05.cu)
 cudaError_t launch_probe_tf32(const float *dA, const float *dB, float *dD, int ksteps, cudaStream_t stream);
 // last diagnostic record written by a K1 watchdog (host-mapped memory), 0 if none

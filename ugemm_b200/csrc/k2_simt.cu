@@ -21,6 +21,10 @@ namespace {
 constexpr int K2_BK = 16;
 constexpr int K2_THREADS = 256;
 constexpr int K2_PAD = 4;
+#ifndef UGEMM_K2_PACKED
+#define UGEMM_K2_PACKED 1
+#endif
+constexpr bool K2_PACKED_FMA = UGEMM_K2_PACKED != 0;
 
 __device__ __forceinline__ float4 load_quad(const float *__restrict__ line, long long c, long long cmax,
                                             bool line_ok, bool vec)
@@ -62,6 +66,25 @@ struct Stager {
 			}
 		}
 	}
+	// Interior fast path: the tile lies fully inside the operand, the operand is 128-bit loadable and the k-tile is
+	// full, so the loads need no guards.  One pointer per thread, set once per CTA tile, advanced per k-tile; the
+	// quads of one thread are a constant number of lines apart.
+	const float *fp;
+	long long fstep;
+	__device__ __forceinline__ void fast_init(const float *__restrict__ base, long long ld, long long mn0, int tid)
+	{
+		if (KCONTIG) { fp = base + (mn0 + tid / (K2_BK / 4)) * ld + (tid % (K2_BK / 4)) * 4; fstep = (K2_THREADS / (K2_BK / 4)) * ld; }
+		else         { fp = base + (long long)(tid / (BMN / 4)) * ld + mn0 + (tid % (BMN / 4)) * 4; fstep = (K2_THREADS / (BMN / 4)) * ld; }
+	}
+	__device__ __forceinline__ void fast_load(long long ld, int tid)
+	{
+		fp += KCONTIG ? (long long)K2_BK : K2_BK * ld;
+#pragma unroll
+		for (int i = 0; i < QUADS; i++) {
+			if (NQ % K2_THREADS != 0 && tid + i * K2_THREADS >= NQ) continue;
+			r[i] = __ldg(reinterpret_cast<const float4 *>(fp + i * fstep));
+		}
+	}
 	__device__ __forceinline__ void store(float (*s)[BMN + K2_PAD], int tid) const
 	{
 #pragma unroll
@@ -90,6 +113,7 @@ k2_simt_kernel(Problem p, const int tiles_m, const int tiles_n, const bool vecA,
 	p.C += (long long)blockIdx.y * p.strideC;
 	static_assert((BM / TM) * (BN / TN) == K2_THREADS, "thread tile must cover the CTA tile");
 	constexpr int HM = TM / 2, HN = TN / 2;
+	constexpr bool PACKED = K2_PACKED_FMA && HN % 2 == 0;   // pairs of adjacent columns inside each half of the thread tile
 	__shared__ __align__(16) float As[2][K2_BK][BM + K2_PAD];
 	__shared__ __align__(16) float Bs[2][K2_BK][BN + K2_PAD];
 
@@ -117,18 +141,18 @@ k2_simt_kernel(Problem p, const int tiles_m, const int tiles_n, const bool vecA,
 	Stager<BN, BKM> sb;
 	const int ktiles = (p.K + K2_BK - 1) / K2_BK;
 
+	// interior tiles of vector-loadable operands take unguarded 128-bit loads for every full k-tile (CTA-uniform test)
+	const bool interior = vecA && vecB && m0 + BM <= p.M && n0 + BN <= p.N;
+	const int fast_tiles = interior ? p.K / K2_BK : 0;
+	sa.fast_init(p.A, p.lda, m0, tid);
+	sb.fast_init(p.B, p.ldb, n0, tid);
 	sa.load(p.A, p.lda, m0, p.M, 0, p.K, vecA, tid);
 	sb.load(p.B, p.ldb, n0, p.N, 0, p.K, vecB, tid);
 	sa.store(As[0], tid);
 	sb.store(Bs[0], tid);
 	__syncthreads();
 
-	for (int t = 0; t < ktiles; t++) {
-		const int cur = t & 1;
-		if (t + 1 < ktiles) {
-			sa.load(p.A, p.lda, m0, p.M, (long long)(t + 1) * K2_BK, p.K, vecA, tid);
-			sb.load(p.B, p.ldb, n0, p.N, (long long)(t + 1) * K2_BK, p.K, vecB, tid);
-		}
+	auto multiply = [&](int cur) {
 #pragma unroll
 		for (int kk = 0; kk < K2_BK; kk++) {
 			float a[TM], b[TN];
@@ -142,11 +166,46 @@ k2_simt_kernel(Problem p, const int tiles_m, const int tiles_n, const bool vecA,
 				b[j] = Bs[cur][kk][tx * HN + j];
 				b[HN + j] = Bs[cur][kk][BN / 2 + tx * HN + j];
 			}
+			if constexpr (PACKED) {
+				// Blackwell packed fp32: one FFMA2 updates two adjacent columns (a 64-bit register pair), which halves the
+				// issue slots per flop and reads every operand as an even/odd register pair (no bank-conflict lottery)
 #pragma unroll
-			for (int i = 0; i < TM; i++)
+				for (int i = 0; i < TM; i++) {
+					const float2 aa = make_float2(a[i], a[i]);
 #pragma unroll
-				for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+					for (int j = 0; j < TN; j += 2) {
+						const float2 r = __ffma2_rn(aa, make_float2(b[j], b[j + 1]), make_float2(acc[i][j], acc[i][j + 1]));
+						acc[i][j] = r.x; acc[i][j + 1] = r.y;
+					}
+				}
+			} else {
+#pragma unroll
+				for (int i = 0; i < TM; i++)
+#pragma unroll
+					for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+			}
 		}
+	};
+
+	int t = 0;
+	// steady state of interior tiles: nothing but 128-bit loads, the FFMA block, the shared-memory stores and one barrier
+	for (; t + 1 < fast_tiles; t++) {
+		const int cur = t & 1;
+		sa.fast_load(p.lda, tid);
+		sb.fast_load(p.ldb, tid);
+		multiply(cur);
+		sa.store(As[cur ^ 1], tid);
+		sb.store(Bs[cur ^ 1], tid);
+		__syncthreads();
+	}
+	// edge tiles, scalar-only operands and the K tail: guarded loads
+	for (; t < ktiles; t++) {
+		const int cur = t & 1;
+		if (t + 1 < ktiles) {
+			sa.load(p.A, p.lda, m0, p.M, (long long)(t + 1) * K2_BK, p.K, vecA, tid);
+			sb.load(p.B, p.ldb, n0, p.N, (long long)(t + 1) * K2_BK, p.K, vecB, tid);
+		}
+		multiply(cur);
 		if (t + 1 < ktiles) {
 			sa.store(As[cur ^ 1], tid);
 			sb.store(Bs[cur ^ 1], tid);
@@ -255,6 +314,7 @@ cudaError_t launch_k2_simt(const Problem &p, cudaStream_t stream, int sm_count)
 	// wasted on columns >= N does not turn a memory-bound shape into a compute-bound one
 	if (p.N <= 16 && p.M >= 256) return launch_cfg<256, 16, 8, 2>(p, stream);
 	if (p.N <= 32 && p.M >= 256) return launch_cfg<256, 32, 8, 4>(p, stream);
+	if (p.N <= 64 && (long long)(p.M / 256) * (p.batch > 0 ? p.batch : 1) >= sm_count) return launch_cfg<256, 64, 8, 8>(p, stream);
 	const long long big_tiles = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128) * (p.batch > 0 ? p.batch : 1);
 	if (big_tiles >= sm_count) return launch_cfg<128, 128, 8, 8>(p, stream);
 	return launch_cfg<64, 64, 4, 4>(p, stream);
