@@ -27,4 +27,24 @@ x = rng.uniform(-1, 1, 8 * 14 * 14).astype(np.float32); w = rng.uniform(-1, 1, 1
 out = np.zeros(16 * 14 * 14, np.float32)
 u.convolution_cuda_LReLU(x, 8, 14, 14, w, 3, 1, 1, out, 16, b)
 print("conv ok", float(np.abs(out).sum()) > 0)
+# K2's interior fast path (aligned, whole tiles) and the narrow / 256x64 tiles
+case("simt", "N", "N", 256, 256, 64, (0, 0, 0))
+case("simt", "T", "T", 256, 128, 48, (0, 0, 0))
+case("simt", "N", "N", 300, 16, 70, (0, 0, 0))
+case("simt", "N", "N", 512, 24, 40, (3, 1, 5))
+# level 1 / level 2
+for n, ix, iy in ((1000, 1, 1), (1027, 1, 1), (333, 2, 3)):
+    xs = rng.uniform(-1, 1, (n - 1) * ix + 1).astype(np.float32); ys = rng.uniform(-1, 1, (n - 1) * iy + 1).astype(np.float32)
+    want = ys.copy(); want[::iy] = np.float32(0.5) * xs[::ix] + want[::iy]
+    u.saxpy_cuda(n, 0.5, xs, ix, ys, iy)
+    assert np.abs(ys - want).max() < 1e-6
+for trans, M, N, pad in (("N", 300, 200, 0), ("N", 512, 4100, 0), ("N", 130, 77, 3), ("T", 300, 200, 0), ("T", 3, 5000, 4), ("T", 17, 33, 1)):
+    lines, cols = (N, M) if trans == "N" else (M, N)
+    Am = rng.uniform(0, 1, (lines, cols + pad)).astype(np.float32); xv = rng.uniform(-1, 1, N).astype(np.float32); yv = rng.uniform(0, 1, M).astype(np.float32)
+    op = Am[:, :cols].T if trans == "N" else Am[:, :cols]
+    want = 1.5 * (op.astype(np.float64) @ xv) + 0.5 * yv
+    u.sgemv_cuda(trans, M, N, 1.5, Am.ravel(), cols + pad, xv, 1, 0.5, yv, 1)
+    e = np.linalg.norm(yv - want) / np.linalg.norm(want)
+    print("sgemv", trans, M, N, pad, "relerr %.2e" % e, flush=True)
+    assert e < 1e-5
 u.sgemm_cuda_finish()

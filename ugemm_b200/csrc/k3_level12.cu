@@ -102,40 +102,82 @@ sgemv_rows_kernel(int M, int N, float alpha, const float *__restrict__ A, long l
 	}
 }
 
-// Columns of A contiguous along the OUTPUT index (the reference's trans == 'N' case, A[m + n*lda]): a warp owns 32
-// consecutive m (one coalesced 128-byte line per n), the 8 warps of a block take n = w, w+8, ... and their partial
-// sums meet in shared memory.  Four n per trip keep four lines in flight per warp.
+// Columns of A contiguous along the OUTPUT index (the reference's trans == 'N' case, A[m + n*lda]): a lane owns V
+// consecutive m (V = 4: one 128-bit load per n when the layout allows, else V = 1), a warp 32*V of them (one or four
+// coalesced 128-byte lines per n); the 8 warps of a block take n = w, w+8, ... of the block's n range and meet in
+// shared memory.  Four n per trip keep four lines in flight per lane.  When M alone cannot fill the machine the n range
+// is cut over grid.y and the slices' partial sums go to a scratch array [slices][M] that sgemv_finish_kernel adds up in
+// a fixed order (no atomics: the result does not depend on scheduling).
+template <int V>
 __global__ void __launch_bounds__(L12_THREADS)
-sgemv_cols_kernel(int M, int N, float alpha, const float *__restrict__ A, long long lda, const float *__restrict__ x, long long incx,
-                  float beta, float *__restrict__ y, long long incy)
+sgemv_cols_kernel(int M, int N, int n_per_slice, float alpha, const float *__restrict__ A, long long lda, const float *__restrict__ x,
+                  long long incx, float beta, float *__restrict__ y, long long incy, float *__restrict__ partial)
 {
 	constexpr int WARPS = L12_THREADS / 32;
-	__shared__ float part[WARPS][32];
+	__shared__ float part[WARPS][32 * V];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const long long m = (long long)blockIdx.x * 32 + lane;
-	float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+	const long long m = ((long long)blockIdx.x * 32 + lane) * V;
+	const int n0 = blockIdx.y * n_per_slice, n1 = min(N, n0 + n_per_slice);
+	float s[4][V];
+#pragma unroll
+	for (int u = 0; u < 4; u++)
+#pragma unroll
+		for (int v = 0; v < V; v++) s[u][v] = 0.f;
 	if (m < M) {
 		const float *col = A + m;
-		int n = w;
-		for (; n + 3 * WARPS < N; n += 4 * WARPS) {
-			const float a0 = __ldg(col + (long long)n * lda), a1 = __ldg(col + (long long)(n + WARPS) * lda);
-			const float a2 = __ldg(col + (long long)(n + 2 * WARPS) * lda), a3 = __ldg(col + (long long)(n + 3 * WARPS) * lda);
-			s0 = fmaf(a0, __ldg(x + (long long)n * incx), s0);
-			s1 = fmaf(a1, __ldg(x + (long long)(n + WARPS) * incx), s1);
-			s2 = fmaf(a2, __ldg(x + (long long)(n + 2 * WARPS) * incx), s2);
-			s3 = fmaf(a3, __ldg(x + (long long)(n + 3 * WARPS) * incx), s3);
-		}
-		for (; n < N; n += WARPS) s0 = fmaf(__ldg(col + (long long)n * lda), __ldg(x + (long long)n * incx), s0);
-	}
-	part[w][lane] = (s0 + s1) + (s2 + s3);
-	__syncthreads();
-	if (w == 0 && m < M) {
-		float s = 0.f;
+		auto ld = [&](int n, float (&a)[V]) {
+			if (V == 4) {
+				const float4 q = __ldg(reinterpret_cast<const float4 *>(col + (long long)n * lda));
+				a[0] = q.x; a[1] = q.y; a[2] = q.z; a[3] = q.w;
+			} else {
+				a[0] = __ldg(col + (long long)n * lda);
+			}
+		};
+		int n = n0 + w;
+		for (; n + 3 * WARPS < n1; n += 4 * WARPS) {
+			float a[4][V], xv[4];
 #pragma unroll
-		for (int i = 0; i < WARPS; i++) s += part[i][lane];
-		float *yp = y + m * incy;
-		*yp = (beta == 0.f) ? alpha * s : fmaf(alpha, s, beta * *yp);
+			for (int u = 0; u < 4; u++) { ld(n + u * WARPS, a[u]); xv[u] = __ldg(x + (long long)(n + u * WARPS) * incx); }
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+#pragma unroll
+				for (int v = 0; v < V; v++) s[u][v] = fmaf(a[u][v], xv[u], s[u][v]);
+		}
+		for (; n < n1; n += WARPS) {
+			float a[V];
+			ld(n, a);
+			const float xv = __ldg(x + (long long)n * incx);
+#pragma unroll
+			for (int v = 0; v < V; v++) s[0][v] = fmaf(a[v], xv, s[0][v]);
+		}
 	}
+#pragma unroll
+	for (int v = 0; v < V; v++) part[w][lane * V + v] = (s[0][v] + s[1][v]) + (s[2][v] + s[3][v]);
+	__syncthreads();
+	// one thread per output of the block adds the 8 warps' sums in warp order
+	for (int o = threadIdx.x; o < 32 * V; o += L12_THREADS) {
+		const long long mo = (long long)blockIdx.x * 32 * V + o;
+		if (mo >= M) continue;
+		float t = 0.f;
+#pragma unroll
+		for (int i = 0; i < WARPS; i++) t += part[i][o];
+		if (partial) partial[(long long)blockIdx.y * M + mo] = t;
+		else {
+			float *yp = y + mo * incy;
+			*yp = (beta == 0.f) ? alpha * t : fmaf(alpha, t, beta * *yp);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(L12_THREADS)
+sgemv_finish_kernel(int M, int slices, float alpha, const float *__restrict__ partial, float beta, float *__restrict__ y, long long incy)
+{
+	const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= M) return;
+	float t = 0.f;
+	for (int sl = 0; sl < slices; sl++) t += partial[(long long)sl * M + m];
+	float *yp = y + m * incy;
+	*yp = (beta == 0.f) ? alpha * t : fmaf(alpha, t, beta * *yp);
 }
 
 bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -178,7 +220,35 @@ cudaError_t launch_sgemv(bool rows_contiguous, int M, int N, float alpha, const 
 		else
 			sgemv_rows_kernel<L12_THREADS><<<(unsigned)M, L12_THREADS, 0, stream>>>(M, N, alpha, A, lda, x, incx, beta, y, incy, vec);
 	} else {
-		sgemv_cols_kernel<<<(unsigned)((M + 31) / 32), L12_THREADS, 0, stream>>>(M, N, alpha, A, lda, x, incx, beta, y, incy);
+		const bool vec = al16(A) && lda % 4 == 0 && M % 4 == 0;
+		const int per_block = vec ? 128 : 32;
+		const long long bx = ((long long)M + per_block - 1) / per_block;
+		// enough blocks for ~4 per SM; a slice keeps >= 256 n so the slicing overhead stays small
+		long long slices = ((long long)sm_count * 4 + bx - 1) / bx;
+		if (slices > (N + 255) / 256) slices = (N + 255) / 256;
+		if (slices < 1) slices = 1;
+		if (slices > 65535) slices = 65535;
+		const int n_per_slice = (int)(((long long)N + slices - 1) / slices);
+		slices = n_per_slice > 0 ? ((long long)N + n_per_slice - 1) / n_per_slice : 1;
+		if (slices < 1) slices = 1;
+		float *partial = nullptr;
+		if (slices > 1 && cudaMallocAsync(reinterpret_cast<void **>(&partial), (size_t)slices * M * sizeof(float), stream) != cudaSuccess) {
+			cudaGetLastError();
+			slices = 1;      // no scratch: one slice per block column, still correct
+		}
+		const int nps = slices > 1 ? n_per_slice : (N > 0 ? N : 1);
+		dim3 grid((unsigned)bx, (unsigned)slices);
+		if (vec) sgemv_cols_kernel<4><<<grid, L12_THREADS, 0, stream>>>(M, N, nps, alpha, A, lda, x, incx, beta, y, incy, slices > 1 ? partial : nullptr);
+		else     sgemv_cols_kernel<1><<<grid, L12_THREADS, 0, stream>>>(M, N, nps, alpha, A, lda, x, incx, beta, y, incy, slices > 1 ? partial : nullptr);
+		cudaError_t e = cudaGetLastError();
+		if (slices > 1) {
+			if (e == cudaSuccess) {
+				sgemv_finish_kernel<<<(unsigned)((M + L12_THREADS - 1) / L12_THREADS), L12_THREADS, 0, stream>>>(M, (int)slices, alpha, partial, beta, y, incy);
+				e = cudaGetLastError();
+			}
+			cudaFreeAsync(partial, stream);
+		}
+		return e;
 	}
 	return cudaGetLastError();
 }
