@@ -160,6 +160,45 @@ def k1_traffic_bytes(wl_name):
         return None
 
 
+def other_shapes(u, peaks, info):
+    """The other named BASELINE shapes at 1 GPU (north_star: every named shape in TFLOP/s and as a fraction of the relevant
+    roofline).  Reported beside the headline, never part of `value`.  Each: 3 warm-ups, 10 launches, CUDA events, best and mean."""
+    tensor_peak = peaks["bf16_burst"] / 6.0
+    ffma_peak = info["sm_count"] * 128 * 2 * info["sm_clock_khz"] * 1e3 / 1e12      # SMs x 128 lanes x 2 flop x max clock
+    out = []
+
+    def run(name, mode, ta, tb, M, N, K, alpha, beta, lda, ldb, ldc, bound):
+        ar, br = (M if ta == "N" else K), (K if tb == "N" else N)
+        dA, dB, dC = u.DeviceBuffer(ar * lda).fill_uniform(1), u.DeviceBuffer(br * ldb).fill_uniform(2), u.DeviceBuffer(M * ldc).fill_uniform(3)
+        avg, best = u.sgemm_cuda_time_dev(mode, 10, 3, "R", ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc)
+        kern = u.last_kernel() + (" (operands repacked for TMA)" if u.last_repacked() else "")
+        flops = 2.0 * M * N * K
+        nbytes = 4.0 * (M * K + K * N + M * N * (2 if beta != 0 else 1))
+        peak = tensor_peak if u.last_kernel() == "3xtf32" else ffma_peak
+        rec = {"shape": name, "mode": mode, "kernel": kern, "ms_avg": avg, "ms_min": best, "tflops": flops / avg / 1e9,
+               "roofline_bound": "tensor (3xTF32)" if u.last_kernel() == "3xtf32" else "fp32 FFMA", "roofline_peak_tflops": peak,
+               "roofline_frac": flops / avg / 1e9 / peak, "algorithmic_gbs": nbytes / avg / 1e6,
+               "hbm_frac": nbytes / avg / 1e6 / peaks["hbm_gbs"]}
+        if bound:
+            rec["note"] = bound
+        out.append(rec)
+        for b in (dA, dB, dC):
+            b.free()
+
+    run("c2 8192^3 NN, K2 plain-fp32 mode", "simt", "N", "N", 8192, 8192, 8192, 1.0, 0.0, 8192, 8192, 8192, None)
+    for ta, tb in (("N", "T"), ("T", "N"), ("T", "T")):
+        M, N, K = 4095, 3001, 2047
+        lda = (K if ta == "N" else M) + 1   # 2048 / 4096: multiples of 4 -> TMA-eligible
+        ldb = (N if tb == "N" else K) + (3 if tb == "N" else 1)
+        run(f"c3 4095x3001x2047 {ta}{tb} alpha=1.5 beta=0.5, ld padded to a multiple of 4", "auto", ta, tb, M, N, K, 1.5, 0.5, lda, ldb, N + 3, None)
+    run("c3 4095x3001x2047 NT alpha=1.5 beta=0.5, odd ld (K+5, K+3, N+7)", "auto", "N", "T", 4095, 3001, 2047, 1.5, 0.5, 2047 + 5, 2047 + 3, 3001 + 7,
+        "TMA-ineligible layout: auto rule (2) repacks, forced simt runs K2 on it directly")
+    run("c4 200704x256x1152 NN (im2col shape)", "auto", "N", "N", 200704, 256, 1152, 1.0, 0.0, 1152, 256, 256,
+        "AI 105 flop/B: above the 3xTF32 ridge, HBM time is ~40% of the tensor time (SURVEY 8d)")
+    run("c4 200704x256x1152 NN beta=1 (accumulate)", "auto", "N", "N", 200704, 256, 1152, 1.0, 1.0, 1152, 256, 256, None)
+    return out
+
+
 def run_single(args, wl_name):
     import numpy as np
 
@@ -206,6 +245,7 @@ def run_single(args, wl_name):
         L.ugemm_cuda_free_host(h)
 
     peaks = measured_peaks()
+    shapes = other_shapes(u, peaks, info) if (wl_name == "c2" and not args.no_shapes) else None
     # a kernel timed alone over a short burst of steps -> burst peak; TF32 dense = bf16 dense / 2; 3 MMAs per product
     peak = peaks["bf16_burst"] / 6.0
     achieved = flops / avg_ms / 1e9
@@ -228,6 +268,8 @@ def run_single(args, wl_name):
                      "nominal_frac": achieved / 375.0},
         "cpu_baseline": {"value": cpu_tf, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
     }
+    if shapes is not None:
+        line["other_shapes"] = shapes
     print(json.dumps(line), flush=True)
 
 
@@ -386,6 +428,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None] + list(WORKLOADS))
+    ap.add_argument("--no-shapes", action="store_true", help="skip the side table of the other BASELINE shapes (N = 1 only)")
     ap.add_argument("--dist", default=os.environ.get("UGEMM_BENCH_DIST", "p2p"), choices=["nccl", "p2p"],
                     help="panel transport for --gpus N > 1: NCCL broadcast or copy-engine peer pull")
     args = ap.parse_args()
