@@ -1,7 +1,7 @@
 # Top-level build for C users of the backend (the Python tests/bench use ugemm_b200/build.py, same flags).
 NVCC  ?= nvcc
 ARCH  := -gencode arch=compute_100a,code=sm_100a
-SRC   := ugemm_b200/csrc/backend.cu ugemm_b200/csrc/k1_tcgen05.cu ugemm_b200/csrc/k2_simt.cu ugemm_b200/csrc/k3_level12.cu
+SRC   := ugemm_b200/csrc/backend.cu ugemm_b200/csrc/k1_tcgen05.cu ugemm_b200/csrc/k2_simt.cu ugemm_b200/csrc/k3_level12.cu ugemm_b200/csrc/k4_dgemm.cu
 LIB   := ugemm_b200/libugemm_cuda.so
 
 all: $(LIB) oracle harness

@@ -186,6 +186,19 @@ void sgemv_cuda(char trans, int M, int N, float alpha, const float *A, int lda, 
 int  sgemv_cuda_dev(void *stream, char trans, int M, int N, float alpha, const float *dA, int lda, const float *dx, int incx,
                     float beta, float *dy, int incy);
 
+/* ---- DGEMM: the path of check_dgemm.c.  Same 14-argument signature in double as dgemm_cpu (ugemm.h:162-178), _dgemm_c
+ * (gemm_cpu.h:284-298 instantiated with real = double, ugemm.h:29-33) and dgemm_avx (dgemm_avx.h:844-858), i.e. usable as the
+ * `uut` of test_dgemm (check_dgemm.c:86-97,255-258).  One kernel (K4, register-blocked DFMA, FP64-pipe bound); semantics,
+ * quirk decisions and error behaviour are those of sgemm_cuda.  dgemm_cuda: host pointers, blocking.  dgemm_cuda_dev:
+ * device pointers, asynchronous.  dgemm_cuda_time_dev: mean / best of `iters` launches by CUDA events.  0 on success. */
+void dgemm_cuda(char major, char transA, char transB, int M, int N, int K, double alpha,
+                const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc);
+int  dgemm_cuda_dev(void *stream, char major, char transA, char transB, int M, int N, int K, double alpha,
+                    const double *dA, int lda, const double *dB, int ldb, double beta, double *dC, int ldc);
+int  dgemm_cuda_time_dev(int iters, int warmup, char major, char transA, char transB, int M, int N, int K, double alpha,
+                         const double *dA, int lda, const double *dB, int ldb, double beta, double *dC, int ldc,
+                         float *ms_avg, float *ms_min);
+
 /* ---- hardware probe used by tests/DESIGN.md: runs one 128 x 16 x (8*ksteps) TF32 tcgen05 product
  * chain on raw fp32 bit patterns and returns the 128x16 fp32 accumulator, so the rounding behaviour of
  * the tensor core (operand truncation, accumulator rounding) can be pinned.  A: 128 x 8*ksteps row-major,

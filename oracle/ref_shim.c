@@ -14,6 +14,9 @@
  *   ref_sgemm_sse  -> sgemm_sse   sgemm_sse.h:365   AVX 8x8 Goto (static in the header)
  *   ref_saxpy_cpu  -> saxpy_cpu   ugemm.h:75        y += alpha*x
  *   ref_sgemv_cpu  -> sgemv_cpu   ugemm.h:124       naive gemv
+ *   ref_dgemm_cpu  -> dgemm_cpu   ugemm.h:162       naive double-precision ground truth
+ *   ref_dgemm_c    -> _dgemm_c    gemm_cpu.h:284 with real = double (ugemm.h:29-33)
+ *   ref_dgemm_avx  -> dgemm_avx   dgemm_avx.h:844   AVX Goto DGEMM, all majors / transposes
  *   ref_sgemm_avx_mt: harness-level wrapper, sgemm_avx on disjoint row slabs of
  *                  A/C from `threads` OpenMP threads.  Legal because all state of
  *                  avx256_noncblas_sgemm lives in the stack-allocated
@@ -40,6 +43,12 @@ void ref_saxpy_cpu(int N, float alpha, const float *x, int incx, float *y, int i
 void ref_sgemv_cpu(char trans, int M, int N, float alpha, const float *A, int lda, const float *x, int incx,
                    float beta, float *y, int incy)
 { sgemv_cpu(trans, M, N, alpha, A, lda, x, incx, beta, y, incy); }
+
+#define DSIG char major, char ta, char tb, int M, int N, int K, double alpha, \
+             const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc
+void ref_dgemm_cpu(DSIG) { dgemm_cpu(ARGS); }
+void ref_dgemm_c  (DSIG) { _dgemm_c(ARGS); }
+void ref_dgemm_avx(DSIG) { dgemm_avx(ARGS); }
 
 int ref_max_threads(void)
 {

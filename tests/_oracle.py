@@ -18,6 +18,9 @@ _SIG14 = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_float,
           _f32p, C.c_int, _f32p, C.c_int, C.c_float, _f32p, C.c_int]
 
 
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_DSIG14 = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double,
+           _f64p, C.c_int, _f64p, C.c_int, C.c_double, _f64p, C.c_int]
 _AXPY = [C.c_int, C.c_float, _f32p, C.c_int, _f32p, C.c_int]
 _GEMV = [C.c_char, C.c_int, C.c_int, C.c_float, _f32p, C.c_int, _f32p, C.c_int, C.c_float, _f32p, C.c_int]
 
@@ -58,6 +61,10 @@ def oracle():
         lib.oracle_convolution.argtypes = [C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p,
                                            C.c_int, C.c_void_p, C.c_float, _f32p]
         lib.oracle_convolution.restype = None
+        lib.oracle_dgemm_naive.argtypes = _DSIG14
+        lib.oracle_dgemm_naive.restype = None
+        lib.oracle_relerr_f64.argtypes = [C.c_int, C.c_int, _f64p, _f64p, C.c_int]
+        lib.oracle_relerr_f64.restype = C.c_double
         lib.oracle_saxpy.argtypes = _AXPY
         lib.oracle_saxpy.restype = None
         lib.oracle_sgemv.argtypes = _GEMV
@@ -85,6 +92,10 @@ def ref():
             lib.ref_saxpy_cpu.restype = None
             lib.ref_sgemv_cpu.argtypes = _GEMV
             lib.ref_sgemv_cpu.restype = None
+        if hasattr(lib, "ref_dgemm_cpu"):
+            for name in ("ref_dgemm_cpu", "ref_dgemm_c", "ref_dgemm_avx"):
+                getattr(lib, name).argtypes = _DSIG14
+                getattr(lib, name).restype = None
         _ref = lib
     return _ref
 
@@ -136,3 +147,18 @@ def run14(fn, major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc, thre
     else:
         fn(threads, *args)
     return out
+
+
+def make_problem_f64(major, ta, tb, M, N, K, pad=(0, 0, 0), seed=1, lo=0.0, hi=1.0, sentinel=None):
+    """float64 twin of make_problem: the seeded fp32 stream widened to double plus a second stream scaled by 2^-24, so
+    the low mantissa bits are populated too (a DGEMM that secretly computed in fp32 would fail the gate)."""
+    (ar, ac), (br, bc), (cr, cc) = stored_shapes(major, ta, tb, M, N, K)
+    lda, ldb, ldc = ac + pad[0], bc + pad[1], cc + pad[2]
+
+    def stream(n, s):
+        return fill_uniform(max(n, 1), s, lo, hi).astype(np.float64) + fill_uniform(max(n, 1), s + 7919, 0.0, 1.0).astype(np.float64) * 2.0 ** -24
+
+    A, B, Cm = stream(ar * lda, seed * 3), stream(br * ldb, seed * 3 + 1), stream(cr * ldc, seed * 3 + 2)
+    if sentinel is not None and pad[2]:
+        Cm.reshape(cr, ldc)[:, cc:] = sentinel
+    return A, lda, B, ldb, Cm, ldc

@@ -16,7 +16,7 @@ HEADER = os.path.join(ROOT, "include", "ugemm_cuda.h")
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b((?:sgemm_cuda|ugemm_cuda|ugemm_fill|im2col_cuda|convolution_cuda|saxpy_cuda|sgemv_cuda)\w*)\s*\(", src)
+    names = re.findall(r"\b((?:sgemm_cuda|ugemm_cuda|ugemm_fill|im2col_cuda|convolution_cuda|saxpy_cuda|sgemv_cuda|dgemm_cuda)\w*)\s*\(", src)
     return sorted(set(names))
 
 

@@ -11,5 +11,5 @@ from .backend import (  # noqa: F401
     k1_eligible, last_error, last_kernel, last_repacked, launch_count, lib, probe_tf32, set_k1_tuning, set_sm_limit, sgemm_cuda,
     sgemm_cuda_3xtf32, sgemm_cuda_batched, sgemm_cuda_batched_dev, sgemm_cuda_dev, sgemm_cuda_finish, sgemm_cuda_init, sgemm_cuda_simt, sgemm_cuda_time_dev,
     sgemm_finish, sgemm_init, sgemm_rnn, sgemm_rnt, sgemm_rtn, sync,
-    saxpy_cuda, saxpy_cuda_dev, sgemv_cuda, sgemv_cuda_dev,
+    saxpy_cuda, saxpy_cuda_dev, sgemv_cuda, sgemv_cuda_dev, dgemm_cuda, dgemm_cuda_dev, dgemm_cuda_time_dev,
 )

@@ -23,13 +23,13 @@ class UgemmCudaError(RuntimeError):
     pass
 
 
-def _ptr(x):
+def _ptr(x, dtype=np.float32):
     """Host numpy array / device pointer int / object with data_ptr() -> c_void_p."""
     if x is None:
         return C.c_void_p(0)
     if isinstance(x, np.ndarray):
-        if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
-            raise TypeError("host buffers must be C-contiguous float32 numpy arrays")
+        if x.dtype != dtype or not x.flags["C_CONTIGUOUS"]:
+            raise TypeError(f"host buffers must be C-contiguous {np.dtype(dtype).name} numpy arrays")
         return C.c_void_p(x.ctypes.data)
     if hasattr(x, "data_ptr"):
         return C.c_void_p(x.data_ptr())
@@ -129,6 +129,14 @@ def lib():
     L.sgemv_cuda.restype = None
     L.sgemv_cuda_dev.argtypes = [C.c_void_p] + L.sgemv_cuda.argtypes
     L.sgemv_cuda_dev.restype = C.c_int
+    dsig14 = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double,
+              C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+    L.dgemm_cuda.argtypes = dsig14
+    L.dgemm_cuda.restype = None
+    L.dgemm_cuda_dev.argtypes = [C.c_void_p] + dsig14
+    L.dgemm_cuda_dev.restype = C.c_int
+    L.dgemm_cuda_time_dev.argtypes = [C.c_int, C.c_int] + dsig14 + [C.POINTER(C.c_float)] * 2
+    L.dgemm_cuda_time_dev.restype = C.c_int
     L.ugemm_cuda_probe_tf32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.ugemm_cuda_probe_tf32.restype = C.c_int
     _lib = L
@@ -145,6 +153,7 @@ EXPORTED_SYMBOLS = [
     "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
     "ugemm_cuda_probe_tf32", "im2col_cuda", "im2col_cuda_dev", "convolution_cuda", "convolution_cuda_LReLU",
     "convolution_cuda_dev", "saxpy_cuda", "saxpy_cuda_dev", "sgemv_cuda", "sgemv_cuda_dev",
+    "dgemm_cuda", "dgemm_cuda_dev", "dgemm_cuda_time_dev",
 ]
 
 
@@ -410,6 +419,29 @@ def sgemv_cuda_dev(stream, trans, M, N, alpha, dA, lda, dx, incx, beta, dy, incy
     if lib().sgemv_cuda_dev(C.c_void_p(stream or 0), _b(trans), M, N, alpha, _ptr(dA), lda, _ptr(dx), incx, beta, _ptr(dy), incy):
         check()
         raise UgemmCudaError("sgemv_cuda_dev failed")
+
+
+# ---- DGEMM (the uut signature of check_dgemm.c:86-97) ------------------------------------------------------
+def dgemm_cuda(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
+    """Host float64 buffers, blocking, C updated in place."""
+    f8 = np.float64
+    lib().dgemm_cuda(_b(major), _b(ta), _b(tb), M, N, K, alpha, _ptr(A, f8), lda, _ptr(B, f8), ldb, beta, _ptr(Cm, f8), ldc)
+    check()
+
+
+def dgemm_cuda_dev(stream, major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc):
+    if lib().dgemm_cuda_dev(C.c_void_p(stream or 0), _b(major), _b(ta), _b(tb), M, N, K, alpha, _ptr(dA), lda, _ptr(dB), ldb, beta, _ptr(dC), ldc):
+        check()
+        raise UgemmCudaError("dgemm_cuda_dev failed")
+
+
+def dgemm_cuda_time_dev(iters, warmup, major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc):
+    avg, best = C.c_float(0), C.c_float(0)
+    if lib().dgemm_cuda_time_dev(iters, warmup, _b(major), _b(ta), _b(tb), M, N, K, alpha, _ptr(dA), lda, _ptr(dB), ldb, beta, _ptr(dC), ldc,
+                                 C.byref(avg), C.byref(best)):
+        check()
+        raise UgemmCudaError("dgemm_cuda_time_dev failed")
+    return avg.value, best.value
 
 
 # ---- the macro API of the reference's GPU harness (sgemm_test.c:19-33): tight row-major, no ld ----------

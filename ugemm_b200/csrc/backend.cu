@@ -840,6 +840,115 @@ void sgemv_cuda(char trans, int M, int N, float alpha, const float *A, int lda, 
 	if (e != cudaSuccess) set_error("sgemv failed: %s", cudaGetErrorString(e));
 }
 
+// ---- DGEMM (check_dgemm.c's path) ----------------------------------------------------------
+static int dnormalise(char major, char ta, char tb, int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb,
+                      double beta, double *C, int ldc, DProblem *p)
+{
+	major = (char)upper(major); ta = (char)upper(ta); tb = (char)upper(tb);
+	if (major != 'R' && major != 'C') { set_error("major must be 'R' or 'C' (got 0x%02x)", major); return 1; }
+	if ((ta != 'N' && ta != 'T') || (tb != 'N' && tb != 'T')) { set_error("transA/transB must be 'N' or 'T'"); return 1; }
+	if (M < 0 || N < 0 || K < 0) { set_error("negative dimension M=%d N=%d K=%d", M, N, K); return 1; }
+	if (major == 'C') {   // column-major C = op(A) op(B) is row-major C^T = op(B)^T op(A)^T over the same buffers
+		const double *tp = A; A = B; B = tp;
+		int ti = lda; lda = ldb; ldb = ti;
+		ti = M; M = N; N = ti;
+		char tc = ta; ta = tb; tb = tc;
+	}
+	const int a_cols = ta == 'N' ? K : M, b_cols = tb == 'N' ? N : K;
+	if (lda < (a_cols > 1 ? a_cols : 1) || ldb < (b_cols > 1 ? b_cols : 1) || ldc < (N > 1 ? N : 1)) {
+		set_error("leading dimension too small (lda=%d ldb=%d ldc=%d for stored widths %d %d %d)", lda, ldb, ldc, a_cols, b_cols, N);
+		return 1;
+	}
+	p->M = M; p->N = N; p->K = K; p->alpha = alpha; p->beta = beta;
+	p->A = A; p->lda = lda; p->a_kmajor = (ta == 'N');
+	p->B = B; p->ldb = ldb; p->b_kmajor = (tb == 'T');
+	p->C = C; p->ldc = ldc;
+	return 0;
+}
+
+static int drun_dev(cudaStream_t stream, const DProblem &p)
+{
+	if (p.M == 0 || p.N == 0) return 0;
+	if ((p.alpha == 0.0 || p.K == 0) && p.beta == 1.0) return 0;
+	if (p.alpha == 0.0 || p.K == 0) CU_TRY(launch_scale_c_f64(p, stream), "scale_c (f64) launch");
+	else CU_TRY(launch_k4_dgemm(p, stream), "K4 (DFMA DGEMM) launch");
+	g.launches++;
+	return 0;
+}
+
+int dgemm_cuda_dev(void *stream, char major, char ta, char tb, int M, int N, int K, double alpha, const double *dA, int lda,
+                   const double *dB, int ldb, double beta, double *dC, int ldc)
+{
+	if (ensure_init()) return 1;
+	DProblem p;
+	if (dnormalise(major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, &p)) return 1;
+	return drun_dev(stream ? static_cast<cudaStream_t>(stream) : g.stream, p);
+}
+
+void dgemm_cuda(char major, char ta, char tb, int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb,
+                double beta, double *C, int ldc)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (ensure_init()) return;
+	DProblem p;
+	if (dnormalise(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, &p)) return;
+	if (p.M == 0 || p.N == 0) return;
+	if ((p.alpha == 0.0 || p.K == 0) && p.beta == 1.0) return;
+	const bool need_ab = !(p.alpha == 0.0 || p.K == 0);
+	const long long a_lines = p.a_kmajor ? p.M : p.K, a_cols = p.a_kmajor ? p.K : p.M;
+	const long long b_lines = p.b_kmajor ? p.N : p.K, b_cols = p.b_kmajor ? p.K : p.N;
+	const size_t a_bytes = need_ab ? (size_t)((a_lines - 1) * p.lda + a_cols) * 8 : 0;
+	const size_t b_bytes = need_ab ? (size_t)((b_lines - 1) * p.ldb + b_cols) * 8 : 0;
+	const size_t c_bytes = (size_t)((long long)(p.M - 1) * p.ldc + p.N) * 8;
+	const size_t offB = align_up(a_bytes, 256), offC = align_up(offB + b_bytes, 256);
+	if (ensure_arena(offC + c_bytes)) return;
+	double *dA = reinterpret_cast<double *>(g.arena), *dB = reinterpret_cast<double *>(g.arena + offB), *dC = reinterpret_cast<double *>(g.arena + offC);
+	cudaError_t e = cudaSuccess;
+	auto up2d = [&](double *d, const double *h, long long ld, long long lines, long long cols) {
+		if (e != cudaSuccess || lines <= 0 || cols <= 0) return;
+		if (ld == cols) e = cudaMemcpyAsync(d, h, (size_t)lines * cols * 8, cudaMemcpyHostToDevice, g.stream);
+		else e = cudaMemcpy2DAsync(d, (size_t)ld * 8, h, (size_t)ld * 8, (size_t)cols * 8, (size_t)lines, cudaMemcpyHostToDevice, g.stream);
+	};
+	if (need_ab) { up2d(dA, p.A, p.lda, a_lines, a_cols); up2d(dB, p.B, p.ldb, b_lines, b_cols); }
+	if (p.beta != 0.0) up2d(dC, p.C, p.ldc, p.M, p.N);
+	if (e != cudaSuccess) { set_error("dgemm H2D copy failed: %s", cudaGetErrorString(e)); return; }
+	DProblem d = p;
+	d.A = dA; d.B = dB; d.C = dC;
+	if (drun_dev(g.stream, d)) return;
+	if (p.ldc == p.N) e = cudaMemcpyAsync(p.C, dC, (size_t)p.M * p.N * 8, cudaMemcpyDeviceToHost, g.stream);
+	else e = cudaMemcpy2DAsync(p.C, (size_t)p.ldc * 8, dC, (size_t)p.ldc * 8, (size_t)p.N * 8, (size_t)p.M, cudaMemcpyDeviceToHost, g.stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+	if (e != cudaSuccess) set_error("dgemm failed: %s", cudaGetErrorString(e));
+}
+
+int dgemm_cuda_time_dev(int iters, int warmup, char major, char ta, char tb, int M, int N, int K, double alpha, const double *dA, int lda,
+                        const double *dB, int ldb, double beta, double *dC, int ldc, float *ms_avg, float *ms_min)
+{
+	if (ensure_init()) return 1;
+	if (iters < 1) iters = 1;
+	if (iters > 1024) iters = 1024;
+	DProblem p;
+	if (dnormalise(major, ta, tb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, &p)) return 1;
+	for (int i = 0; i < warmup; i++)
+		if (drun_dev(g.stream, p)) return 1;
+	CU_TRY(cudaStreamSynchronize(g.stream), "warm-up sync");
+	cudaEvent_t ev[2];
+	float total = 0.f, best = 1e30f;
+	CU_TRY(cudaEventCreate(&ev[0]), "cudaEventCreate");
+	CU_TRY(cudaEventCreate(&ev[1]), "cudaEventCreate");
+	int rc = 0;
+	for (int i = 0; i < iters && !rc; i++) {
+		cudaEventRecord(ev[0], g.stream);
+		rc = drun_dev(g.stream, p);
+		cudaEventRecord(ev[1], g.stream);
+		if (!rc && cudaEventSynchronize(ev[1]) != cudaSuccess) { set_error("timed dgemm launch failed"); rc = 1; }
+		if (!rc) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[0], ev[1]); total += ms; if (ms < best) best = ms; }
+	}
+	cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+	if (!rc) { if (ms_avg) *ms_avg = total / iters; if (ms_min) *ms_min = best; }
+	return rc;
+}
+
 int ugemm_cuda_probe_tf32(const float *A, const float *B, float *D, int ksteps)
 {
 	if (ensure_init()) return 1;

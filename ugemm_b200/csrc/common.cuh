@@ -25,6 +25,15 @@ struct Problem {
 	long long strideA = 0, strideB = 0, strideC = 0;
 };
 
+// DGEMM (K4) problem, normalised to row-major like Problem
+struct DProblem {
+	int M, N, K;
+	double alpha, beta;
+	const double *A; long long lda; bool a_kmajor;
+	const double *B; long long ldb; bool b_kmajor;
+	double *C; long long ldc;
+};
+
 // flags: bit0 = share one shared-memory read of A_big between big*small and big*big (A collector);
 // bits 1-4 are ABLATION switches for bottleneck analysis only (results are wrong with them):
 // 2 transform skips its stores, 4 transform skips loads and stores, 8 only big*big is issued, 16 epilogue skips stores,
@@ -44,6 +53,9 @@ cudaError_t launch_im2col(const float *im, int channels, int height, int width, 
 cudaError_t launch_saxpy(long long n, float alpha, const float *x, long long incx, float *y, long long incy, cudaStream_t stream, int sm_count);
 cudaError_t launch_sgemv(bool rows_contiguous, int M, int N, float alpha, const float *A, long long lda, const float *x, long long incx,
                          float beta, float *y, long long incy, cudaStream_t stream, int sm_count);
+// K4: register-blocked DFMA DGEMM (k4_dgemm.cu) and its C <- beta*C companion
+cudaError_t launch_k4_dgemm(const DProblem &p, cudaStream_t stream);
+cudaError_t launch_scale_c_f64(const DProblem &p, cudaStream_t stream);
 // probe (k1_tcgen05.cu)
 cudaError_t launch_probe_tf32(const float *dA, const float *dB, float *dD, int ksteps, cudaStream_t stream);
 // last diagnostic record written by a K1 watchdog (host-mapped memory), 0 if none
