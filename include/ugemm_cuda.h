@@ -158,7 +158,18 @@ int  ugemm_fill_uniform_dev_2d(float *dx, size_t rows, size_t cols, size_t ld, u
  *                          (sgemm_ocl1.h:301-338): + bias[ch] and LeakyReLU(0.1), FUSED into the GEMM epilogue instead of
  *                          the reference's separate host loop (sgemm_gl1.h:210-217).
  *   *_dev                  device pointers, asynchronous; d_workspace holds ich*k*k*Ho*Wo floats; d_bias may be NULL;
- *                          slope = 1 means no activation.  Returns 0 on success. */
+ *                          slope = 1 means no activation.  Returns 0 on success.
+ *   convolution_cuda_batched_dev   `nimg` images [nimg][ich][h][w] -> [nimg][ch][Ho*Wo] with shared weights (BASELINE config 4 is 64 images
+ *                          of 128 x 56 x 56, 256 filters 3 x 3: the GEMM M=256, N=64*3136, K=1152 in the reference's orientation).
+ * Fused path (implicit GEMM), stride 1: the column matrix is never built -- one image-sized pass makes a channels-last copy of
+ * the input (stream-ordered scratch, k*k times smaller than the column matrix) from which K1 gathers its B tiles with 4-D TMA
+ * boxes (zero padding = TMA out-of-bounds fill); d_workspace is not touched and may be NULL.  Automatic rule: taken when the padded work (output width and channels rounded up to 32) stays within 30 %
+ * of the real work, ch >= 64 and there are >= 256 output pixels; sgemm_cuda_set_conv_fusion(0 never | 1 whenever possible |
+ * -1 rule); sgemm_cuda_last_conv_fused() reports what the last convolution did. */
+int  convolution_cuda_batched_dev(int mode, void *stream, const float *d_inputs, int nimg, int ich, int w, int h, const float *d_weights,
+                                  int k, int pad, int stride, float *d_outputs, int ch, const float *d_bias, float slope, float *d_workspace);
+void sgemm_cuda_set_conv_fusion(int mode);
+int  sgemm_cuda_last_conv_fused(void);
 void im2col_cuda(const float *im, int channels, int height, int width, int k, int pad, int stride, float *col);
 int  im2col_cuda_dev(const float *d_im, int channels, int height, int width, int k, int pad, int stride, float *d_col, void *stream);
 void convolution_cuda(const float *inputs, int ich, int w, int h, const float *weights, int k, int pad, int stride,

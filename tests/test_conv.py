@@ -99,3 +99,74 @@ def test_gpu_im2col_and_convolution(u, geom):
     neg = plain < -1e-3
     if neg.any():
         assert np.allclose(out2.reshape(ch, -1)[neg], 0.1 * plain[neg], rtol=1e-3, atol=1e-5)
+
+
+FUSED_GEOMS = [  # ich, h, w, k, pad, ch, nimg  (stride 1)
+    (32, 8, 32, 3, 1, 128, 1),      # one 32-pixel chunk per output row, exact channel block
+    (64, 14, 64, 3, 1, 256, 1),     # 2-CTA-sized M
+    (128, 56, 56, 3, 1, 256, 1),    # one image of BASELINE config 4 (output width 56 -> padded to 64)
+    (40, 20, 36, 3, 0, 130, 2),     # ragged channels (40 -> 64), ragged filters, wo = 34, no padding, two images
+    (24, 12, 28, 5, 2, 96, 3),      # 5x5, ich < 32
+    (3, 16, 32, 3, 1, 64, 2),       # first-layer-like: 3 channels
+    (96, 9, 12, 1, 0, 64, 4),       # 1x1 convolution, wo = 12
+    (16, 10, 8, 2, 1, 70, 1),       # even kernel, wo = 9
+    (64, 15, 30, 3, 1, 96, 2),      # width not a multiple of 4, odd height
+    (30, 11, 57, 3, 1, 128, 1),     # odd width, channels not a multiple of 4 (30 -> cs 32)
+    (6, 7, 9, 3, 2, 64, 2),         # pad > (k-1)/2: output larger than the input
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", FUSED_GEOMS)
+def test_gpu_implicit_gemm_convolution(u, geom):
+    """The fused (implicit-GEMM, 4-D TMA gather) convolution against the oracle's im2col + GEMM, image by image, with and
+    without bias + LeakyReLU, and against the unfused CUDA path on the same inputs."""
+    ich, h, w, k, pad, ch, nimg = geom
+    ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    x = O.fill_uniform(nimg * ich * h * w, 301, -0.5, 0.5)
+    wgt = O.fill_uniform(ch * ich * k * k, 302, -0.5, 0.5)
+    bias = O.fill_uniform(ch, 303, -0.5, 0.5)
+    dx, dw, db = u.DeviceBuffer(x.size).upload(x), u.DeviceBuffer(wgt.size).upload(wgt), u.DeviceBuffer(ch).upload(bias)
+    dout, dws = u.DeviceBuffer(nimg * ch * ho * wo), u.DeviceBuffer(ich * k * k * ho * wo)
+    try:
+        for d_bias, b_host, slope in ((None, None, 1.0), (db, bias, 0.1)):
+            want = np.concatenate([oracle_conv(x[i * ich * h * w:(i + 1) * ich * h * w], ich, w, h, wgt, k, pad, 1, ch, b_host, slope)[0]
+                                   for i in range(nimg)])
+            u.set_conv_fusion(1)
+            dout.upload(np.full(dout.n, np.nan, np.float32))
+            u.convolution_cuda_batched_dev("auto", None, dx, nimg, ich, w, h, dw, k, pad, 1, dout, ch, d_bias, slope, None)   # no workspace needed
+            u.sync()
+            assert u.last_conv_fused() and u.last_kernel() == "3xtf32"
+            got = dout.download()
+            e = np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64))
+            assert np.isfinite(got).all() and e <= 1e-5, (geom, slope, e)
+            u.set_conv_fusion(0)
+            u.convolution_cuda_batched_dev("auto", None, dx, nimg, ich, w, h, dw, k, pad, 1, dout, ch, d_bias, slope, dws)
+            u.sync()
+            assert not u.last_conv_fused()
+            ref = dout.download()
+            assert np.linalg.norm(got.astype(np.float64) - ref) / np.linalg.norm(ref.astype(np.float64)) <= 1e-5
+    finally:
+        u.set_conv_fusion(-1)
+
+
+@pytest.mark.gpu
+def test_conv_fusion_rule_and_fallbacks(u):
+    """auto rule: fused only for stride 1 and bounded padding waste; everything else takes im2col + GEMM."""
+    def run(ich, h, w, k, pad, stride, ch):
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        x, wgt, _ = make_conv(ich, h, w, k, ch, seed=90)
+        dx, dw = u.DeviceBuffer(x.size).upload(x), u.DeviceBuffer(wgt.size).upload(wgt)
+        dout, dws = u.DeviceBuffer(ch * ho * wo), u.DeviceBuffer(ich * k * k * ho * wo)
+        u.convolution_cuda_dev("auto", None, dx, ich, w, h, dw, k, pad, stride, dout, ch, None, 1.0, dws)
+        u.sync()
+        want, _ = oracle_conv(x, ich, w, h, wgt, k, pad, stride, ch, None, 1.0)
+        got = dout.download()
+        assert np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64)) <= 1e-5
+        return u.last_conv_fused()
+    assert run(128, 56, 56, 3, 1, 1, 256)          # config 4's layer: 64/56 * 128/128 = 1.14 -> fused
+    assert not run(64, 57, 41, 3, 1, 2, 96)        # stride 2
+    assert run(64, 30, 30, 3, 1, 1, 96)            # any width: 32/30 padded columns
+    assert not run(128, 13, 12, 3, 1, 1, 256)      # wo = 12 -> 32: too much padded work
+    assert not run(3, 32, 32, 3, 1, 1, 64)         # 3 channels -> 32
+    assert not run(64, 28, 28, 3, 1, 1, 32)        # few filters

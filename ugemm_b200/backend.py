@@ -137,6 +137,12 @@ def lib():
     L.dgemm_cuda_dev.restype = C.c_int
     L.dgemm_cuda_time_dev.argtypes = [C.c_int, C.c_int] + dsig14 + [C.POINTER(C.c_float)] * 2
     L.dgemm_cuda_time_dev.restype = C.c_int
+    L.convolution_cuda_batched_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                               C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]
+    L.convolution_cuda_batched_dev.restype = C.c_int
+    L.sgemm_cuda_set_conv_fusion.argtypes = [C.c_int]
+    L.sgemm_cuda_set_conv_fusion.restype = None
+    L.sgemm_cuda_last_conv_fused.restype = C.c_int
     L.ugemm_cuda_probe_tf32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.ugemm_cuda_probe_tf32.restype = C.c_int
     _lib = L
@@ -152,7 +158,7 @@ EXPORTED_SYMBOLS = [
     "ugemm_cuda_memcpy_async", "ugemm_cuda_ipc_export", "ugemm_cuda_ipc_import", "ugemm_cuda_ipc_close",
     "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
     "ugemm_cuda_probe_tf32", "im2col_cuda", "im2col_cuda_dev", "convolution_cuda", "convolution_cuda_LReLU",
-    "convolution_cuda_dev", "saxpy_cuda", "saxpy_cuda_dev", "sgemv_cuda", "sgemv_cuda_dev",
+    "convolution_cuda_dev", "convolution_cuda_batched_dev", "sgemm_cuda_set_conv_fusion", "sgemm_cuda_last_conv_fused", "saxpy_cuda", "saxpy_cuda_dev", "sgemv_cuda", "sgemv_cuda_dev",
     "dgemm_cuda", "dgemm_cuda_dev", "dgemm_cuda_time_dev",
 ]
 
@@ -396,6 +402,24 @@ def convolution_cuda_dev(mode, stream, d_inputs, ich, w, h, d_weights, k, pad, s
     if rc:
         check()
         raise UgemmCudaError("convolution_cuda_dev failed")
+
+
+def convolution_cuda_batched_dev(mode, stream, d_inputs, nimg, ich, w, h, d_weights, k, pad, stride, d_outputs, ch, d_bias, slope, d_workspace):
+    """nimg images [nimg][ich][h][w] -> [nimg][ch][Ho*Wo]; one fused implicit-GEMM launch when the layout allows."""
+    rc = lib().convolution_cuda_batched_dev(_MODES[mode], C.c_void_p(stream or 0), _ptr(d_inputs), nimg, ich, w, h, _ptr(d_weights), k, pad, stride,
+                                            _ptr(d_outputs), ch, _ptr(d_bias), slope, _ptr(d_workspace))
+    if rc:
+        check()
+        raise UgemmCudaError("convolution_cuda_batched_dev failed")
+
+
+def set_conv_fusion(mode=-1):
+    """-1 by rule, 0 never (im2col + GEMM), 1 implicit GEMM whenever the hard constraints allow."""
+    lib().sgemm_cuda_set_conv_fusion(int(mode))
+
+
+def last_conv_fused():
+    return bool(lib().sgemm_cuda_last_conv_fused())
 
 
 # ---- level 1 / level 2 (argument order of saxpy_cpu ugemm.h:75 and sgemv_cpu ugemm.h:124) ----------------

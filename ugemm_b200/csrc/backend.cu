@@ -34,6 +34,8 @@ struct State {
 	size_t arena_bytes = 0;
 	K1Tuning tuning = {4, 0, 0, 1};   // promote every 4 k-blocks (128 k), truncation split, CTA pairing by problem size, A collector
 	int last_kernel = 0;
+	int last_conv_fused = 0;         // last convolution ran as an implicit GEMM (no column matrix)
+	int conv_fusion = -1;            // -1 by rule, 0 never, 1 whenever the hard constraints allow
 	int last_repacked = 0;           // last auto launch copied an operand to an aligned leading dimension first
 	int sm_limit = 0;                // 0 = all SMs; otherwise K1's persistent grid is capped (leaves SMs to NCCL)
 	unsigned long long launches = 0;
@@ -541,6 +543,8 @@ const char *sgemm_cuda_last_error(void) { return g_has_err ? g_err : nullptr; }
 void sgemm_cuda_clear_error(void) { g_has_err = false; g_err[0] = 0; }
 int sgemm_cuda_last_kernel(void) { return g.last_kernel; }
 int sgemm_cuda_last_repacked(void) { return g.last_repacked; }
+int sgemm_cuda_last_conv_fused(void) { return g.last_conv_fused; }
+void sgemm_cuda_set_conv_fusion(int mode) { g.conv_fusion = mode < 0 ? -1 : (mode > 0 ? 1 : 0); }
 unsigned long long sgemm_cuda_launch_count(void) { return g.launches; }
 
 int ugemm_cuda_device_info(int *sm_count, int *sm_clock_khz, size_t *hbm_bytes, char *name, int name_len)
@@ -697,9 +701,75 @@ int im2col_cuda_dev(const float *d_im, int channels, int height, int width, int 
 	return 0;
 }
 
+// Implicit-GEMM convolution on K1 (stride 1).  Under the automatic rule an efficiency bound applies: the GEMM is computed on
+// a column index padded to a multiple of 32 per output row and on a channel count padded to a multiple of 32, and the padded
+// work must stay within 30 % of the real work -- otherwise materialising the column matrix and running the dense GEMM is cheaper.
+static bool conv_fusable(int mode, int nimg, int ich, int w, int h, int k, int pad, int stride, int ch)
+{
+	if (mode == UGEMM_MODE_SIMT || g.conv_fusion == 0 || stride != 1) return false;
+	const long long ho = h + 2 * pad - k + 1, wo = w + 2 * pad - k + 1;
+	if (ho < 1 || wo < 1 || ho * ((wo + 31) / 32 * 32) > 0x7fffffffLL) return false;
+	if (g.conv_fusion > 0) return true;
+	const long long wp = (wo + 31) / 32 * 32, ichp = (ich + 31) / 32 * 32;
+	return ch >= 64 && ho * wo * nimg >= 256 && (double)(wp * ichp) <= 1.3 * (double)(wo * ich);
+}
+
+static int conv_fused_dev(cudaStream_t stream, const float *d_inputs, int nimg, int ich, int w, int h, const float *d_weights, int k, int pad,
+                          float *d_outputs, int ch, const float *d_bias, float slope)
+{
+	ConvProblem c;
+	c.nimg = nimg; c.ich = ich; c.h = h; c.w = w; c.ichp = (ich + 31) / 32 * 32; c.cs = (ich + 3) / 4 * 4;
+	c.k = k; c.pad = pad; c.ho = h + 2 * pad - k + 1; c.wo = w + 2 * pad - k + 1; c.ch = ch;
+	c.out = d_outputs; c.bias = d_bias; c.slope = slope;
+	// scratch: channels-last copy of the images (image-sized, k*k times smaller than the column matrix) + repacked weights
+	const size_t hwc_bytes = align_up_sz((size_t)nimg * h * w * c.cs * sizeof(float), 256), w_bytes = (size_t)ch * k * k * c.ichp * sizeof(float);
+	char *ws = nullptr;
+	CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&ws), hwc_bytes + w_bytes, stream), "convolution scratch");
+	float *hwc = reinterpret_cast<float *>(ws), *wr = reinterpret_cast<float *>(ws + hwc_bytes);
+	c.in_hwc = hwc; c.wgt_kkc = wr;
+	cudaError_t e = launch_chw_to_hwc(d_inputs, nimg, ich, h, w, c.cs, hwc, stream);
+	if (e == cudaSuccess) e = launch_conv_weight_repack(d_weights, ch, ich, k, c.ichp, wr, stream);
+	if (e == cudaSuccess) e = launch_k1_conv(c, g.tuning, stream, (g.sm_limit > 0 && g.sm_limit < g.sm_count) ? g.sm_limit : g.sm_count);
+	cudaFreeAsync(ws, stream);
+	CU_TRY(e, "K1 implicit-GEMM convolution launch");
+	g.last_kernel = UGEMM_MODE_3XTF32; g.last_conv_fused = 1; g.last_repacked = 0;
+	g.launches += 3;
+	return 0;
+}
+
+static int conv_check(int nimg, int ich, int w, int h, int k, int pad, int stride, int ch)
+{
+	if (nimg < 0 || ich <= 0 || ch <= 0 || k <= 0 || stride <= 0 || pad < 0 || h <= 0 || w <= 0 || h + 2 * pad < k || w + 2 * pad < k) {
+		set_error("convolution: bad geometry (images=%d C=%d H=%d W=%d k=%d pad=%d stride=%d ch=%d)", nimg, ich, h, w, k, pad, stride, ch);
+		return 1;
+	}
+	return 0;
+}
+
+int convolution_cuda_batched_dev(int mode, void *stream, const float *d_inputs, int nimg, int ich, int w, int h, const float *d_weights, int k,
+                                 int pad, int stride, float *d_outputs, int ch, const float *d_bias, float slope, float *d_workspace)
+{
+	if (ensure_init()) return 1;
+	if (conv_check(nimg, ich, w, h, k, pad, stride, ch)) return 1;
+	if (nimg == 0) return 0;
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+	if (conv_fusable(mode, nimg, ich, w, h, k, pad, stride, ch))
+		return conv_fused_dev(st, d_inputs, nimg, ich, w, h, d_weights, k, pad, d_outputs, ch, d_bias, slope);
+	const long long ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+	for (int i = 0; i < nimg; i++)      // the column matrix of one image at a time through the same workspace (stream order keeps it safe)
+		if (convolution_cuda_dev(mode, st, d_inputs + (size_t)i * ich * h * w, ich, w, h, d_weights, k, pad, stride,
+		                         d_outputs + (size_t)i * ch * ho * wo, ch, d_bias, slope, d_workspace)) return 1;
+	return 0;
+}
+
 int convolution_cuda_dev(int mode, void *stream, const float *d_inputs, int ich, int w, int h, const float *d_weights, int k,
                          int pad, int stride, float *d_outputs, int ch, const float *d_bias, float slope, float *d_workspace)
 {
+	if (ensure_init()) return 1;
+	if (conv_check(1, ich, w, h, k, pad, stride, ch)) return 1;
+	g.last_conv_fused = 0;
+	if (conv_fusable(mode, 1, ich, w, h, k, pad, stride, ch))
+		return conv_fused_dev(stream ? static_cast<cudaStream_t>(stream) : g.stream, d_inputs, 1, ich, w, h, d_weights, k, pad, d_outputs, ch, d_bias, slope);
 	if (im2col_cuda_dev(d_inputs, ich, h, w, k, pad, stride, d_workspace, stream)) return 1;
 	const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
 	const long long npix = (long long)ho * wo, kk = (long long)ich * k * k;

@@ -34,6 +34,17 @@ struct DProblem {
 	double *C; long long ldc;
 };
 
+// Implicit-GEMM convolution on K1 (stride 1): out[img][co][io*wo + jo] = sum_{c,ki,kj} w[co][c][ki][kj] * in[img][c][io+ki-pad][jo+kj-pad]
+// (+ bias[co], LeakyReLU).  The column matrix of the reference's im2col (sgemm_ocl1.h:81-119) is never built: the B operand
+// tiles are gathered by 4-D TMA boxes from in_hwc, a channels-last copy [img][y][x][cs] of the image (one image-sized pass,
+// launch_chw_to_hwc; cs = ich rounded up to 4).  wgt_kkc = weights repacked to [co][ki*k+kj][ichp], ichp = ich rounded up to 32.
+struct ConvProblem {
+	const float *in_hwc; int cs; int nimg, ich, h, w;
+	const float *wgt_kkc; int ichp;
+	int k, pad, ho, wo, ch;
+	float *out; const float *bias; float slope;
+};
+
 // flags: bit0 = share one shared-memory read of A_big between big*small and big*big (A collector);
 // bits 1-4 are ABLATION switches for bottleneck analysis only (results are wrong with them):
 // 2 transform skips its stores, 4 transform skips loads and stores, 8 only big*big is issued, 16 epilogue skips stores,
@@ -45,6 +56,10 @@ cudaError_t launch_k2_simt(const Problem &p, cudaStream_t stream, int sm_count);
 // K1: 3xTF32 tcgen05 kernel (k1_tcgen05.cu).  *why (optional) receives a static string on ineligibility.
 bool        k1_eligible(const Problem &p, const char **why);
 cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count);
+// implicit-GEMM convolution (k1_tcgen05.cu): weight repack [co][c][ki][kj] -> [co][ki*k+kj][ichp] (zero padded), and the launch
+cudaError_t launch_conv_weight_repack(const float *w, int ch, int ich, int k, int ichp, float *dst, cudaStream_t stream);
+cudaError_t launch_chw_to_hwc(const float *in, int nimg, int ich, int h, int w, int cs, float *out, cudaStream_t stream);
+cudaError_t launch_k1_conv(const ConvProblem &c, const K1Tuning &t, cudaStream_t stream, int sm_count);
 // C <- beta*C over the M x N region (alpha==0 or K==0 path)
 cudaError_t launch_scale_c(const Problem &p, cudaStream_t stream);
 // im2col of a planar C x H x W image into the (C*k*k) x (Ho*Wo) column matrix (k2_simt.cu)

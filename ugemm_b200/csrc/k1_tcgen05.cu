@@ -60,6 +60,9 @@ struct K1Params {
 	int a_kmajor, b_kmajor;
 	int tiles_m, tiles_n, num_tiles;
 	int num_k_blocks, kc_blocks, split, vecC, flags;
+	// implicit-GEMM convolution (CONV instantiation): padded output width (multiple of 32), output width / height,
+	// kernel size, padding, 32-channel blocks per kernel position, pixels per output plane
+	int cv_wp, cv_wo, cv_ho, cv_k, cv_pad, cv_cblocks, cv_npix;
 	unsigned *diag;
 	int *sched;        // [0] next tile index (atomic), [1] clusters finished; self-resetting
 	long long *prof;   // flags & 32: per-role cycle counters of the first 4 CTAs (16 slots each), debug only
@@ -136,7 +139,15 @@ __device__ __forceinline__ float tf32_rna(float x)
 
 // PROF compiles the per-role cycle counters in (UGEMM_K1_FLAGS bit 5); the production instantiation has none, which
 // keeps ~10 registers out of the epilogue's hot drain loop.
-template <int CG, bool PROF>
+// CONV: the B operand is an image gathered by 4-D TMA boxes (implicit im2col, stride 1).  GEMM column n' = io * cv_wp + jo
+// with cv_wp = output width rounded up to 32, so every 32-column chunk of a tile is one output-row segment (io, jo0..jo0+31)
+// and, for k-block kb = (ki*k + kj) * cv_cblocks + cb, one box {32 channels, 32 x, 1 y, 1 image} of the channels-last copy of
+// the image at c = 32*cb, x = jo0 + kj - pad, y = io + ki - pad: 32 rows of 128 contiguous bytes, i.e. a quarter of a dense
+// K-major B tile.  (TMA needs the box start 16-byte aligned in the contiguous dimension, so the one-pixel shifts of a
+// convolution cannot be taken along x of the planar image [measured: illegal instruction]; channels-last puts them on outer
+// dimensions.)  Padding pixels and channels beyond ich are TMA out-of-bounds zero fill; columns jo >= wo are computed and
+// never stored.
+template <int CG, bool PROF, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const K1Params P)
 {
@@ -211,6 +222,15 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				decode_tile(tile - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
 				const int a_row0 = tm * UMMA_M + (int)cta_rank * ROWS;
 				const int b_row0 = tn * BN + (int)cta_rank * ROWS;
+				int cio[ROWS / 32], cjo[ROWS / 32];     // CONV: output row / first output column of each 32-column chunk
+				if (CONV) {
+#pragma unroll
+					for (int j = 0; j < ROWS / 32; j++) {
+						const int n0 = b_row0 + 32 * j;
+						cio[j] = n0 / P.cv_wp;
+						cjo[j] = n0 - cio[j] * P.cv_wp;
+					}
+				}
 				for (int kb = 0; kb < nkb && !(P.flags & 64); kb++, it++) {
 					const int s = it % STAGES;
 					const uint32_t ph = (it / STAGES) & 1;
@@ -220,6 +240,15 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					mbar_arrive_expect_tx(full_bar(s), RAW_BYTES);
 					const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + OPER_BYTES;
 					const int k0 = kb * BK;
+					if (CONV) {
+						const int kpos = kb / P.cv_cblocks, c0 = (kb - kpos * P.cv_cblocks) * 32;
+						const int ki = kpos / P.cv_k, kj = kpos - ki * P.cv_k;
+						tma_load_3d_hint(sA, &tmA, full_bar(s), k0, a_row0, 0, hintA);       // repacked weights, K-major, shared by all images
+#pragma unroll
+						for (int j = 0; j < ROWS / 32; j++)
+							tma_load_4d_hint(sB + j * 4096, &tmB, full_bar(s), c0, cjo[j] + kj - P.cv_pad, cio[j] + ki - P.cv_pad, inst, hintB);
+						continue;
+					}
 					if (P.a_kmajor) tma_load_3d_hint(sA, &tmA, full_bar(s), k0, a_row0, inst, hintA);
 					else
 						for (int j = 0; j < ROWS / 32; j++) tma_load_3d_hint(sA + j * 4096, &tmA, full_bar(s), a_row0 + 32 * j, k0, inst, hintA);
@@ -382,11 +411,11 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			decode_tile(tile - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
 			float acc[NG][32];
 			const long long row = (long long)tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane;
-			float *crow = P.C + (long long)inst * P.strideC + row * P.ldc;
+			float *crow = P.C + (long long)inst * P.strideC + row * (CONV ? (long long)P.cv_npix : P.ldc);
 			// beta != 0: the old C is folded in UP FRONT -- the running sums start at (beta/alpha)*C, loaded while the
 			// tile's first MMAs run and the epilogue warps would idle anyway -- so the tile end is store-only and
 			// never stalls the accumulator hand-over on a global-load round trip.
-			if (preload_c && row < P.M) {
+			if (!CONV && preload_c && row < P.M) {
 #pragma unroll
 				for (int g = 0; g < NG; g++) {
 					const long long col0 = (long long)tn * BN + h * (BN / 2) + g * 32;
@@ -438,6 +467,31 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				const bool post = P.bias != nullptr || slope != 1.f;   // bias[row] + LeakyReLU (convolution callers)
 				const float bm = P.bias ? __ldg(P.bias + row) : 0.f;
 				auto act = [&](float x) { x += bm; return x > 0.f ? x : x * slope; };
+				if (CONV) {
+					// each 32-column group is one output-row segment: map it back from the padded column index
+#pragma unroll
+					for (int g = 0; g < NG; g++) {
+						const int n0 = tn * BN + h * (BN / 2) + g * 32;
+						const int io = n0 / P.cv_wp, jo0 = n0 - io * P.cv_wp;
+						const int valid = io < P.cv_ho ? P.cv_wo - jo0 : 0;      // columns of this group that exist (may be <= 0 or >= 32)
+						const int off = io * P.cv_wo + jo0;
+						float *dst = crow + off;
+						const bool vec = P.vecC && (off & 3) == 0;
+#pragma unroll
+						for (int i = 0; i < 32; i += 4) {
+							float4 o;
+							o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1]; o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
+							if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
+							if (vec && i + 3 < valid) *reinterpret_cast<float4 *>(dst + i) = o;
+							else {
+								if (i + 0 < valid) dst[i + 0] = o.x;
+								if (i + 1 < valid) dst[i + 1] = o.y;
+								if (i + 2 < valid) dst[i + 2] = o.z;
+								if (i + 3 < valid) dst[i + 3] = o.w;
+							}
+						}
+					}
+				} else
 #pragma unroll
 				for (int g = 0; g < NG; g++) {
 					const long long col0 = (long long)tn * BN + h * (BN / 2) + g * 32;
@@ -586,29 +640,15 @@ unsigned *diag_dev()
 	return g_diag_dev;
 }
 
-template <int CG>
-cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
+// common tail of the GEMM and convolution launches: scheduler counters, attributes, cluster launch
+template <int CG, bool CONV>
+cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
-	CUtensorMap tmA, tmB;
-	if (!make_operand_map(&tmA, p.A, p.M, p.K, p.lda, p.a_kmajor, p.batch, p.strideA)) return cudaErrorInvalidValue;
-	if (!make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.b_kmajor, p.batch, p.strideB)) return cudaErrorInvalidValue;
-	K1Params P;
-	P.M = p.M; P.N = p.N; P.K = p.K; P.alpha = p.alpha; P.beta = p.beta; P.C = p.C; P.ldc = p.ldc;
-	P.bias = p.bias; P.slope = p.slope;
-	P.a_kmajor = p.a_kmajor; P.b_kmajor = p.b_kmajor;
-	const int tile_m = 128 * CG, tile_n = 128 * CG;
-	P.tiles_m = (p.M + tile_m - 1) / tile_m;
-	P.tiles_n = (p.N + tile_n - 1) / tile_n;
-	P.tiles_per_batch = P.tiles_m * P.tiles_n;
-	P.strideC = p.strideC;
-	const long long nt = (long long)P.tiles_m * P.tiles_n * (p.batch > 0 ? p.batch : 1);
 	if (nt > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
 	P.num_tiles = (int)nt;
-	P.num_k_blocks = (p.K + BK - 1) / BK;
 	P.kc_blocks = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
 	P.split = t.split;
 	P.flags = t.flags;
-	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0) ? 1 : 0;
 	P.diag = diag_dev();
 	// dynamic-scheduler counters: a small pool so launches on different streams do not share a slot
 	static int *sched_pool = nullptr;
@@ -621,19 +661,22 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	P.sched = sched_pool + 2 * (sched_next++ % SCHED_POOL);
 	P.prof = nullptr;
 	static long long *prof_dev = nullptr;
-	if (t.flags & 32) {
+	const bool prof = !CONV && (t.flags & 32);
+	if (prof) {
 		if (!prof_dev) cudaMalloc(&prof_dev, 64 * sizeof(long long));
 		cudaMemsetAsync(prof_dev, 0, 64 * sizeof(long long), stream);
 		P.prof = prof_dev;
 	}
 
-	static bool attr_set[3] = {false, false, false};
-	if (!attr_set[CG]) {
-		cudaError_t e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+	static bool attr_set = false;      // one flag per <CG, CONV> instantiation of this function
+	if (!attr_set) {
+		cudaError_t e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, false, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 		if (e != cudaSuccess) return e;
-		e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-		if (e != cudaSuccess) return e;
-		attr_set[CG] = true;
+		if (!CONV) {
+			e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+			if (e != cudaSuccess) return e;
+		}
+		attr_set = true;
 	}
 	const int max_clusters = sm_count / CG;
 	const int clusters = (int)(nt < max_clusters ? nt : max_clusters);
@@ -646,9 +689,9 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr; cfg.numAttrs = 1;
-	cudaError_t le = (t.flags & 32) ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true>, tmA, tmB, P)
-	                                : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false>, tmA, tmB, P);
-	if (le == cudaSuccess && (t.flags & 32)) {   // debug: per-role cycle breakdown of CTAs 0..3 on stderr
+	cudaError_t le = prof ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true, false>, tmA, tmB, P)
+	                      : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false, CONV>, tmA, tmB, P);
+	if (le == cudaSuccess && prof) {   // debug: per-role cycle breakdown of CTAs 0..3 on stderr
 		long long h[64];
 		if (cudaStreamSynchronize(stream) == cudaSuccess && cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
 			for (int c = 0; c < 4; c++)
@@ -657,6 +700,99 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 				        h[16 * c + 8], h[16 * c + 9], h[16 * c + 10], h[16 * c + 11], h[16 * c + 12]);
 	}
 	return le;
+}
+
+template <int CG>
+cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
+{
+	CUtensorMap tmA, tmB;
+	if (!make_operand_map(&tmA, p.A, p.M, p.K, p.lda, p.a_kmajor, p.batch, p.strideA)) return cudaErrorInvalidValue;
+	if (!make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.b_kmajor, p.batch, p.strideB)) return cudaErrorInvalidValue;
+	K1Params P = {};
+	P.M = p.M; P.N = p.N; P.K = p.K; P.alpha = p.alpha; P.beta = p.beta; P.C = p.C; P.ldc = p.ldc;
+	P.bias = p.bias; P.slope = p.slope;
+	P.a_kmajor = p.a_kmajor; P.b_kmajor = p.b_kmajor;
+	const int tile_m = 128 * CG, tile_n = 128 * CG;
+	P.tiles_m = (p.M + tile_m - 1) / tile_m;
+	P.tiles_n = (p.N + tile_n - 1) / tile_n;
+	P.tiles_per_batch = P.tiles_m * P.tiles_n;
+	P.strideC = p.strideC;
+	const long long nt = (long long)P.tiles_m * P.tiles_n * (p.batch > 0 ? p.batch : 1);
+	P.num_k_blocks = (p.K + BK - 1) / BK;
+	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0) ? 1 : 0;
+	return launch_kernel<CG, false>(tmA, tmB, P, nt, t, stream, sm_count);
+}
+
+// channels-last image as a 4-D tensor {c: cs, x: w, y: h, image: nimg}, box {32 c, 32 x, 1 y, 1}: one box = 32 output pixels of one
+// output row x 32 input channels at one kernel position = 32 rows of 128 B, laid out like 32 rows of a dense K-major tile
+bool make_image_map(CUtensorMap *map, const ConvProblem &c)
+{
+	EncodeTiledFn fn = encode_fn();
+	if (!fn) return false;
+	cuuint64_t gdim[4] = {(cuuint64_t)c.cs, (cuuint64_t)c.w, (cuuint64_t)c.h, (cuuint64_t)c.nimg};
+	cuuint64_t gstride[3] = {(cuuint64_t)c.cs * 4, (cuuint64_t)c.cs * c.w * 4, (cuuint64_t)c.cs * c.w * c.h * 4};
+	cuuint32_t box[4] = {32, 32, 1, 1}, estr[4] = {1, 1, 1, 1};
+	return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(c.in_hwc), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int CG>
+cudaError_t launch_conv_cg(const ConvProblem &c, const K1Tuning &t, cudaStream_t stream, int sm_count)
+{
+	const int kk = c.k * c.k * c.ichp, npix = c.ho * c.wo, wp = (c.wo + 31) / 32 * 32;
+	CUtensorMap tmA, tmB;
+	if (!make_operand_map(&tmA, c.wgt_kkc, c.ch, kk, kk, true, 1, 0)) return cudaErrorInvalidValue;
+	if (!make_image_map(&tmB, c)) return cudaErrorInvalidValue;
+	K1Params P = {};
+	P.M = c.ch; P.N = c.ho * wp; P.K = kk; P.alpha = 1.f; P.beta = 0.f; P.C = c.out; P.ldc = npix;
+	P.bias = c.bias; P.slope = c.slope;
+	P.a_kmajor = 1; P.b_kmajor = 1;
+	const int tile_m = 128 * CG, tile_n = 128 * CG;
+	P.tiles_m = (P.M + tile_m - 1) / tile_m;
+	P.tiles_n = (P.N + tile_n - 1) / tile_n;
+	P.tiles_per_batch = P.tiles_m * P.tiles_n;
+	P.strideC = (long long)c.ch * npix;
+	const long long nt = (long long)P.tiles_m * P.tiles_n * c.nimg;
+	P.num_k_blocks = kk / BK;
+	P.vecC = ((reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && npix % 4 == 0) ? 1 : 0;
+	P.cv_wp = wp; P.cv_wo = c.wo; P.cv_ho = c.ho; P.cv_k = c.k; P.cv_pad = c.pad; P.cv_cblocks = c.ichp / 32; P.cv_npix = npix;
+	return launch_kernel<CG, true>(tmA, tmB, P, nt, t, stream, sm_count);
+}
+
+// planar [img][c][y][x] -> channels-last [img][y][x][cs] (cs = ich rounded up to 4, the pad channels zero): one image-sized HBM pass
+// through a 32 x 32 shared-memory tile so that both sides are coalesced.  blockIdx.z = img * h + y.
+__global__ void __launch_bounds__(256)
+chw_to_hwc_kernel(const float *__restrict__ in, int ich, int h, int w, int cs, float *__restrict__ out)
+{
+	__shared__ float tile[32][33];
+	const int img = blockIdx.z / h, y = blockIdx.z - img * h;
+	const int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	const float *src = in + ((long long)img * ich * h + y) * w;         // + c * h * w + x
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int c = c0 + r, x = x0 + tx;
+		tile[r][tx] = (c < ich && x < w) ? __ldg(src + (long long)c * h * w + x) : 0.f;
+	}
+	__syncthreads();
+	float *dst = out + (((long long)img * h + y) * w) * cs;             // + x * cs + c
+#pragma unroll
+	for (int r = ty; r < 32; r += 8) {
+		const int x = x0 + r, c = c0 + tx;
+		if (x < w && c < cs) dst[(long long)x * cs + c] = tile[tx][r];
+	}
+}
+
+// dst[co][(ki*k + kj)*ichp + c] = w[co][c][ki][kj], zero for ich <= c < ichp
+__global__ void conv_weight_repack_kernel(const float *__restrict__ w, int ch, int ich, int k, int ichp, float *__restrict__ dst)
+{
+	const long long total = (long long)ch * k * k * ichp;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		const int c = (int)(i % ichp);
+		const long long r = i / ichp;
+		const int kpos = (int)(r % (k * k)), co = (int)(r / (k * k));
+		dst[i] = c < ich ? __ldg(w + ((long long)co * ich + c) * k * k + kpos) : 0.f;
+	}
 }
 
 } // namespace
@@ -687,6 +823,47 @@ cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t s
 	}
 	if (cg == 1) return launch_cg<1>(p, t, stream, sm_count);
 	return launch_cg<2>(p, t, stream, sm_count);
+}
+
+cudaError_t launch_conv_weight_repack(const float *w, int ch, int ich, int k, int ichp, float *dst, cudaStream_t stream)
+{
+	const long long total = (long long)ch * k * k * ichp;
+	if (total <= 0) return cudaSuccess;
+	long long blocks = (total + 255) / 256;
+	if (blocks > 148LL * 16) blocks = 148LL * 16;
+	conv_weight_repack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w, ch, ich, k, ichp, dst);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_chw_to_hwc(const float *in, int nimg, int ich, int h, int w, int cs, float *out, cudaStream_t stream)
+{
+	if (nimg <= 0 || (long long)nimg * h > 65535LL * 1) {
+		// grid.z is limited to 65535: walk the images in groups
+		for (int i0 = 0; i0 < nimg;) {
+			int n = 65535 / h; if (n < 1) return cudaErrorInvalidConfiguration;
+			if (n > nimg - i0) n = nimg - i0;
+			dim3 grid((unsigned)((w + 31) / 32), (unsigned)((cs + 31) / 32), (unsigned)(n * h));
+			chw_to_hwc_kernel<<<grid, 256, 0, stream>>>(in + (size_t)i0 * ich * h * w, ich, h, w, cs, out + (size_t)i0 * h * w * cs);
+			i0 += n;
+		}
+		return cudaGetLastError();
+	}
+	dim3 grid((unsigned)((w + 31) / 32), (unsigned)((cs + 31) / 32), (unsigned)(nimg * h));
+	chw_to_hwc_kernel<<<grid, 256, 0, stream>>>(in, ich, h, w, cs, out);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_k1_conv(const ConvProblem &c, const K1Tuning &t, cudaStream_t stream, int sm_count)
+{
+	if (!encode_fn()) return cudaErrorNotSupported;
+	int cg = t.cta_group;
+	if (cg != 1 && cg != 2) {
+		const long long wp = (c.wo + 31) / 32 * 32;
+		const long long pair_tiles = (long long)((c.ch + 255) / 256) * ((c.ho * wp + 255) / 256) * c.nimg;
+		cg = (pair_tiles * 8 >= (long long)(sm_count / 2) * 6) ? 2 : 1;
+	}
+	if (cg == 1) return launch_conv_cg<1>(c, t, stream, sm_count);
+	return launch_conv_cg<2>(c, t, stream, sm_count);
 }
 
 cudaError_t launch_probe_tf32(const float *dA, const float *dB, float *dD, int ksteps, cudaStream_t stream)

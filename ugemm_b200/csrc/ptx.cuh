@@ -80,6 +80,13 @@ __device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const void *tmap,
 	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint) : "memory");
 }
 
+// 4-D variant (implicit-GEMM convolution: x, y, channel, image)
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t hint)
+{
+	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint) : "memory");
+}
+
 // ---- tensor memory --------------------------------------------------------------------------------------
 template <int CG> __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
 {
