@@ -161,7 +161,7 @@ int  ugemm_fill_uniform_dev_2d(float *dx, size_t rows, size_t cols, size_t ld, u
  *                          slope = 1 means no activation.  Returns 0 on success.
  *   convolution_cuda_batched_dev   `nimg` images [nimg][ich][h][w] -> [nimg][ch][Ho*Wo] with shared weights (BASELINE config 4 is 64 images
  *                          of 128 x 56 x 56, 256 filters 3 x 3: the GEMM M=256, N=64*3136, K=1152 in the reference's orientation).
- * Fused path (implicit GEMM), stride 1: the column matrix is never built -- one image-sized pass makes a channels-last copy of
+ * Fused path (implicit GEMM), strides 1..8: the column matrix is never built -- one image-sized pass makes a channels-last copy of
  * the input (stream-ordered scratch, k*k times smaller than the column matrix) from which K1 gathers its B tiles with 4-D TMA
  * boxes (zero padding = TMA out-of-bounds fill); d_workspace is not touched and may be NULL.  Automatic rule: taken when the padded work (output width and channels rounded up to 32) stays within 30 %
  * of the real work, ch >= 64 and there are >= 256 output pixels; sgemm_cuda_set_conv_fusion(0 never | 1 whenever possible |

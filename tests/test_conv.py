@@ -101,18 +101,22 @@ def test_gpu_im2col_and_convolution(u, geom):
         assert np.allclose(out2.reshape(ch, -1)[neg], 0.1 * plain[neg], rtol=1e-3, atol=1e-5)
 
 
-FUSED_GEOMS = [  # ich, h, w, k, pad, ch, nimg  (stride 1)
-    (32, 8, 32, 3, 1, 128, 1),      # one 32-pixel chunk per output row, exact channel block
-    (64, 14, 64, 3, 1, 256, 1),     # 2-CTA-sized M
-    (128, 56, 56, 3, 1, 256, 1),    # one image of BASELINE config 4 (output width 56 -> padded to 64)
-    (40, 20, 36, 3, 0, 130, 2),     # ragged channels (40 -> 64), ragged filters, wo = 34, no padding, two images
-    (24, 12, 28, 5, 2, 96, 3),      # 5x5, ich < 32
-    (3, 16, 32, 3, 1, 64, 2),       # first-layer-like: 3 channels
-    (96, 9, 12, 1, 0, 64, 4),       # 1x1 convolution, wo = 12
-    (16, 10, 8, 2, 1, 70, 1),       # even kernel, wo = 9
-    (64, 15, 30, 3, 1, 96, 2),      # width not a multiple of 4, odd height
-    (30, 11, 57, 3, 1, 128, 1),     # odd width, channels not a multiple of 4 (30 -> cs 32)
-    (6, 7, 9, 3, 2, 64, 2),         # pad > (k-1)/2: output larger than the input
+FUSED_GEOMS = [  # ich, h, w, k, pad, ch, nimg, stride
+    (32, 8, 32, 3, 1, 128, 1, 1),      # one 32-pixel chunk per output row, exact channel block
+    (64, 14, 64, 3, 1, 256, 1, 1),     # 2-CTA-sized M
+    (128, 56, 56, 3, 1, 256, 1, 1),    # one image of BASELINE config 4 (output width 56 -> padded to 64)
+    (40, 20, 36, 3, 0, 130, 2, 1),     # ragged channels (40 -> 64), ragged filters, wo = 34, no padding, two images
+    (24, 12, 28, 5, 2, 96, 3, 1),      # 5x5, ich < 32
+    (3, 16, 32, 3, 1, 64, 2, 1),       # first-layer-like: 3 channels
+    (96, 9, 12, 1, 0, 64, 4, 1),       # 1x1 convolution, wo = 12
+    (16, 10, 8, 2, 1, 70, 1, 1),       # even kernel, wo = 9
+    (64, 15, 30, 3, 1, 96, 2, 1),      # width not a multiple of 4, odd height
+    (30, 11, 57, 3, 1, 128, 1, 1),     # odd width, channels not a multiple of 4 (30 -> cs 32)
+    (6, 7, 9, 3, 2, 64, 2, 1),         # pad > (k-1)/2: output larger than the input
+    (64, 57, 41, 3, 1, 96, 2, 2),      # stride 2 (TMA element stride), odd sizes
+    (32, 64, 64, 3, 1, 128, 1, 2),     # stride 2, wo = 32
+    (48, 33, 70, 5, 2, 64, 1, 3),      # stride 3, 5x5
+    (32, 16, 16, 2, 0, 64, 2, 2),      # 2x2 stride 2 (pooling-like), wo = 8
 ]
 
 
@@ -121,8 +125,8 @@ FUSED_GEOMS = [  # ich, h, w, k, pad, ch, nimg  (stride 1)
 def test_gpu_implicit_gemm_convolution(u, geom):
     """The fused (implicit-GEMM, 4-D TMA gather) convolution against the oracle's im2col + GEMM, image by image, with and
     without bias + LeakyReLU, and against the unfused CUDA path on the same inputs."""
-    ich, h, w, k, pad, ch, nimg = geom
-    ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    ich, h, w, k, pad, ch, nimg, stride = geom
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
     x = O.fill_uniform(nimg * ich * h * w, 301, -0.5, 0.5)
     wgt = O.fill_uniform(ch * ich * k * k, 302, -0.5, 0.5)
     bias = O.fill_uniform(ch, 303, -0.5, 0.5)
@@ -130,18 +134,18 @@ def test_gpu_implicit_gemm_convolution(u, geom):
     dout, dws = u.DeviceBuffer(nimg * ch * ho * wo), u.DeviceBuffer(ich * k * k * ho * wo)
     try:
         for d_bias, b_host, slope in ((None, None, 1.0), (db, bias, 0.1)):
-            want = np.concatenate([oracle_conv(x[i * ich * h * w:(i + 1) * ich * h * w], ich, w, h, wgt, k, pad, 1, ch, b_host, slope)[0]
+            want = np.concatenate([oracle_conv(x[i * ich * h * w:(i + 1) * ich * h * w], ich, w, h, wgt, k, pad, stride, ch, b_host, slope)[0]
                                    for i in range(nimg)])
             u.set_conv_fusion(1)
             dout.upload(np.full(dout.n, np.nan, np.float32))
-            u.convolution_cuda_batched_dev("auto", None, dx, nimg, ich, w, h, dw, k, pad, 1, dout, ch, d_bias, slope, None)   # no workspace needed
+            u.convolution_cuda_batched_dev("auto", None, dx, nimg, ich, w, h, dw, k, pad, stride, dout, ch, d_bias, slope, None)   # no workspace needed
             u.sync()
             assert u.last_conv_fused() and u.last_kernel() == "3xtf32"
             got = dout.download()
             e = np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64))
             assert np.isfinite(got).all() and e <= 1e-5, (geom, slope, e)
             u.set_conv_fusion(0)
-            u.convolution_cuda_batched_dev("auto", None, dx, nimg, ich, w, h, dw, k, pad, 1, dout, ch, d_bias, slope, dws)
+            u.convolution_cuda_batched_dev("auto", None, dx, nimg, ich, w, h, dw, k, pad, stride, dout, ch, d_bias, slope, dws)
             u.sync()
             assert not u.last_conv_fused()
             ref = dout.download()
@@ -152,7 +156,7 @@ def test_gpu_implicit_gemm_convolution(u, geom):
 
 @pytest.mark.gpu
 def test_conv_fusion_rule_and_fallbacks(u):
-    """auto rule: fused only for stride 1 and bounded padding waste; everything else takes im2col + GEMM."""
+    """auto rule: fused only for bounded padding waste (and strides <= 8); everything else takes im2col + GEMM."""
     def run(ich, h, w, k, pad, stride, ch):
         ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
         x, wgt, _ = make_conv(ich, h, w, k, ch, seed=90)
@@ -165,7 +169,9 @@ def test_conv_fusion_rule_and_fallbacks(u):
         assert np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64)) <= 1e-5
         return u.last_conv_fused()
     assert run(128, 56, 56, 3, 1, 1, 256)          # config 4's layer: 64/56 * 128/128 = 1.14 -> fused
-    assert not run(64, 57, 41, 3, 1, 2, 96)        # stride 2
+    assert not run(64, 57, 41, 3, 1, 2, 96)        # stride 2: wo = 21 -> 32, too much padded work
+    assert run(64, 57, 61, 3, 1, 2, 96)            # stride 2: wo = 31 -> 32
+    assert not run(64, 100, 100, 3, 1, 9, 96)      # stride 9: beyond the TMA box limit
     assert run(64, 30, 30, 3, 1, 1, 96)            # any width: 32/30 padded columns
     assert not run(128, 13, 12, 3, 1, 1, 256)      # wo = 12 -> 32: too much padded work
     assert not run(3, 32, 32, 3, 1, 1, 64)         # 3 channels -> 32

@@ -47,4 +47,30 @@ for trans, M, N, pad in (("N", 300, 200, 0), ("N", 512, 4100, 0), ("N", 130, 77,
     e = np.linalg.norm(yv - want) / np.linalg.norm(want)
     print("sgemv", trans, M, N, pad, "relerr %.2e" % e, flush=True)
     assert e < 1e-5
+# implicit-GEMM convolution (4-D TMA gather), stride 1 and 2, two images; DGEMM
+for (ich, h, w, k, pad, ch, nimg, stride) in ((40, 20, 36, 3, 1, 130, 2, 1), (32, 17, 33, 3, 1, 64, 1, 2)):
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    xi = rng.uniform(-.5, .5, nimg * ich * h * w).astype(np.float32); wg = rng.uniform(-.5, .5, ch * ich * k * k).astype(np.float32)
+    dx, dw, do = u.DeviceBuffer(xi.size).upload(xi), u.DeviceBuffer(wg.size).upload(wg), u.DeviceBuffer(nimg * ch * ho * wo)
+    u.set_conv_fusion(1)
+    u.convolution_cuda_batched_dev("auto", None, dx, nimg, ich, w, h, dw, k, pad, stride, do, ch, None, 1.0, None)
+    u.sync()
+    got = do.download().reshape(nimg, ch, ho, wo).astype(np.float64)
+    xp = np.zeros((nimg, ich, h + 2 * pad, w + 2 * pad)); xp[:, :, pad:pad + h, pad:pad + w] = xi.reshape(nimg, ich, h, w)
+    W = wg.reshape(ch, ich, k, k).astype(np.float64); ref = np.zeros((nimg, ch, ho, wo))
+    for ki in range(k):
+        for kj in range(k):
+            ref += np.einsum("oc,nchw->nohw", W[:, :, ki, kj], xp[:, :, ki:ki + stride * ho:stride, kj:kj + stride * wo:stride])
+    e = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    print("conv fused", u.last_conv_fused(), (ich, h, w, k, pad, ch, nimg, stride), "relerr %.2e" % e, flush=True)
+    assert u.last_conv_fused() and e < 1e-5
+u.set_conv_fusion(-1)
+for ta, tb, M, N, K in (("N", "N", 130, 70, 33), ("T", "T", 128, 64, 16), ("N", "T", 17, 9, 5)):
+    ar, ac = (M, K) if ta == "N" else (K, M); br, bc = (K, N) if tb == "N" else (N, K)
+    Ad = rng.uniform(0, 1, (ar, ac)); Bd = rng.uniform(0, 1, (br, bc)); Cd = rng.uniform(0, 1, (M, N)); C0 = Cd.copy()
+    u.dgemm_cuda("R", ta, tb, M, N, K, 1.5, Ad.ravel(), ac, Bd.ravel(), bc, 0.5, Cd.ravel(), N)
+    ref = 1.5 * ((Ad if ta == "N" else Ad.T) @ (Bd if tb == "N" else Bd.T)) + 0.5 * C0
+    e = np.linalg.norm(Cd - ref) / np.linalg.norm(ref)
+    print("dgemm", ta, tb, M, N, K, "relerr %.2e" % e, flush=True)
+    assert e < 2e-14
 u.sgemm_cuda_finish()

@@ -701,13 +701,13 @@ int im2col_cuda_dev(const float *d_im, int channels, int height, int width, int 
 	return 0;
 }
 
-// Implicit-GEMM convolution on K1 (stride 1).  Under the automatic rule an efficiency bound applies: the GEMM is computed on
+// Implicit-GEMM convolution on K1 (strides 1..8).  Under the automatic rule an efficiency bound applies: the GEMM is computed on
 // a column index padded to a multiple of 32 per output row and on a channel count padded to a multiple of 32, and the padded
 // work must stay within 30 % of the real work -- otherwise materialising the column matrix and running the dense GEMM is cheaper.
 static bool conv_fusable(int mode, int nimg, int ich, int w, int h, int k, int pad, int stride, int ch)
 {
-	if (mode == UGEMM_MODE_SIMT || g.conv_fusion == 0 || stride != 1) return false;
-	const long long ho = h + 2 * pad - k + 1, wo = w + 2 * pad - k + 1;
+	if (mode == UGEMM_MODE_SIMT || g.conv_fusion == 0 || stride < 1 || stride > 8) return false;   // TMA box <= 256 elements: 32*stride
+	const long long ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
 	if (ho < 1 || wo < 1 || ho * ((wo + 31) / 32 * 32) > 0x7fffffffLL) return false;
 	if (g.conv_fusion > 0) return true;
 	const long long wp = (wo + 31) / 32 * 32, ichp = (ich + 31) / 32 * 32;
@@ -715,11 +715,11 @@ static bool conv_fusable(int mode, int nimg, int ich, int w, int h, int k, int p
 }
 
 static int conv_fused_dev(cudaStream_t stream, const float *d_inputs, int nimg, int ich, int w, int h, const float *d_weights, int k, int pad,
-                          float *d_outputs, int ch, const float *d_bias, float slope)
+                          int stride, float *d_outputs, int ch, const float *d_bias, float slope)
 {
 	ConvProblem c;
 	c.nimg = nimg; c.ich = ich; c.h = h; c.w = w; c.ichp = (ich + 31) / 32 * 32; c.cs = (ich + 3) / 4 * 4;
-	c.k = k; c.pad = pad; c.ho = h + 2 * pad - k + 1; c.wo = w + 2 * pad - k + 1; c.ch = ch;
+	c.k = k; c.pad = pad; c.stride = stride; c.ho = (h + 2 * pad - k) / stride + 1; c.wo = (w + 2 * pad - k) / stride + 1; c.ch = ch;
 	c.out = d_outputs; c.bias = d_bias; c.slope = slope;
 	// scratch: channels-last copy of the images (image-sized, k*k times smaller than the column matrix) + repacked weights
 	const size_t hwc_bytes = align_up_sz((size_t)nimg * h * w * c.cs * sizeof(float), 256), w_bytes = (size_t)ch * k * k * c.ichp * sizeof(float);
@@ -754,7 +754,7 @@ int convolution_cuda_batched_dev(int mode, void *stream, const float *d_inputs, 
 	if (nimg == 0) return 0;
 	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
 	if (conv_fusable(mode, nimg, ich, w, h, k, pad, stride, ch))
-		return conv_fused_dev(st, d_inputs, nimg, ich, w, h, d_weights, k, pad, d_outputs, ch, d_bias, slope);
+		return conv_fused_dev(st, d_inputs, nimg, ich, w, h, d_weights, k, pad, stride, d_outputs, ch, d_bias, slope);
 	const long long ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
 	for (int i = 0; i < nimg; i++)      // the column matrix of one image at a time through the same workspace (stream order keeps it safe)
 		if (convolution_cuda_dev(mode, st, d_inputs + (size_t)i * ich * h * w, ich, w, h, d_weights, k, pad, stride,
@@ -769,7 +769,7 @@ int convolution_cuda_dev(int mode, void *stream, const float *d_inputs, int ich,
 	if (conv_check(1, ich, w, h, k, pad, stride, ch)) return 1;
 	g.last_conv_fused = 0;
 	if (conv_fusable(mode, 1, ich, w, h, k, pad, stride, ch))
-		return conv_fused_dev(stream ? static_cast<cudaStream_t>(stream) : g.stream, d_inputs, 1, ich, w, h, d_weights, k, pad, d_outputs, ch, d_bias, slope);
+		return conv_fused_dev(stream ? static_cast<cudaStream_t>(stream) : g.stream, d_inputs, 1, ich, w, h, d_weights, k, pad, stride, d_outputs, ch, d_bias, slope);
 	if (im2col_cuda_dev(d_inputs, ich, h, w, k, pad, stride, d_workspace, stream)) return 1;
 	const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
 	const long long npix = (long long)ho * wo, kk = (long long)ich * k * k;

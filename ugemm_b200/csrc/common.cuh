@@ -34,14 +34,14 @@ struct DProblem {
 	double *C; long long ldc;
 };
 
-// Implicit-GEMM convolution on K1 (stride 1): out[img][co][io*wo + jo] = sum_{c,ki,kj} w[co][c][ki][kj] * in[img][c][io+ki-pad][jo+kj-pad]
+// Implicit-GEMM convolution on K1: out[img][co][io*wo + jo] = sum_{c,ki,kj} w[co][c][ki][kj] * in[img][c][io*stride+ki-pad][jo*stride+kj-pad]
 // (+ bias[co], LeakyReLU).  The column matrix of the reference's im2col (sgemm_ocl1.h:81-119) is never built: the B operand
 // tiles are gathered by 4-D TMA boxes from in_hwc, a channels-last copy [img][y][x][cs] of the image (one image-sized pass,
 // launch_chw_to_hwc; cs = ich rounded up to 4).  wgt_kkc = weights repacked to [co][ki*k+kj][ichp], ichp = ich rounded up to 32.
 struct ConvProblem {
 	const float *in_hwc; int cs; int nimg, ich, h, w;
 	const float *wgt_kkc; int ichp;
-	int k, pad, ho, wo, ch;
+	int k, pad, stride, ho, wo, ch;
 	float *out; const float *bias; float slope;
 };
 

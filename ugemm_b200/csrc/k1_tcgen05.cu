@@ -62,7 +62,7 @@ struct K1Params {
 	int num_k_blocks, kc_blocks, split, vecC, flags;
 	// implicit-GEMM convolution (CONV instantiation): padded output width (multiple of 32), output width / height,
 	// kernel size, padding, 32-channel blocks per kernel position, pixels per output plane
-	int cv_wp, cv_wo, cv_ho, cv_k, cv_pad, cv_cblocks, cv_npix;
+	int cv_wp, cv_wo, cv_ho, cv_k, cv_pad, cv_cblocks, cv_npix, cv_stride;
 	unsigned *diag;
 	int *sched;        // [0] next tile index (atomic), [1] clusters finished; self-resetting
 	long long *prof;   // flags & 32: per-role cycle counters of the first 4 CTAs (16 slots each), debug only
@@ -139,10 +139,10 @@ __device__ __forceinline__ float tf32_rna(float x)
 
 // PROF compiles the per-role cycle counters in (UGEMM_K1_FLAGS bit 5); the production instantiation has none, which
 // keeps ~10 registers out of the epilogue's hot drain loop.
-// CONV: the B operand is an image gathered by 4-D TMA boxes (implicit im2col, stride 1).  GEMM column n' = io * cv_wp + jo
+// CONV: the B operand is an image gathered by 4-D TMA boxes (implicit im2col; strides 1..8 through the TMA element stride).  GEMM column n' = io * cv_wp + jo
 // with cv_wp = output width rounded up to 32, so every 32-column chunk of a tile is one output-row segment (io, jo0..jo0+31)
 // and, for k-block kb = (ki*k + kj) * cv_cblocks + cb, one box {32 channels, 32 x, 1 y, 1 image} of the channels-last copy of
-// the image at c = 32*cb, x = jo0 + kj - pad, y = io + ki - pad: 32 rows of 128 contiguous bytes, i.e. a quarter of a dense
+// the image at c = 32*cb, x = jo0*stride + kj - pad, y = io*stride + ki - pad: 32 rows of 128 contiguous bytes, i.e. a quarter of a dense
 // K-major B tile.  (TMA needs the box start 16-byte aligned in the contiguous dimension, so the one-pixel shifts of a
 // convolution cannot be taken along x of the planar image [measured: illegal instruction]; channels-last puts them on outer
 // dimensions.)  Padding pixels and channels beyond ich are TMA out-of-bounds zero fill; columns jo >= wo are computed and
@@ -246,7 +246,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 						tma_load_3d_hint(sA, &tmA, full_bar(s), k0, a_row0, 0, hintA);       // repacked weights, K-major, shared by all images
 #pragma unroll
 						for (int j = 0; j < ROWS / 32; j++)
-							tma_load_4d_hint(sB + j * 4096, &tmB, full_bar(s), c0, cjo[j] + kj - P.cv_pad, cio[j] + ki - P.cv_pad, inst, hintB);
+							tma_load_4d_hint(sB + j * 4096, &tmB, full_bar(s), c0, cjo[j] * P.cv_stride + kj - P.cv_pad, cio[j] * P.cv_stride + ki - P.cv_pad, inst, hintB);
 						continue;
 					}
 					if (P.a_kmajor) tma_load_3d_hint(sA, &tmA, full_bar(s), k0, a_row0, inst, hintA);
@@ -731,7 +731,9 @@ bool make_image_map(CUtensorMap *map, const ConvProblem &c)
 	if (!fn) return false;
 	cuuint64_t gdim[4] = {(cuuint64_t)c.cs, (cuuint64_t)c.w, (cuuint64_t)c.h, (cuuint64_t)c.nimg};
 	cuuint64_t gstride[3] = {(cuuint64_t)c.cs * 4, (cuuint64_t)c.cs * c.w * 4, (cuuint64_t)c.cs * c.w * c.h * 4};
-	cuuint32_t box[4] = {32, 32, 1, 1}, estr[4] = {1, 1, 1, 1};
+	// a strided convolution reads every stride-th pixel of the row: the box spans 32*stride pixels and the TMA element stride
+	// picks 32 of them
+	cuuint32_t box[4] = {32, (cuuint32_t)(32 * c.stride), 1, 1}, estr[4] = {1, (cuuint32_t)c.stride, 1, 1};
 	return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(c.in_hwc), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
 	          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -755,7 +757,7 @@ cudaError_t launch_conv_cg(const ConvProblem &c, const K1Tuning &t, cudaStream_t
 	const long long nt = (long long)P.tiles_m * P.tiles_n * c.nimg;
 	P.num_k_blocks = kk / BK;
 	P.vecC = ((reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && npix % 4 == 0) ? 1 : 0;
-	P.cv_wp = wp; P.cv_wo = c.wo; P.cv_ho = c.ho; P.cv_k = c.k; P.cv_pad = c.pad; P.cv_cblocks = c.ichp / 32; P.cv_npix = npix;
+	P.cv_wp = wp; P.cv_wo = c.wo; P.cv_ho = c.ho; P.cv_k = c.k; P.cv_pad = c.pad; P.cv_cblocks = c.ichp / 32; P.cv_npix = npix; P.cv_stride = c.stride;
 	return launch_kernel<CG, true>(tmA, tmB, P, nt, t, stream, sm_count);
 }
 
