@@ -362,3 +362,17 @@ def test_k2_narrow_n_tiles(u, ta, tb):
     e = sampled_rows_check(u, "auto", 200704, 16, 1152, [(0, 32), (200672, 32)], 0.0, 1.0)
     assert u.last_kernel() == "simt"
     assert e <= TOL
+
+
+@pytest.mark.parametrize("ta", ["N", "T"])
+def test_k2_big_tiles_interior_and_edges(u, ta):
+    """K2 with >= one 128x128 tile per SM: whole-tile shapes (the unguarded interior loop), K tails that end inside a 128-bit
+    quad / inside a k-tile, and ragged M / N whose last tile row and column take the guarded loop."""
+    for i, (M, N, K) in enumerate(((1664, 1536, 64), (1664, 1536, 100), (1664, 1536, 19), (1701, 1541, 70), (2048, 1280, 1), (1536, 1700, 33))):
+        for alpha, beta in ((1.0, 0.0), (1.5, 0.5)):
+            (ar, ac), (br, bc), _ = O.stored_shapes("R", ta, "N", M, N, K)
+            pad = ((-ac) % 4, (-bc) % 4, 3)      # lda, ldb multiples of 4 (16-byte copies), ldc odd
+            check_case(u, "simt", "R", ta, "N", M, N, K, alpha, beta, pad, seed=80 + i)
+            assert u.last_kernel() == "simt"
+    # column-major maps onto the same kernel with the operands swapped
+    check_case(u, "simt", "C", "N", ta, 1536, 1664, 50, 1.5, 0.5, (0, 0, 0), seed=90)
