@@ -42,6 +42,10 @@ __device__ __forceinline__ float4 load_quad(const float *__restrict__ line, long
 // Operand staging.  The shared tile is always [BK][BMN + PAD] (k-major rows of the M or N extent).
 //   KCONTIG: global lines run along k (row-major 'N' A, or 'T' B): line index = m (or n), column = k
 //   else   : global lines run along m/n (row-major 'T' A, or 'N' B): line index = k, column = m (or n)
+// line-index swizzle of k-contiguous operands in shared memory (identity for the others, and for 16-wide tiles whose
+// half-tiles are narrower than the swizzle): lines of rows k >= 8 are stored XOR 8
+__device__ __forceinline__ constexpr int swz(int k) { return (k & 8) ? 8 : 0; }
+
 template <int BMN, bool KCONTIG>
 struct Stager {
 	static constexpr int NQ = BMN * K2_BK / 4;                              // quads in the tile
@@ -92,7 +96,9 @@ struct Stager {
 			int f = tid + i * K2_THREADS;
 			if (NQ % K2_THREADS != 0 && f >= NQ) continue;
 			if (KCONTIG) {
-				int line = f / (K2_BK / 4), kq = (f % (K2_BK / 4)) * 4;
+				// transposing store: a warp writes 8 lines x 4 k-quads; rows kq and kq+8 are 8*(BMN+PAD) floats = a multiple
+				// of 32 banks apart, so the k >= 8 half of the tile keeps its lines XOR 8 (see swz()) and the store is conflict-free
+				int line = (f / (K2_BK / 4)) ^ (BMN >= 32 ? swz(f % (K2_BK / 4) * 4) : 0), kq = (f % (K2_BK / 4)) * 4;
 				s[kq + 0][line] = r[i].x; s[kq + 1][line] = r[i].y;
 				s[kq + 2][line] = r[i].z; s[kq + 3][line] = r[i].w;
 			} else {
@@ -152,19 +158,22 @@ k2_simt_kernel(Problem p, const int tiles_m, const int tiles_n, const bool vecA,
 	sb.store(Bs[0], tid);
 	__syncthreads();
 
+	// first line of this thread's fragment in each half of the tile, plain and XOR 8 (k >= 8 rows of k-contiguous operands,
+	// see swz()); the XOR flips bit 3 only, so the HM / HN consecutive lines of a fragment stay consecutive and aligned
+	const int a_off[2] = {ty * HM, (ty * HM) ^ 8}, b_off[2] = {tx * HN, (tx * HN) ^ 8};
 	auto multiply = [&](int cur) {
 #pragma unroll
 		for (int kk = 0; kk < K2_BK; kk++) {
 			float a[TM], b[TN];
 #pragma unroll
 			for (int i = 0; i < HM; i++) {
-				a[i] = As[cur][kk][ty * HM + i];
-				a[HM + i] = As[cur][kk][BM / 2 + ty * HM + i];
+				a[i] = As[cur][kk][a_off[AK && BM >= 32 && swz(kk) ? 1 : 0] + i];
+				a[HM + i] = As[cur][kk][BM / 2 + a_off[AK && BM >= 32 && swz(kk) ? 1 : 0] + i];
 			}
 #pragma unroll
 			for (int j = 0; j < HN; j++) {
-				b[j] = Bs[cur][kk][tx * HN + j];
-				b[HN + j] = Bs[cur][kk][BN / 2 + tx * HN + j];
+				b[j] = Bs[cur][kk][b_off[BKM && BN >= 32 && swz(kk) ? 1 : 0] + j];
+				b[HN + j] = Bs[cur][kk][BN / 2 + b_off[BKM && BN >= 32 && swz(kk) ? 1 : 0] + j];
 			}
 			if constexpr (PACKED) {
 				// Blackwell packed fp32: one FFMA2 updates two adjacent columns (a 64-bit register pair), which halves the
