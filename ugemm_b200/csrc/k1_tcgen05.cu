@@ -839,19 +839,13 @@ cudaError_t launch_conv_weight_repack(const float *w, int ch, int ich, int k, in
 
 cudaError_t launch_chw_to_hwc(const float *in, int nimg, int ich, int h, int w, int cs, float *out, cudaStream_t stream)
 {
-	if (nimg <= 0 || (long long)nimg * h > 65535LL * 1) {
-		// grid.z is limited to 65535: walk the images in groups
-		for (int i0 = 0; i0 < nimg;) {
-			int n = 65535 / h; if (n < 1) return cudaErrorInvalidConfiguration;
-			if (n > nimg - i0) n = nimg - i0;
-			dim3 grid((unsigned)((w + 31) / 32), (unsigned)((cs + 31) / 32), (unsigned)(n * h));
-			chw_to_hwc_kernel<<<grid, 256, 0, stream>>>(in + (size_t)i0 * ich * h * w, ich, h, w, cs, out + (size_t)i0 * h * w * cs);
-			i0 += n;
-		}
-		return cudaGetLastError();
+	if (h < 1 || h > 65535) return cudaErrorInvalidConfiguration;
+	const int per_launch = 65535 / h;                 // grid.z = images x rows is limited to 65535
+	for (int i0 = 0; i0 < nimg; i0 += per_launch) {
+		const int n = nimg - i0 < per_launch ? nimg - i0 : per_launch;
+		dim3 grid((unsigned)((w + 31) / 32), (unsigned)((cs + 31) / 32), (unsigned)(n * h));
+		chw_to_hwc_kernel<<<grid, 256, 0, stream>>>(in + (size_t)i0 * ich * h * w, ich, h, w, cs, out + (size_t)i0 * h * w * cs);
 	}
-	dim3 grid((unsigned)((w + 31) / 32), (unsigned)((cs + 31) / 32), (unsigned)(nimg * h));
-	chw_to_hwc_kernel<<<grid, 256, 0, stream>>>(in, ich, h, w, cs, out);
 	return cudaGetLastError();
 }
 
