@@ -376,3 +376,28 @@ def test_k2_big_tiles_interior_and_edges(u, ta):
             assert u.last_kernel() == "simt"
     # column-major maps onto the same kernel with the operands swapped
     check_case(u, "simt", "C", "N", ta, 1536, 1664, 50, 1.5, 0.5, (0, 0, 0), seed=90)
+
+
+def test_k1_stream_k_tail_is_deterministic_and_exact_enough(u):
+    """Shapes whose tile count is not a multiple of the SM-pair count finish their last round by stream-K (tail tiles cut along K,
+    partial sums added in a fixed order by a second kernel): results must be reproducible bit for bit and meet the gate, for
+    ragged edges, beta != 0 and the bias + LeakyReLU epilogue's plain path."""
+    for i, (M, N, K, ta, tb) in enumerate(((1100, 900, 1024, "N", "N"), (4095, 3001, 2047, "N", "T"), (2048, 2048, 2048, "N", "N"),
+                                           (768, 640, 4096, "T", "N"), (4096, 4096, 512, "N", "N"))):
+        (ar, ac), (br, bc), _ = O.stored_shapes("R", ta, tb, M, N, K)
+        pad = ((-ac) % 4, (-bc) % 4, (-N) % 4 + 4)
+        A, lda, B, ldb, Cm, ldc = O.make_problem("R", ta, tb, M, N, K, pad=pad, seed=60 + i, sentinel=-77.0)
+        g1 = gpu14(u, "3xtf32", "R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+        g2 = gpu14(u, "3xtf32", "R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+        assert np.array_equal(g1, g2), "stream-K result changed between two identical calls"
+        assert np.array_equal(g1.reshape(M, ldc)[:, N:], Cm.reshape(M, ldc)[:, N:]), "ld padding of C was written"
+        if M * N * K <= 2.2e9:
+            want = oracle14("R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+            assert O.relerr("R", M, N, want, g1, ldc) <= TOL
+        else:   # sampled rows against fp64
+            opA = A.reshape(ar, lda)[:, :ac] if ta == "N" else A.reshape(ar, lda)[:, :ac].T
+            opB = B.reshape(br, ldb)[:, :bc] if tb == "N" else B.reshape(br, ldb)[:, :bc].T
+            rows = np.linspace(0, M - 1, 24).astype(int)
+            ref = 1.5 * (opA[rows].astype(np.float64) @ opB.astype(np.float64)) + 0.5 * Cm.reshape(M, ldc)[rows, :N]
+            got = g1.reshape(M, ldc)[rows, :N]
+            assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= TOL

@@ -60,6 +60,11 @@ struct K1Params {
 	int a_kmajor, b_kmajor;
 	int tiles_m, tiles_n, num_tiles;
 	int num_k_blocks, kc_blocks, split, vecC, flags;
+	// stream-K tail (sk_q > 0): work items [0, sk_full) are whole tiles; the remaining sk_rem tiles are cut into chunk ranges of
+	// sk_q promotion chunks (kc_blocks k-blocks each, sk_nch per tile), two items per range (a range may straddle one tile
+	// boundary); their raw partial sums go to sk_ws[slot][tile_m x tile_n] and k1_tail_fixup_kernel adds them up in range order
+	int sk_full, sk_rem, sk_nch, sk_q;
+	float *sk_ws;
 	// implicit-GEMM convolution (CONV instantiation): padded output width (multiple of 32), output width / height,
 	// kernel size, padding, 32-channel blocks per kernel position, pixels per output plane
 	int cv_wp, cv_wo, cv_ho, cv_k, cv_pad, cv_cblocks, cv_npix, cv_stride;
@@ -103,6 +108,29 @@ __device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, 
 	const int r = tile - group * per_group;
 	tm = first_m + r % gsize;
 	tn = r / gsize;
+}
+
+// A work item of the dynamic scheduler -> one or two segments (tile, k-block range, workspace slot).  Items below sk_full
+// are whole tiles (one segment, slot < 0: normal epilogue into C).  Item sk_full + r is chunk range r = [r*q, (r+1)*q) of the
+// tail's sk_rem * sk_nch chunks; a range may straddle one tile boundary, so it has up to two segments: h = 0 inside the
+// tile it starts in, h = 1 (possibly absent) in the next tile.  One pair processes a whole range, so the tail is balanced:
+// every pair claims one range of q chunks.  Every role of the kernel decodes items with this one function, so they all agree.
+struct Item { int tile, kb0, kb1, slot; };      // kb1 <= kb0: no such segment
+__device__ __host__ __forceinline__ Item decode_item(int item, int h, int sk_full, int sk_rem, int sk_nch, int sk_q, int kc, int nkb)
+{
+	Item it;
+	if (sk_q <= 0 || item < sk_full) { it.tile = item; it.kb0 = 0; it.kb1 = h == 0 ? nkb : 0; it.slot = -1; return it; }
+	const int r = item - sk_full;
+	const int total = sk_rem * sk_nch;
+	const int lo = r * sk_q, hi = lo + sk_q < total ? lo + sk_q : total;
+	const int ta = lo / sk_nch, bnd = (ta + 1) * sk_nch;
+	const int tr = ta + h, c0 = h ? bnd : lo, c1 = h ? hi : (hi < bnd ? hi : bnd);
+	it.tile = sk_full + tr;
+	it.slot = 2 * r + h;
+	it.kb0 = (c0 - tr * sk_nch) * kc;
+	it.kb1 = (c1 - tr * sk_nch) * kc < nkb ? (c1 - tr * sk_nch) * kc : nkb;
+	if (c1 <= c0) { it.kb0 = it.kb1 = 0; }
+	return it;
 }
 
 // ---- dynamic tile scheduler ------------------------------------------------------------------------------------
@@ -216,7 +244,11 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			const uint64_t hintA = (P.flags & 128) ? L2_EVICT_LAST : (P.flags & 1024) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
 			const uint64_t hintB = (P.flags & 512) ? L2_EVICT_LAST : (P.flags & 256) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
 			int nt = 0;
-			for (int tile; (tile = next_tile<CG>(bar_base, nt, false, 0, P.diag)) >= 0;) {
+			for (int item; (item = next_tile<CG>(bar_base, nt, false, 0, P.diag)) >= 0;) {
+				for (int sg = 0; sg < 2; sg++) {
+				const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
+				if (wi.kb1 <= wi.kb0) continue;
+				const int tile = wi.tile;
 				int tm, tn;
 				const int inst = tile / P.tiles_per_batch;
 				decode_tile(tile - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
@@ -231,7 +263,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 						cjo[j] = n0 - cio[j] * P.cv_wp;
 					}
 				}
-				for (int kb = 0; kb < nkb && !(P.flags & 64); kb++, it++) {
+				for (int kb = wi.kb0; kb < wi.kb1 && !(P.flags & 64); kb++, it++) {
 					const int s = it % STAGES;
 					const uint32_t ph = (it / STAGES) & 1;
 					const long long tw = tick<PROF>();
@@ -256,6 +288,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					else
 						for (int j = 0; j < ROWS / 32; j++) tma_load_3d_hint(sB + j * 4096, &tmB, full_bar(s), b_row0 + 32 * j, k0, inst, hintB);
 				}
+				}
 			}
 			if (prof) { prof[0] = w_empty; prof[1] = tick<PROF>() - t_begin; }
 		} else if (warp == 1 && lane == 0 && cta_rank == 0) {
@@ -270,8 +303,11 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			int it = 0, ci = 0;
 			long long w_xf = 0, w_te = 0; const long long t_begin = tick<PROF>();
 			int nt = 0;
-			while (next_tile<CG>(bar_base, nt, false, 0, P.diag) >= 0) {
-				for (int kb0 = 0; kb0 < nkb; kb0 += kc, ci++) {
+			for (int item; (item = next_tile<CG>(bar_base, nt, false, 0, P.diag)) >= 0;) {
+				for (int sg = 0; sg < 2; sg++) {
+				const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
+				if (wi.kb1 <= wi.kb0) continue;
+				for (int kb0 = wi.kb0; kb0 < wi.kb1; kb0 += kc, ci++) {
 					const int acc = ci & 1;
 					const uint32_t aph = (ci >> 1) & 1;
 					long long tw = tick<PROF>();
@@ -280,7 +316,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					w_te += tick<PROF>() - tw;
 					tc_fence_after();
 					const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-					const int kb1 = min(kb0 + kc, nkb);
+					const int kb1 = min(kb0 + kc, wi.kb1);
 					for (int kb = kb0; kb < kb1; kb++, it++) {
 						const int s = it % STAGES;
 						const uint32_t ph = (it / STAGES) & 1;
@@ -314,6 +350,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					}
 					mma_commit<CG>(tfull_bar(acc));     // accumulator chunk complete
 				}
+				}
 			}
 			if (prof) { prof[2] = w_xf; prof[3] = w_te; prof[4] = tick<PROF>() - t_begin; }
 		} else if (warp == 2 && lane == 0 && cta_rank == 0) {
@@ -324,8 +361,18 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				const uint32_t ph = (n / SCHED_SLOTS) & 1;
 				const uint32_t full = bar_base + 8u * (14 + slot), empty = bar_base + 8u * (14 + SCHED_SLOTS + slot);
 				if (CG == 2) mbar_wait_cluster(empty, ph ^ 1u, P.diag, 7); else mbar_wait(empty, ph ^ 1u, P.diag, 7);
-				int tile = atomicAdd(P.sched, 1);
-				if (tile >= P.num_tiles) tile = -1;
+				int tile;
+				if (P.sk_q > 0) {
+					// stream-K launches are scheduled statically: full tiles round-robin (sk_full is a multiple of the cluster
+					// count, so every pair gets the same number, and tiles of one round are consecutive = L2-friendly), then this
+					// pair's own tail range.  The dynamic counter claims up to SCHED_SLOTS items ahead, which at a few tiles per
+					// pair would hand the cheap tail ranges to whoever asks last and leave the others with whole tiles.
+					const int rounds = P.sk_full / num_clusters;
+					tile = n < rounds ? n * num_clusters + cluster_id : (n == rounds && P.sk_full + cluster_id < P.num_tiles ? P.sk_full + cluster_id : -1);
+				} else {
+					tile = atomicAdd(P.sched, 1);
+					if (tile >= P.num_tiles) tile = -1;
+				}
 				asm volatile("st.shared.b32 [%0], %1;" ::"r"(slots + 4u * slot), "r"(tile) : "memory");
 				if (CG == 2) {
 					asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 1;\n\t"
@@ -351,8 +398,11 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		int it = 0;
 		long long w_full = 0, t_work = 0, t_fence = 0; const long long t_begin = tick<PROF>();
 		int nt = 0;
-		while (next_tile<CG>(bar_base, nt, true, lane, P.diag) >= 0) {
-			for (int kb = 0; kb < nkb && !(P.flags & 64); kb++, it++) {
+		for (int item; (item = next_tile<CG>(bar_base, nt, true, lane, P.diag)) >= 0;) {
+			for (int sg = 0; sg < 2; sg++) {
+			const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
+			if (wi.kb1 <= wi.kb0) continue;
+			for (int kb = wi.kb0; kb < wi.kb1 && !(P.flags & 64); kb++, it++) {
 				if (!XF_SPLIT_STAGE && it % XF_GROUPS != grp) continue;
 				const int s = it % STAGES;
 				const uint32_t ph = (it / STAGES) & 1;
@@ -391,6 +441,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				const long long t3 = tick<PROF>();
 				w_full += t1 - t0; t_work += t2 - t1; t_fence += t3 - t2;
 			}
+			}
 		}
 		if (prof && threadIdx.x == 128) { prof[5] = w_full; prof[6] = t_work; prof[7] = t_fence; prof[8] = tick<PROF>() - t_begin; }
 	} else {
@@ -405,7 +456,11 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		int ci = 0;
 		long long w_tf = 0, t_drain = 0, t_store = 0; const long long t_begin = tick<PROF>();
 		int nt = 0;
-		for (int tile; (tile = next_tile<CG>(bar_base, nt, true, lane, P.diag)) >= 0;) {
+		for (int item; (item = next_tile<CG>(bar_base, nt, true, lane, P.diag)) >= 0;) {
+			for (int sg = 0; sg < 2; sg++) {
+			const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
+			if (wi.kb1 <= wi.kb0) continue;
+			const int tile = wi.tile;
 			int tm, tn;
 			const int inst = tile / P.tiles_per_batch;
 			decode_tile(tile - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
@@ -415,7 +470,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			// beta != 0: the old C is folded in UP FRONT -- the running sums start at (beta/alpha)*C, loaded while the
 			// tile's first MMAs run and the epilogue warps would idle anyway -- so the tile end is store-only and
 			// never stalls the accumulator hand-over on a global-load round trip.
-			if (!CONV && preload_c && row < P.M) {
+			if (!CONV && preload_c && wi.slot < 0 && row < P.M) {
 #pragma unroll
 				for (int g = 0; g < NG; g++) {
 					const long long col0 = (long long)tn * BN + h * (BN / 2) + g * 32;
@@ -436,7 +491,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
 					for (int i = 0; i < 32; i++) acc[g][i] = 0.f;
 			}
-			for (int kb0 = 0; kb0 < nkb; kb0 += kc, ci++) {
+			for (int kb0 = wi.kb0; kb0 < wi.kb1; kb0 += kc, ci++) {
 				const int ab = ci & 1;
 				const uint32_t aph = (ci >> 1) & 1;
 				const long long t0 = tick<PROF>();
@@ -460,6 +515,16 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				w_tf += t1 - t0; t_drain += tick<PROF>() - t1;
 			}
 			const long long ts0 = tick<PROF>();
+			if (!CONV && wi.slot >= 0) {
+				// stream-K part: raw partial sums to the workspace tile of this item (tile-local layout, UMMA_M x BN floats)
+				float *wrow = P.sk_ws + (long long)wi.slot * (UMMA_M * BN) + (long long)((int)cta_rank * ROWS + q * 32 + lane) * BN + h * (BN / 2);
+#pragma unroll
+				for (int g = 0; g < NG; g++)
+#pragma unroll
+					for (int i = 0; i < 32; i += 4)
+						*reinterpret_cast<float4 *>(wrow + g * 32 + i) = make_float4(acc[g][i], acc[g][i + 1], acc[g][i + 2], acc[g][i + 3]);
+				continue;
+			}
 			// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
 			const float beta = preload_c ? 0.f : P.beta;   // already folded into acc when preloaded
 			if (row < P.M && !(P.flags & 16)) {
@@ -524,6 +589,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				}
 			}
 			t_store += tick<PROF>() - ts0;
+			}
 		}
 		if (prof && threadIdx.x == 32 * (4 + 4 * XF_GROUPS)) { prof[9] = w_tf; prof[10] = t_drain; prof[11] = t_store; prof[12] = tick<PROF>() - t_begin; }
 	}
@@ -532,6 +598,52 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 	tc_fence_before();
 	if (CG == 2) { cluster_arrive(); cluster_wait(); } else __syncthreads();
 	if (warp == 1) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stream-K fix-up: C tile = alpha * (sum of the tile's partial-sum parts, in range order) + beta * C (+ bias, LeakyReLU).
+// FIXUP_SPLIT CTAs per tail tile; the parts are L2-resident (just written by K1).  Deterministic: no atomics, fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FIXUP_SPLIT = 8;       // CTAs per tail tile
+template <int CG>
+__global__ void __launch_bounds__(256)
+k1_tail_fixup_kernel(const K1Params P)
+{
+	constexpr int TM_ = 128 * CG, TN_ = 128 * CG, Q = TN_ / 4, ROWS_PER_CTA = TM_ / FIXUP_SPLIT;
+	const int r = blockIdx.x;
+	int tm, tn;
+	decode_tile(P.sk_full + r, P.tiles_m, P.tiles_n, tm, tn);
+	const int r_lo = (r * P.sk_nch) / P.sk_q, r_hi = ((r + 1) * P.sk_nch - 1) / P.sk_q;
+	const float alpha = P.alpha, beta = P.beta, slope = P.slope;
+	const bool post = P.bias != nullptr || slope != 1.f;
+#pragma unroll 4
+	for (int idx = threadIdx.x; idx < ROWS_PER_CTA * Q; idx += blockDim.x) {
+		const int row = blockIdx.y * ROWS_PER_CTA + idx / Q, c4 = (idx % Q) * 4;
+		const long long gm = (long long)tm * TM_ + row, gn = (long long)tn * TN_ + c4;
+		if (gm >= P.M || gn >= P.N) continue;
+		float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+		for (int rr = r_lo; rr <= r_hi; rr++) {
+			const int slot = 2 * rr + (((rr * P.sk_q) / P.sk_nch == r) ? 0 : 1);
+			const float4 v = *reinterpret_cast<const float4 *>(P.sk_ws + (long long)slot * (TM_ * TN_) + (long long)row * TN_ + c4);
+			sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+		}
+		float *cp = P.C + gm * P.ldc + gn;
+		const float bm = P.bias ? __ldg(P.bias + gm) : 0.f;
+		auto fin = [&](float acc, float cold) {
+			float o = beta != 0.f ? fmaf(alpha, acc, beta * cold) : alpha * acc;
+			if (post) { o += bm; o = o > 0.f ? o : o * slope; }
+			return o;
+		};
+		if (P.vecC && gn + 3 < P.N) {
+			float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (beta != 0.f) c = *reinterpret_cast<const float4 *>(cp);
+			*reinterpret_cast<float4 *>(cp) = make_float4(fin(sum.x, c.x), fin(sum.y, c.y), fin(sum.z, c.z), fin(sum.w, c.w));
+		} else {
+			const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
+			for (int e = 0; e < 4; e++)
+				if (gn + e < P.N) cp[e] = fin(sv[e], beta != 0.f ? cp[e] : 0.f);
+		}
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -720,7 +832,39 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	const long long nt = (long long)P.tiles_m * P.tiles_n * (p.batch > 0 ? p.batch : 1);
 	P.num_k_blocks = (p.K + BK - 1) / BK;
 	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0) ? 1 : 0;
-	return launch_kernel<CG, false>(tmA, tmB, P, nt, t, stream, sm_count);
+
+	// Stream-K tail.  A persistent grid of `pairs` clusters finishes nt tiles in ceil(nt / pairs) rounds; when the last round is
+	// only partly filled (c3: 192 tiles on 74 pairs = 2.6 rounds, 4096^3: 3.5, anything smaller than the machine: < 1), its
+	// tiles are cut along K into equal chunk ranges, one per pair, whose partial sums meet in a workspace (decode_item,
+	// k1_tail_fixup_kernel).  Taken when it shortens the last round by at least 15 %.
+	const int kc_eff = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
+	const int nch = (P.num_k_blocks + kc_eff - 1) / kc_eff;
+	const long long pairs = sm_count / CG;
+	long long items = nt;
+	float *ws = nullptr;
+	if (!(t.flags & 2048) && p.batch <= 1 && nch >= 2 && pairs > 0 && nt % pairs != 0) {   // (ranges <= pairs = clusters launched)
+		const long long full = nt / pairs * pairs, rem = nt - full;
+		const long long q = (rem * nch + pairs - 1) / pairs, ranges = (rem * nch + q - 1) / q;
+		// expected saving: (1 - q/nch) of one round out of ceil(nt / pairs); the fix-up pass and the tail's poorer L2 locality
+		// (parts of one tile run at different k offsets) cost a few percent of a round, so small savings are not worth it
+		const double saved_rounds = 1.0 - (double)q / nch, rounds = (double)((nt + pairs - 1) / pairs);
+		if (saved_rounds >= 0.15 && saved_rounds / rounds >= 0.04 && rem * nch < 0x3fffffffLL) {
+			const size_t tile_bytes = (size_t)tile_m * tile_n * sizeof(float);
+			if (cudaMallocAsync(reinterpret_cast<void **>(&ws), (size_t)(2 * ranges) * tile_bytes, stream) == cudaSuccess) {
+				P.sk_full = (int)full; P.sk_rem = (int)rem; P.sk_nch = nch; P.sk_q = (int)q; P.sk_ws = ws;
+				items = full + ranges;
+			} else { cudaGetLastError(); ws = nullptr; }
+		}
+	}
+	cudaError_t e = launch_kernel<CG, false>(tmA, tmB, P, items, t, stream, sm_count);
+	if (ws) {
+		if (e == cudaSuccess) {
+			k1_tail_fixup_kernel<CG><<<dim3((unsigned)P.sk_rem, FIXUP_SPLIT), 256, 0, stream>>>(P);
+			e = cudaGetLastError();
+		}
+		cudaFreeAsync(ws, stream);
+	}
+	return e;
 }
 
 // channels-last image as a 4-D tensor {c: cs, x: w, y: h, image: nimg}, box {32 c, 32 x, 1 y, 1}: one box = 32 output pixels of one
