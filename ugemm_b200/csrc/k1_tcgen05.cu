@@ -966,6 +966,10 @@ cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t s
 		// SMs (measured cross-over between 1536^3 = 36 pair tiles and 2048^3 = 64, profiles/r1_sizes.txt)
 		const long long pair_tiles = (long long)((p.M + 255) / 256) * ((p.N + 255) / 256) * (p.batch > 0 ? p.batch : 1);
 		cg = (pair_tiles * 8 >= (long long)(sm_count / 2) * 6) ? 2 : 1;
+		// with the stream-K tail, fewer pair tiles still fill the machine when K is long enough to give every pair >= 4
+		// promotion chunks (1024 x 1024 x 8192: 109 vs 134 us; 1536^3: 58 vs 62 us; profiles/r1_sizes.txt)
+		const int nkb = (p.K + BK - 1) / BK, kc_eff = (t.kc_blocks > 0 && t.kc_blocks < nkb) ? t.kc_blocks : nkb;
+		if (cg == 1 && !(t.flags & 2048) && p.batch <= 1 && pair_tiles * ((nkb + kc_eff - 1) / kc_eff) >= 4LL * (sm_count / 2)) cg = 2;
 	}
 	if (cg == 1) return launch_cg<1>(p, t, stream, sm_count);
 	return launch_cg<2>(p, t, stream, sm_count);
