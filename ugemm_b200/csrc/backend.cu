@@ -143,6 +143,17 @@ int repack_for_tma(const Problem &p, cudaStream_t stream, Problem *q, void **scr
 	return 0;
 }
 
+// K1 launch with the backend's tuning.  While an SM limit is set (the sharded driver leaves SMs to NCCL, whose CTAs may delay
+// some of K1's persistent pairs) the statically scheduled stream-K tail is switched off: the dynamic scheduler absorbs late
+// pairs, a static schedule would wait for them.
+cudaError_t launch_k1(const Problem &p, cudaStream_t stream)
+{
+	const bool limited = g.sm_limit > 0 && g.sm_limit < g.sm_count;
+	K1Tuning t = g.tuning;
+	if (limited) t.flags |= 2048;
+	return launch_k1_3xtf32(p, t, stream, limited ? g.sm_limit : g.sm_count);
+}
+
 // device-pointer GEMM on `stream`
 int run_dev(int mode, cudaStream_t stream, const Problem &p)
 {
@@ -159,7 +170,7 @@ int run_dev(int mode, cudaStream_t stream, const Problem &p)
 	if (mode == UGEMM_MODE_AUTO && use == UGEMM_MODE_SIMT && auto_wants_repack(p)) {
 		Problem q; void *scratch = nullptr;
 		if (repack_for_tma(p, stream, &q, &scratch) == 0 && k1_eligible(q, nullptr)) {
-			cudaError_t e = launch_k1_3xtf32(q, g.tuning, stream, (g.sm_limit > 0 && g.sm_limit < g.sm_count) ? g.sm_limit : g.sm_count);
+			cudaError_t e = launch_k1(q, stream);
 			if (scratch) cudaFreeAsync(scratch, stream);
 			CU_TRY(e, "K1 (3xTF32 tcgen05, repacked operands) launch");
 			g.last_kernel = UGEMM_MODE_3XTF32; g.last_repacked = 1;
@@ -172,7 +183,7 @@ int run_dev(int mode, cudaStream_t stream, const Problem &p)
 	if (use == UGEMM_MODE_3XTF32) {
 		const char *why = nullptr;
 		if (!k1_eligible(p, &why)) { set_error("3xTF32 kernel not applicable: %s", why); return 1; }
-		CU_TRY(launch_k1_3xtf32(p, g.tuning, stream, (g.sm_limit > 0 && g.sm_limit < g.sm_count) ? g.sm_limit : g.sm_count), "K1 (3xTF32 tcgen05) launch");
+		CU_TRY(launch_k1(p, stream), "K1 (3xTF32 tcgen05) launch");
 	} else if (use == UGEMM_MODE_SIMT) {
 		CU_TRY(launch_k2_simt(p, stream, g.sm_count), "K2 (SIMT FFMA) launch");
 	} else {

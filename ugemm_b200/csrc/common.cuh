@@ -49,6 +49,7 @@ struct ConvProblem {
 // bits 1-4 are ABLATION switches for bottleneck analysis only (results are wrong with them):
 // 2 transform skips its stores, 4 transform skips loads and stores, 8 only big*big is issued, 16 epilogue skips stores,
 // 32 per-role cycle counters to stderr, 64 MMA free-run (no TMA / transform / stage barriers: raw tensor-pipe ceiling).
+// bits 7-10: L2 eviction hints of the TMA loads (experiments); bit 11 (2048): stream-K tail off (A/B runs, SM-limited launches).
 struct K1Tuning { int kc_blocks; int split; int cta_group; int flags; };
 
 // K2: register-blocked FFMA kernel (k2_simt.cu)
