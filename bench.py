@@ -196,7 +196,60 @@ def other_shapes(u, peaks, info):
     run("c4 200704x256x1152 NN (im2col shape)", "auto", "N", "N", 200704, 256, 1152, 1.0, 0.0, 1152, 256, 256,
         "AI 105 flop/B: above the 3xTF32 ridge, HBM time is ~40% of the tensor time (SURVEY 8d)")
     run("c4 200704x256x1152 NN beta=1 (accumulate)", "auto", "N", "N", 200704, 256, 1152, 1.0, 1.0, 1152, 256, 256, None)
+    out += widened_rows(u, peaks, info, tensor_peak)
     return out
+
+
+def widened_rows(u, peaks, info, tensor_peak):
+    """SURVEY section 8(f) rows at 1 GPU: the fused convolution that produces config 4's GEMM, SAXPY / SGEMV against the measured
+    HBM bandwidth, DGEMM against the FP64 pipe.  Wall clock around 10 back-to-back launches bracketed by device syncs."""
+    def timed(fn, iters=10, warm=3):
+        for _ in range(warm):
+            fn()
+        u.sync()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        u.sync()
+        return (time.perf_counter() - t0) / iters * 1e3
+
+    rows = []
+    nimg, ich, h, w, k, pad, ch = 64, 128, 56, 56, 3, 1, 256
+    dx, dw = u.DeviceBuffer(nimg * ich * h * w).fill_uniform(1, -0.5, 0.5), u.DeviceBuffer(ch * ich * k * k).fill_uniform(2, -0.5, 0.5)
+    db, dout = u.DeviceBuffer(ch).fill_uniform(3, -0.5, 0.5), u.DeviceBuffer(nimg * ch * h * w)
+    ms = timed(lambda: u.convolution_cuda_batched_dev("auto", None, dx, nimg, ich, w, h, dw, k, pad, 1, dout, ch, db, 0.1, None))
+    flops = 2.0 * nimg * ch * h * w * ich * k * k
+    rows.append({"shape": "convolution 64 x (128x56x56) -> 256 filters 3x3 pad 1 + bias + LeakyReLU (the layer behind c4), implicit GEMM",
+                 "kernel": "3xtf32 CONV (4-D TMA gather)" if u.last_conv_fused() else "im2col + GEMM", "ms_avg": ms, "tflops": flops / ms / 1e9,
+                 "roofline_bound": "tensor (3xTF32)", "roofline_peak_tflops": tensor_peak, "roofline_frac": flops / ms / 1e9 / tensor_peak,
+                 "note": "time includes the channels-last staging pass and the weight repack; the 925 MB column matrix is never built"})
+    for b in (dx, dw, db, dout):
+        b.free()
+    n = 1 << 28
+    dx, dy = u.DeviceBuffer(n).fill_uniform(1), u.DeviceBuffer(n).fill_uniform(2)
+    ms = timed(lambda: u.saxpy_cuda_dev(None, n, 0.5, dx, 1, dy, 1))
+    rows.append({"shape": "saxpy n=2^28", "kernel": "saxpy_vec", "ms_avg": ms, "algorithmic_gbs": 12.0 * n / ms / 1e6, "roofline_bound": "hbm",
+                 "roofline_peak_gbs": peaks["hbm_gbs"], "roofline_frac": 12.0 * n / ms / 1e6 / peaks["hbm_gbs"]})
+    dx.free(); dy.free()
+    M = N = 16384
+    dA, dx, dy = u.DeviceBuffer(M * N).fill_uniform(3), u.DeviceBuffer(N).fill_uniform(4, -0.5, 0.5), u.DeviceBuffer(M)
+    for trans in ("T", "N"):
+        ms = timed(lambda: u.sgemv_cuda_dev(None, trans, M, N, 1.0, dA, M, dx, 1, 0.0, dy, 1))
+        rows.append({"shape": f"sgemv '{trans}' 16384x16384", "kernel": "sgemv_rows" if trans == "T" else "sgemv_cols", "ms_avg": ms,
+                     "algorithmic_gbs": 4.0 * M * N / ms / 1e6, "roofline_bound": "hbm", "roofline_peak_gbs": peaks["hbm_gbs"],
+                     "roofline_frac": 4.0 * M * N / ms / 1e6 / peaks["hbm_gbs"]})
+    for b in (dA, dx, dy):
+        b.free()
+    n = 4096
+    dA, dB, dC = u.DeviceBuffer(2 * n * n).fill_uniform(5), u.DeviceBuffer(2 * n * n).fill_uniform(6), u.DeviceBuffer(2 * n * n)
+    # the fp32 fill makes each double a pair of random fp32 words: finite, in [2^-127, 2) -- fine for a throughput run
+    avg, best = u.dgemm_cuda_time_dev(10, 3, "R", "N", "N", n, n, n, 1.0, dA, n, dB, n, 0.0, dC, n)
+    fp64_peak = info["sm_count"] * 64 * 2 * info["sm_clock_khz"] * 1e3 / 1e12
+    rows.append({"shape": "dgemm 4096^3 NN", "kernel": "K4 DFMA", "ms_avg": avg, "ms_min": best, "tflops": 2.0 * n ** 3 / avg / 1e9,
+                 "roofline_bound": "fp64 pipe", "roofline_peak_tflops": fp64_peak, "roofline_frac": 2.0 * n ** 3 / avg / 1e9 / fp64_peak})
+    for b in (dA, dB, dC):
+        b.free()
+    return rows
 
 
 def run_single(args, wl_name):

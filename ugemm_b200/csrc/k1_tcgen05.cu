@@ -515,7 +515,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				w_tf += t1 - t0; t_drain += tick<PROF>() - t1;
 			}
 			const long long ts0 = tick<PROF>();
-			if (!CONV && wi.slot >= 0) {
+			if (wi.slot >= 0) {
 				// stream-K part: raw partial sums to the workspace tile of this item (tile-local layout, UMMA_M x BN floats)
 				float *wrow = P.sk_ws + (long long)wi.slot * (UMMA_M * BN) + (long long)((int)cta_rank * ROWS + q * 32 + lane) * BN + h * (BN / 2);
 #pragma unroll
@@ -612,7 +612,9 @@ k1_tail_fixup_kernel(const K1Params P)
 	constexpr int TM_ = 128 * CG, TN_ = 128 * CG, Q = TN_ / 4, ROWS_PER_CTA = TM_ / FIXUP_SPLIT;
 	const int r = blockIdx.x;
 	int tm, tn;
-	decode_tile(P.sk_full + r, P.tiles_m, P.tiles_n, tm, tn);
+	const int inst = (P.sk_full + r) / P.tiles_per_batch;
+	decode_tile(P.sk_full + r - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
+	const bool conv = P.cv_wp > 0;
 	const int r_lo = (r * P.sk_nch) / P.sk_q, r_hi = ((r + 1) * P.sk_nch - 1) / P.sk_q;
 	const float alpha = P.alpha, beta = P.beta, slope = P.slope;
 	const bool post = P.bias != nullptr || slope != 1.f;
@@ -627,21 +629,31 @@ k1_tail_fixup_kernel(const K1Params P)
 			const float4 v = *reinterpret_cast<const float4 *>(P.sk_ws + (long long)slot * (TM_ * TN_) + (long long)row * TN_ + c4);
 			sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
 		}
-		float *cp = P.C + gm * P.ldc + gn;
+		float *cp = P.C + (long long)inst * P.strideC + gm * P.ldc + gn;
+		int valid = 4;                              // elements of this quad that exist in C
+		bool vec = P.vecC;
+		if (conv) {                                 // padded column index -> (output row, output column); a quad never straddles rows
+			const int io = (int)(gn / P.cv_wp), jo = (int)(gn - (long long)io * P.cv_wp);
+			valid = io < P.cv_ho ? P.cv_wo - jo : 0;
+			const int off = io * P.cv_wo + jo;
+			cp = P.C + (long long)inst * P.strideC + gm * (long long)P.cv_npix + off;
+			vec = vec && (off & 3) == 0;
+		} else if (gn + 3 >= P.N) valid = (int)(P.N - gn);
+		if (valid <= 0) continue;
 		const float bm = P.bias ? __ldg(P.bias + gm) : 0.f;
 		auto fin = [&](float acc, float cold) {
 			float o = beta != 0.f ? fmaf(alpha, acc, beta * cold) : alpha * acc;
 			if (post) { o += bm; o = o > 0.f ? o : o * slope; }
 			return o;
 		};
-		if (P.vecC && gn + 3 < P.N) {
+		if (vec && valid >= 4) {
 			float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
 			if (beta != 0.f) c = *reinterpret_cast<const float4 *>(cp);
 			*reinterpret_cast<float4 *>(cp) = make_float4(fin(sum.x, c.x), fin(sum.y, c.y), fin(sum.z, c.z), fin(sum.w, c.w));
 		} else {
 			const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
 			for (int e = 0; e < 4; e++)
-				if (gn + e < P.N) cp[e] = fin(sv[e], beta != 0.f ? cp[e] : 0.f);
+				if (e < valid) cp[e] = fin(sv[e], beta != 0.f ? cp[e] : 0.f);
 		}
 	}
 }
@@ -814,6 +826,45 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Para
 	return le;
 }
 
+// Stream-K tail.  A persistent grid of `pairs` clusters finishes nt tiles in ceil(nt / pairs) rounds; when the last round is
+// only partly filled (c3: 192 tiles on 74 pairs = 2.6 rounds, 4096^3: 3.5, anything smaller than the machine: < 1), its
+// tiles are cut along K into equal chunk ranges, one per pair, whose partial sums meet in a workspace (decode_item,
+// k1_tail_fixup_kernel).  Taken when it shortens the last round by at least 15 % and the launch by at least 12 %.
+template <int CG, bool CONV>
+cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
+{
+	const int kc_eff = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
+	const int nch = (P.num_k_blocks + kc_eff - 1) / kc_eff;
+	const long long pairs = sm_count / CG;
+	const int tile_m = 128 * CG, tile_n = 128 * CG;
+	long long items = nt;
+	float *ws = nullptr;
+	if (!(t.flags & 2048) && nch >= 2 && pairs > 0 && nt % pairs != 0) {
+		const long long full = nt / pairs * pairs, rem = nt - full;
+		const long long q = (rem * nch + pairs - 1) / pairs, ranges = (rem * nch + q - 1) / q;
+		// expected saving: (1 - q/nch) of one round out of ceil(nt / pairs); the fix-up pass and the tail's poorer L2 locality
+		// (parts of one tile run at different k offsets) cost a few percent of a round, so small savings are not worth it
+		const double saved_rounds = 1.0 - (double)q / nch, rounds = (double)((nt + pairs - 1) / pairs);
+		// (measured: a modelled saving of 7-11 % of the launch came out as a 2-4 % loss, 13 % as a 10 % gain)
+		if (saved_rounds >= 0.15 && saved_rounds / rounds >= 0.12 && rem * nch < 0x3fffffffLL) {
+			const size_t tile_bytes = (size_t)tile_m * tile_n * sizeof(float);
+			if (cudaMallocAsync(reinterpret_cast<void **>(&ws), (size_t)(2 * ranges) * tile_bytes, stream) == cudaSuccess) {
+				P.sk_full = (int)full; P.sk_rem = (int)rem; P.sk_nch = nch; P.sk_q = (int)q; P.sk_ws = ws;
+				items = full + ranges;
+			} else { cudaGetLastError(); ws = nullptr; }
+		}
+	}
+	cudaError_t e = launch_kernel<CG, CONV>(tmA, tmB, P, items, t, stream, sm_count);
+	if (ws) {
+		if (e == cudaSuccess) {
+			k1_tail_fixup_kernel<CG><<<dim3((unsigned)P.sk_rem, FIXUP_SPLIT), 256, 0, stream>>>(P);
+			e = cudaGetLastError();
+		}
+		cudaFreeAsync(ws, stream);
+	}
+	return e;
+}
+
 template <int CG>
 cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
@@ -833,38 +884,7 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	P.num_k_blocks = (p.K + BK - 1) / BK;
 	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0) ? 1 : 0;
 
-	// Stream-K tail.  A persistent grid of `pairs` clusters finishes nt tiles in ceil(nt / pairs) rounds; when the last round is
-	// only partly filled (c3: 192 tiles on 74 pairs = 2.6 rounds, 4096^3: 3.5, anything smaller than the machine: < 1), its
-	// tiles are cut along K into equal chunk ranges, one per pair, whose partial sums meet in a workspace (decode_item,
-	// k1_tail_fixup_kernel).  Taken when it shortens the last round by at least 15 %.
-	const int kc_eff = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
-	const int nch = (P.num_k_blocks + kc_eff - 1) / kc_eff;
-	const long long pairs = sm_count / CG;
-	long long items = nt;
-	float *ws = nullptr;
-	if (!(t.flags & 2048) && p.batch <= 1 && nch >= 2 && pairs > 0 && nt % pairs != 0) {   // (ranges <= pairs = clusters launched)
-		const long long full = nt / pairs * pairs, rem = nt - full;
-		const long long q = (rem * nch + pairs - 1) / pairs, ranges = (rem * nch + q - 1) / q;
-		// expected saving: (1 - q/nch) of one round out of ceil(nt / pairs); the fix-up pass and the tail's poorer L2 locality
-		// (parts of one tile run at different k offsets) cost a few percent of a round, so small savings are not worth it
-		const double saved_rounds = 1.0 - (double)q / nch, rounds = (double)((nt + pairs - 1) / pairs);
-		if (saved_rounds >= 0.15 && saved_rounds / rounds >= 0.04 && rem * nch < 0x3fffffffLL) {
-			const size_t tile_bytes = (size_t)tile_m * tile_n * sizeof(float);
-			if (cudaMallocAsync(reinterpret_cast<void **>(&ws), (size_t)(2 * ranges) * tile_bytes, stream) == cudaSuccess) {
-				P.sk_full = (int)full; P.sk_rem = (int)rem; P.sk_nch = nch; P.sk_q = (int)q; P.sk_ws = ws;
-				items = full + ranges;
-			} else { cudaGetLastError(); ws = nullptr; }
-		}
-	}
-	cudaError_t e = launch_kernel<CG, false>(tmA, tmB, P, items, t, stream, sm_count);
-	if (ws) {
-		if (e == cudaSuccess) {
-			k1_tail_fixup_kernel<CG><<<dim3((unsigned)P.sk_rem, FIXUP_SPLIT), 256, 0, stream>>>(P);
-			e = cudaGetLastError();
-		}
-		cudaFreeAsync(ws, stream);
-	}
-	return e;
+	return launch_with_tail<CG, false>(tmA, tmB, P, nt, t, stream, sm_count);
 }
 
 // channels-last image as a 4-D tensor {c: cs, x: w, y: h, image: nimg}, box {32 c, 32 x, 1 y, 1}: one box = 32 output pixels of one
@@ -902,7 +922,7 @@ cudaError_t launch_conv_cg(const ConvProblem &c, const K1Tuning &t, cudaStream_t
 	P.num_k_blocks = kk / BK;
 	P.vecC = ((reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && npix % 4 == 0) ? 1 : 0;
 	P.cv_wp = wp; P.cv_wo = c.wo; P.cv_ho = c.ho; P.cv_k = c.k; P.cv_pad = c.pad; P.cv_cblocks = c.ichp / 32; P.cv_npix = npix; P.cv_stride = c.stride;
-	return launch_kernel<CG, true>(tmA, tmB, P, nt, t, stream, sm_count);
+	return launch_with_tail<CG, true>(tmA, tmB, P, nt, t, stream, sm_count);
 }
 
 // planar [img][c][y][x] -> channels-last [img][y][x][cs] (cs = ich rounded up to 4, the pad channels zero): one image-sized HBM pass
