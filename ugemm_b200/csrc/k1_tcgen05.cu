@@ -8,21 +8,26 @@
 // Replaces the reference's blocked inner loops (sgemm_avx256.h:20-390, gemm_cpu.h:96-282, the OpenCL
 // gemm_fast / gemm_rnn kernels sgemm_ocl.h:444-538, sgemm_ocl2.h:17-90) for TMA-eligible problems.
 //
-// Structure (one CTA per SM, optionally paired as a 2-CTA cluster issuing cta_group::2 MMAs):
+// Structure (one CTA per SM, optionally paired as a 2-CTA cluster issuing cta_group::2 MMAs; 640 threads):
 //   warp 0      TMA producer: raw fp32 tiles of op(A) (128 rows) and op(B) (128 rows) per k-block of 32,
 //               128B-swizzled, into a 3-stage shared-memory ring.  K-major operands: one {32 k x 128 row}
 //               box, SWIZZLE_128B.  MN-major operands (transA=='T' / transB=='N'): four {32 mn x 32 k}
 //               boxes, SWIZZLE_128B_ATOM_32B (the only MN-major layout tcgen05 accepts for 32-bit types).
-//               Ragged M/N/K edges are zero-filled by TMA out-of-bounds handling.
-//   warps 4-11  transform (two warpgroups alternating k-blocks, so the shared-memory round trips and the proxy
-//               fence of one stage overlap the next): read each landed stage, write the "small" operand copies
-//               (same swizzled layout, so the transform is a flat element-wise pass), fence.proxy.async, signal.
+//               Ragged M/N/K edges are zero-filled by TMA out-of-bounds handling.  CONV instantiation: the B
+//               boxes are gathered from a channels-last image with 4-D coordinates (implicit im2col).
 //   warp 1      MMA issuer (leader CTA only): per k-step of 8: small*big, big*small, big*big into the TMEM
 //               accumulator; tcgen05.commit releases the stage; accumulators are double-buffered in TMEM.
-//   warps 12-19 epilogue: tcgen05.ld the accumulator, (optionally) promote partial sums every kc_blocks
-//               k-blocks into fp32 registers with round-to-nearest adds, then fused alpha/beta and
-//               direct global stores (row per thread, 128 B contiguous per 32-column group).
-//   Persistent: each CTA (pair) walks a static, L2-friendly grouped tile order.
+//   warp 2      work scheduler (leader CTA only): claims tile indices from a global atomic counter -- or, for a
+//               stream-K launch, walks the static schedule -- and publishes them to every role of both CTAs
+//               through a 4-deep shared-memory ring.
+//   warps 4-11  transform (two warpgroups sharing every stage): read each landed stage, write the "small"
+//               operand copies (same swizzled layout, so the transform is a flat element-wise pass),
+//               fence.proxy.async, signal.
+//   warps 12-19 epilogue: tcgen05.ld the accumulator, promote partial sums every kc_blocks k-blocks into fp32
+//               registers with round-to-nearest adds, then fused alpha/beta(/bias/LeakyReLU) and direct global
+//               stores (row per thread, 128 B contiguous per 32-column group) -- or, for a stream-K part, raw
+//               partial sums into the workspace that k1_tail_fixup_kernel adds up.
+//   Persistent: tiles are handed out in an L2-friendly grouped order (8 m-tiles share an n sweep).
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda.h>
