@@ -176,3 +176,20 @@ def test_conv_fusion_rule_and_fallbacks(u):
     assert not run(128, 13, 12, 3, 1, 1, 256)      # wo = 12 -> 32: too much padded work
     assert not run(3, 32, 32, 3, 1, 1, 64)         # 3 channels -> 32
     assert not run(64, 28, 28, 3, 1, 1, 32)        # few filters
+
+
+@pytest.mark.gpu
+def test_conv_unfused_path_requires_a_workspace(u):
+    """A geometry that takes im2col + GEMM with d_workspace == NULL is an error, not a crash; the output is untouched."""
+    ich, h, w, k, pad, stride, ch = 8, 20, 20, 3, 1, 9, 16
+    x, wgt, _ = make_conv(ich, h, w, k, ch, seed=95)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    dx, dw = u.DeviceBuffer(x.size).upload(x), u.DeviceBuffer(wgt.size).upload(wgt)
+    sentinel = np.full(ch * ho * wo, 7.0, np.float32)
+    dout = u.DeviceBuffer(sentinel.size).upload(sentinel)
+    with pytest.raises(u.UgemmCudaError):
+        u.convolution_cuda_dev("auto", None, dx, ich, w, h, dw, k, pad, stride, dout, ch, None, 1.0, None)
+    with pytest.raises(u.UgemmCudaError):
+        u.convolution_cuda_batched_dev("auto", None, dx, 1, ich, w, h, dw, k, pad, stride, dout, ch, None, 1.0, None)
+    u.sync()
+    assert np.array_equal(dout.download(), sentinel)

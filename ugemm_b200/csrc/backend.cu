@@ -766,6 +766,7 @@ int convolution_cuda_batched_dev(int mode, void *stream, const float *d_inputs, 
 	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
 	if (conv_fusable(mode, nimg, ich, w, h, k, pad, stride, ch))
 		return conv_fused_dev(st, d_inputs, nimg, ich, w, h, d_weights, k, pad, stride, d_outputs, ch, d_bias, slope);
+	if (!d_workspace) { set_error("convolution: this geometry takes the im2col path and needs d_workspace (ich*k*k*Ho*Wo floats)"); return 1; }
 	const long long ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
 	for (int i = 0; i < nimg; i++)      // the column matrix of one image at a time through the same workspace (stream order keeps it safe)
 		if (convolution_cuda_dev(mode, st, d_inputs + (size_t)i * ich * h * w, ich, w, h, d_weights, k, pad, stride,
@@ -781,6 +782,7 @@ int convolution_cuda_dev(int mode, void *stream, const float *d_inputs, int ich,
 	g.last_conv_fused = 0;
 	if (conv_fusable(mode, 1, ich, w, h, k, pad, stride, ch))
 		return conv_fused_dev(stream ? static_cast<cudaStream_t>(stream) : g.stream, d_inputs, 1, ich, w, h, d_weights, k, pad, stride, d_outputs, ch, d_bias, slope);
+	if (!d_workspace) { set_error("convolution: this geometry takes the im2col path and needs d_workspace (ich*k*k*Ho*Wo floats)"); return 1; }
 	if (im2col_cuda_dev(d_inputs, ich, h, w, k, pad, stride, d_workspace, stream)) return 1;
 	const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
 	const long long npix = (long long)ho * wo, kk = (long long)ich * k * k;
