@@ -401,3 +401,13 @@ def test_k1_stream_k_tail_is_deterministic_and_exact_enough(u):
             ref = 1.5 * (opA[rows].astype(np.float64) @ opB.astype(np.float64)) + 0.5 * Cm.reshape(M, ldc)[rows, :N]
             got = g1.reshape(M, ldc)[rows, :N]
             assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= TOL
+
+
+def test_auto_dispatch_skinny_but_large_goes_to_k1(u):
+    """One side >= 128, the other >= 48, M*N*K >= 2^26: K1 on a zero-filled tile beats K2 (dispatch rule)."""
+    for (M, N, K, want) in ((4096, 64, 512, "3xtf32"), (64, 4096, 512, "3xtf32"), (8192, 48, 256, "3xtf32"), (4096, 32, 512, "simt"),
+                            (4096, 64, 128, "simt"), (100, 100, 8192, "simt")):
+        for ta, tb in (("N", "N"), ("T", "T")):
+            (ar, ac), (br, bc), _ = O.stored_shapes("R", ta, tb, M, N, K)
+            check_case(u, "auto", "R", ta, tb, M, N, K, 1.5, 0.5, ((-ac) % 4, (-bc) % 4, 1), seed=33)
+            assert u.last_kernel() == want, (M, N, K, ta, tb)

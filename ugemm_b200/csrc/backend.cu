@@ -101,9 +101,14 @@ int normalise(char major, char ta, char tb, int M, int N, int K, float alpha, co
 	return 0;
 }
 
+// At least one full 128-wide tile side of tensor work; the other side may be as narrow as 48 once the problem is big enough to
+// amortise K1's launch (its zero-filled tile columns cost nothing extra: a 200704 x 64 x 1152 product takes 0.50 ms on K1,
+// 0.66 ms on K2; 200704 x 96: 0.50 vs 1.47 ms; at N = 32 K2's narrow tiles win, 0.40 vs 0.49 ms -- profiles/r1_skinny_k1_vs_k2.jsonl).
 bool auto_prefers_k1(const Problem &p)
 {
-	return k1_eligible(p, nullptr) && p.M >= 128 && p.N >= 128 && p.K >= 32;
+	if (!k1_eligible(p, nullptr) || p.K < 32) return false;
+	if (p.M >= 128 && p.N >= 128) return true;
+	return p.M >= 48 && p.N >= 48 && (p.M >= 128 || p.N >= 128) && (double)p.M * p.N * p.K >= 67108864.0;
 }
 
 bool tma_ok(const float *ptr, long long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 4 == 0; }
@@ -285,7 +290,8 @@ void run_host(int mode, char major, char ta, char tb, int M, int N, int K, float
 	float *dA = reinterpret_cast<float *>(g.arena + offA), *dB = reinterpret_cast<float *>(g.arena + offB);
 	float *dC = reinterpret_cast<float *>(g.arena + offC);
 
-	if (need_ab && p.M >= 2048 && !getenv("UGEMM_CUDA_NO_PIPELINE")) {
+	// the panel pipeline only pays when the transfers are long (>= 64 MB in flight); small problems go up, run and come back whole
+	if (need_ab && p.M >= 2048 && a_bytes + b_bytes + c_bytes >= (64u << 20) && !getenv("UGEMM_CUDA_NO_PIPELINE")) {
 		if (mode == UGEMM_MODE_3XTF32) {
 			Problem chk = p; chk.A = dA; chk.B = dB; chk.C = dC;
 			const char *why = nullptr;
