@@ -1033,6 +1033,7 @@ cudaError_t launch_k1_conv(const ConvProblem &c, const K1Tuning &t, cudaStream_t
 		const long long wp = (c.wo + 31) / 32 * 32;
 		const long long pair_tiles = (long long)((c.ch + 255) / 256) * ((c.ho * wp + 255) / 256) * c.nimg;
 		cg = (pair_tiles * 8 >= (long long)(sm_count / 2) * 6) ? 2 : 1;
+		if (c.ch <= 128 || (long long)c.ho * wp <= 128) cg = 1;      // one single-CTA tile covers that side (see launch_k1_3xtf32)
 	}
 	if (cg == 1) return launch_conv_cg<1>(c, t, stream, sm_count);
 	return launch_conv_cg<2>(c, t, stream, sm_count);
