@@ -245,7 +245,7 @@ def widened_rows(u, peaks, info, tensor_peak):
     # the fp32 fill makes each double a pair of random fp32 words: finite, in [2^-127, 2) -- fine for a throughput run
     avg, best = u.dgemm_cuda_time_dev(10, 3, "R", "N", "N", n, n, n, 1.0, dA, n, dB, n, 0.0, dC, n)
     fp64_peak = info["sm_count"] * 64 * 2 * info["sm_clock_khz"] * 1e3 / 1e12
-    rows.append({"shape": "dgemm 4096^3 NN", "kernel": "K4 DFMA", "ms_avg": avg, "ms_min": best, "tflops": 2.0 * n ** 3 / avg / 1e9,
+    rows.append({"shape": "dgemm 4096^3 NN", "kernel": "K4 DMMA (mma.sync.m8n8k4.f64)", "ms_avg": avg, "ms_min": best, "tflops": 2.0 * n ** 3 / avg / 1e9,
                  "roofline_bound": "fp64 pipe", "roofline_peak_tflops": fp64_peak, "roofline_frac": 2.0 * n ** 3 / avg / 1e9 / fp64_peak})
     for b in (dA, dB, dC):
         b.free()

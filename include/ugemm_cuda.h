@@ -200,7 +200,7 @@ int  sgemv_cuda_dev(void *stream, char trans, int M, int N, float alpha, const f
 
 /* ---- DGEMM: the path of check_dgemm.c.  Same 14-argument signature in double as dgemm_cpu (ugemm.h:162-178), _dgemm_c
  * (gemm_cpu.h:284-298 instantiated with real = double, ugemm.h:29-33) and dgemm_avx (dgemm_avx.h:844-858), i.e. usable as the
- * `uut` of test_dgemm (check_dgemm.c:86-97,255-258).  One kernel (K4, register-blocked DFMA, FP64-pipe bound); semantics,
+ * `uut` of test_dgemm (check_dgemm.c:86-97,255-258).  One kernel (K4, FP64 tensor-core mma.sync inner loop, FP64-pipe bound); semantics,
  * quirk decisions and error behaviour are those of sgemm_cuda.  dgemm_cuda: host pointers, blocking.  dgemm_cuda_dev:
  * device pointers, asynchronous.  dgemm_cuda_time_dev: mean / best of `iters` launches by CUDA events.  0 on success. */
 void dgemm_cuda(char major, char transA, char transB, int M, int N, int K, double alpha,

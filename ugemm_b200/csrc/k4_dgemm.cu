@@ -1,11 +1,13 @@
-// k4_dgemm.cu -- K4: register-blocked DFMA DGEMM for sm_100a (the double-precision sibling of K2).
+// k4_dgemm.cu -- K4: DGEMM for sm_100a on the FP64 tensor path (the double-precision sibling of K2).
 //
 // Replaces the reference's dgemm_cpu (ugemm.h:162-285), _dgemm_c (gemm_cpu.h instantiated with real = double,
 // ugemm.h:29-33) and dgemm_avx (dgemm_avx.h:844-925) -- the three rows of check_dgemm.c:255-258 -- for device data.
 // Same semantics as the SGEMM path: C = alpha * op(A) op(B) + beta * C, row- or column-major, N/T, any ld.
 //
-// Shape of the kernel: 128 x 64 C tile per CTA, BK = 8, 256 threads, each thread an 8 x 4 register tile of doubles split
-// in halves per dimension so the shared-memory reads are conflict-free 128-bit loads (two doubles).  Global loads are
+// Shape of the kernel: 128 x 64 C tile per CTA, BK = 8, 256 threads.  The products run on the FP64 tensor path (DMMA,
+// mma.sync.m8n8k4.f64 -- there is no tcgen05 kind for fp64): each warp owns a 32 x 32 block of the tile as 4 x 4 MMA tiles
+// (one double of A and of B per lane and tile, two accumulators per lane and tile).  -DUGEMM_K4_DMMA=0 builds the plain DFMA
+// variant (8 x 4 register tile per thread, halves per dimension so the shared-memory reads are 128-bit).  Global loads are
 // 128-bit when the operand allows it (base 16 B aligned, ld even); interior tiles take the same unguarded steady-state loop
 // as K2; transposes are folded into the global->shared staging.  Bound: the FP64 pipe, 148 SMs x 64 lanes x 2 x clock
 // = 37.2 TFLOP/s at 1965 MHz.  Algorithmic cost 2*M*N*K flop, 8*(MK + KN + MN(1+[beta != 0])) bytes.
@@ -17,7 +19,10 @@ namespace {
 
 constexpr int D_BK = 8;
 constexpr int D_THREADS = 256;
-constexpr int D_PAD = 2;
+constexpr int D_PAD = 4;      // row pitch = 4 mod 16 doubles: the 4 k-rows x 8 lines of an MMA fragment load hit 16 distinct 8-byte banks
+#ifndef UGEMM_K4_DMMA
+#define UGEMM_K4_DMMA 1
+#endif
 constexpr int D_BM = 128, D_BN = 64, D_TM = 8, D_TN = 4;
 
 __device__ __forceinline__ double2 load_pair(const double *__restrict__ line, long long c, long long cmax, bool line_ok, bool vec)
@@ -107,11 +112,23 @@ k4_dgemm_kernel(DProblem p, const int tiles_m, const int tiles_n, const bool vec
 	const int tn = (int)((tile % per_group) / gsize);
 	const long long m0 = (long long)tm * BM, n0 = (long long)tn * BN;
 
+#if UGEMM_K4_DMMA
+	// warp w: rows (w / 2) * 32 .. +32, columns (w % 2) * 32 .. +32 of the CTA tile; lane = 4 * g + q.
+	// m8n8k4 fragments: A[row g][k q], B[k q][col g], C[row g][cols 2q, 2q+1]
+	const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+	const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+	double acc[4][4][2];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#else
 	double acc[TM][TN];
 #pragma unroll
 	for (int i = 0; i < TM; i++)
 #pragma unroll
 		for (int j = 0; j < TN; j++) acc[i][j] = 0.0;
+#endif
 
 	DStager<BM, AK> sa;
 	DStager<BN, BKM> sb;
@@ -127,8 +144,26 @@ k4_dgemm_kernel(DProblem p, const int tiles_m, const int tiles_n, const bool vec
 	__syncthreads();
 
 	auto multiply = [&](int cur) {
+#if UGEMM_K4_DMMA
+#pragma unroll
+		for (int k4 = 0; k4 < D_BK; k4 += 4) {
+			double a[4], b[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++) a[i] = As[cur][k4 + q][wm + i * 8 + g];
+#pragma unroll
+			for (int j = 0; j < 4; j++) b[j] = Bs[cur][k4 + q][wn + j * 8 + g];
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+					asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+					             : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b[j]));
+		}
+		return;
+#endif
 #pragma unroll
 		for (int kk = 0; kk < D_BK; kk++) {
+#if !UGEMM_K4_DMMA
 			double a[TM], b[TN];
 #pragma unroll
 			for (int i = 0; i < HM; i++) {
@@ -144,6 +179,7 @@ k4_dgemm_kernel(DProblem p, const int tiles_m, const int tiles_n, const bool vec
 			for (int i = 0; i < TM; i++)
 #pragma unroll
 				for (int j = 0; j < TN; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+#endif
 		}
 	};
 
@@ -173,6 +209,32 @@ k4_dgemm_kernel(DProblem p, const int tiles_m, const int tiles_n, const bool vec
 
 	// fused epilogue: C = alpha*acc + beta*C (C never read when beta == 0), ld padding never touched
 	const double alpha = p.alpha, beta = p.beta;
+#if UGEMM_K4_DMMA
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const long long m = m0 + wm + i * 8 + g;
+		if (m >= p.M) continue;
+		double *crow = p.C + m * p.ldc;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const long long n = n0 + wn + j * 8 + 2 * q;
+			if (vecC && n + 1 < p.N) {
+				double2 *cp = reinterpret_cast<double2 *>(crow + n);
+				double2 o;
+				if (beta != 0.0) {
+					const double2 c = *cp;
+					o.x = fma(alpha, acc[i][j][0], beta * c.x); o.y = fma(alpha, acc[i][j][1], beta * c.y);
+				} else { o.x = alpha * acc[i][j][0]; o.y = alpha * acc[i][j][1]; }
+				*cp = o;
+			} else {
+#pragma unroll
+				for (int e = 0; e < 2; e++)
+					if (n + e < p.N) crow[n + e] = (beta != 0.0) ? fma(alpha, acc[i][j][e], beta * crow[n + e]) : alpha * acc[i][j][e];
+			}
+		}
+	}
+	return;
+#else
 #pragma unroll
 	for (int i = 0; i < TM; i++) {
 		const long long m = m0 + (i < HM ? ty * HM + i : BM / 2 + ty * HM + (i - HM));
@@ -199,6 +261,7 @@ k4_dgemm_kernel(DProblem p, const int tiles_m, const int tiles_n, const bool vec
 			}
 		}
 	}
+#endif
 }
 
 __global__ void scale_c_f64_kernel(double *C, long long ldc, int M, int N, double beta)
