@@ -337,9 +337,9 @@ def run_multi(args, wl_name):
     # the panel broadcasts only have to keep up with the GEMM of the previous slab, not saturate NVLink: a few CTAs
     # per communicator are enough and fit in the SMs the sharded driver leaves free (ugemm_b200/dist.py)
     os.environ.setdefault("NCCL_MAX_CTAS", "4")
-    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, set by some images) goes to stdout too
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line: NCCL's own log (the image sets NCCL_DEBUG=VERSION, whose banner goes to stdout) is
+    # sent to stderr instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local)
     u.sgemm_cuda_init(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
