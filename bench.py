@@ -337,9 +337,11 @@ def run_multi(args, wl_name):
     # the panel broadcasts only have to keep up with the GEMM of the previous slab, not saturate NVLink: a few CTAs
     # per communicator are enough and fit in the SMs the sharded driver leaves free (ugemm_b200/dist.py)
     os.environ.setdefault("NCCL_MAX_CTAS", "4")
-    # stdout carries exactly one JSON line: NCCL's own log (the image sets NCCL_DEBUG=VERSION, whose banner goes to stdout) is
-    # sent to stderr instead
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line.  NCCL printf()s its version banner to stdout at NCCL_DEBUG=VERSION / WARN (the image
+    # sets VERSION), so file descriptor 1 points at stderr for the whole run and the JSON line is written to the saved stdout.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     u.sgemm_cuda_init(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -472,7 +474,7 @@ def run_multi(args, wl_name):
                          "frac": flops / ms_compute / 1e9 / peak, "traffic": None,
                          "peak_basis": f"{world} x {peaks['source']} bf16 dense burst {peaks['bf16_burst']:.1f} / 6; achieved = compute-only (panels resident)"},
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     dist.barrier()
     dist.destroy_process_group()
 
