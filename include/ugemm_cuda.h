@@ -133,6 +133,29 @@ int   ugemm_cuda_ipc_export(void *dptr, void *handle64);
 void *ugemm_cuda_ipc_import(const void *handle64);
 int   ugemm_cuda_ipc_close(void *mapped);
 
+/* ---- single-process multi-GPU SGEMM (one host thread drives every GPU of the box; the C host program's way to the
+ * sharded path -- bench.py's one-process-per-GPU twin is ugemm_b200/dist.py).  The reference has no multi-device path:
+ * its OpenCL backend owns one device and one queue (ocl.h:141-193); this extends the uut signature (check_sgemm.c:96-103)
+ * by a process grid.  C is cut into pr x pc blocks, GPU i*pc + j owns block (i, j) and receives A row-panel i and B
+ * column-panel j; K is not split, so there is one exchange step and no reduction.  Panels travel slab by slab along K as a
+ * pipelined relay on the copy engines over NVLink (caller's buffer -> GPU (i,0) -> (i,1) ...; B down the columns), the
+ * product of slab t (beta = 1 after the first) runs while slab t+1 is in flight (overlap != 0), or after the whole
+ * distribution (overlap == 0, which separates distribution time from compute time; overlap == 2 also cuts K into slabs on
+ * a 1 x 1 grid, which is only useful for testing the slab arithmetic on one GPU).
+ *   sgemm_cuda_mgpu_init(n): GPUs 0..n-1, peer access all-to-all, per-GPU streams and a cached arena; 0 = OK.
+ *   sgemm_cuda_mgpu(...):    A, B, C are host pointers (pinned for speed) or device pointers of ANY GPU (unified
+ *                            addressing); same argument checks, quick returns and alpha/beta/ld semantics as sgemm_cuda;
+ *                            blocking; C's ld padding is never written; pr * pc <= n.  Returns 0 / 1 (sticky error).
+ *   timings_ms (optional, 4 floats): [0] host wall clock of the call, [1] max over GPUs of start -> C block written back,
+ *                            [2] max over GPUs of start -> last panel slab landed, [3] max over GPUs of first product
+ *                            start -> last product end. */
+int  sgemm_cuda_mgpu_init(int ngpus);
+void sgemm_cuda_mgpu_finish(void);
+int  sgemm_cuda_mgpu_count(void);     /* GPUs initialised by sgemm_cuda_mgpu_init, 0 if none */
+int  ugemm_cuda_device_count(void);   /* CUDA devices visible to this process (0 without a driver); never an error */
+int  sgemm_cuda_mgpu(char major, char transA, char transB, int M, int N, int K, float alpha, const float *A, int lda,
+                     const float *B, int ldb, float beta, float *C, int ldc, int pr, int pc, int overlap, float *timings_ms);
+
 /* ---- counter-based uniform stream, identical on host and device (so a 32768^2 operand can be generated
  * on the GPU and any sampled row regenerated on the host for verification):
  *   x[i] = fmaf(hi-lo, (splitmix64(seed*0x9E3779B97F4A7C15 + i) >> 40) * 2^-24, lo)

@@ -100,6 +100,17 @@ def lib():
     L.ugemm_cuda_ipc_import.restype = C.c_void_p
     L.ugemm_cuda_ipc_close.argtypes = [C.c_void_p]
     L.ugemm_cuda_ipc_close.restype = C.c_int
+    L.sgemm_cuda_mgpu_init.argtypes = [C.c_int]
+    L.sgemm_cuda_mgpu_init.restype = C.c_int
+    L.sgemm_cuda_mgpu_finish.argtypes = []
+    L.sgemm_cuda_mgpu_finish.restype = None
+    L.sgemm_cuda_mgpu_count.argtypes = []
+    L.sgemm_cuda_mgpu_count.restype = C.c_int
+    L.ugemm_cuda_device_count.argtypes = []
+    L.ugemm_cuda_device_count.restype = C.c_int
+    L.sgemm_cuda_mgpu.argtypes = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.sgemm_cuda_mgpu.restype = C.c_int
     L.ugemm_fill_uniform_host.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_float, C.c_float]
     L.ugemm_fill_uniform_host.restype = None
     L.ugemm_fill_uniform_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_float, C.c_float, C.c_void_p]
@@ -156,6 +167,7 @@ EXPORTED_SYMBOLS = [
     "sgemm_cuda_set_k1_tuning", "sgemm_cuda_set_sm_limit", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
     "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
     "ugemm_cuda_memcpy_async", "ugemm_cuda_ipc_export", "ugemm_cuda_ipc_import", "ugemm_cuda_ipc_close",
+    "sgemm_cuda_mgpu_init", "sgemm_cuda_mgpu_finish", "sgemm_cuda_mgpu_count", "sgemm_cuda_mgpu", "ugemm_cuda_device_count",
     "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
     "ugemm_cuda_probe_tf32", "im2col_cuda", "im2col_cuda_dev", "convolution_cuda", "convolution_cuda_LReLU",
     "convolution_cuda_dev", "convolution_cuda_batched_dev", "sgemm_cuda_set_conv_fusion", "sgemm_cuda_last_conv_fused", "saxpy_cuda", "saxpy_cuda_dev", "sgemv_cuda", "sgemv_cuda_dev",
@@ -361,6 +373,38 @@ def ipc_import(handle):
 
 def ipc_close(ptr):
     lib().ugemm_cuda_ipc_close(C.c_void_p(ptr))
+
+
+def sgemm_cuda_mgpu_init(ngpus):
+    """GPUs 0..ngpus-1 driven by this one process (peer access, per-GPU streams and arenas)."""
+    if lib().sgemm_cuda_mgpu_init(int(ngpus)):
+        check()
+        raise UgemmCudaError("sgemm_cuda_mgpu_init failed")
+
+
+def sgemm_cuda_mgpu_finish():
+    lib().sgemm_cuda_mgpu_finish()
+
+
+def sgemm_cuda_mgpu_count():
+    return int(lib().sgemm_cuda_mgpu_count())
+
+
+def visible_gpus():
+    """Number of CUDA devices this process can see (0 without a driver)."""
+    return int(lib().ugemm_cuda_device_count())
+
+
+def sgemm_cuda_mgpu(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc, pr, pc, overlap=1):
+    """Sharded SGEMM over a pr x pc grid of GPUs from ONE process; A/B/C host arrays or device pointers of any GPU.
+    Returns the 4 timings (ms): host wall, device span, distribution span, product span."""
+    t = (C.c_float * 4)()
+    rc = lib().sgemm_cuda_mgpu(_b(major), _b(ta), _b(tb), M, N, K, alpha, _ptr(A), lda, _ptr(B), ldb, beta, _ptr(Cm), ldc,
+                               int(pr), int(pc), int(overlap), C.cast(t, C.c_void_p))
+    if rc:
+        check()
+        raise UgemmCudaError("sgemm_cuda_mgpu failed")
+    return tuple(t)
 
 
 def sync():

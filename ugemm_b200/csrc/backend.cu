@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 
 using namespace ugemm;
@@ -1061,6 +1062,296 @@ int ugemm_cuda_probe_tf32(const float *A, const float *B, float *D, int ksteps)
 	if (rc && !g_has_err) set_error("probe failed: %s", cudaGetErrorString(cudaGetLastError()));
 	cudaFree(dA); cudaFree(dB); cudaFree(dD);
 	return rc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Single-process multi-GPU SGEMM (SURVEY §8 e): the C host program's way to the sharded path (ugemm_b200/dist.py is the
+// one-process-per-GPU twin used by bench.py).  C is cut into a pr x pc grid of blocks; device d = i*pc + j owns block
+// (i, j) and needs A row-panel i and B column-panel j.  K is not split across devices: one exchange step, no reduction.
+//
+// Distribution is a pipelined relay over NVLink on the copy engines (no SM is taken from the GEMM): K is cut into slabs;
+// slab t of A panel i is pulled by device (i, 0) from the caller's buffer and then by (i, 1) from (i, 0), (i, 2) from
+// (i, 1) ...; B panels relay down the grid columns the same way -- so the root's egress is one copy of A and one of B,
+// every device forwards at most its own two panels, and slab t+1 travels while slab t is multiplied (beta = 1 after the
+// first slab).  The local product is run_dev(), i.e. the same rule-based K1/K2 launch as sgemm_cuda_dev.
+// A, B, C may be pinned/pageable host memory or device memory of any GPU (unified addressing; copies use
+// cudaMemcpyDefault).  Blocking, like every host-pointer entry point.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int MG_MAX_DEV = 16, MG_MAX_SLABS = 64;
+struct MgDev {
+	cudaStream_t copy_a = nullptr, copy_b = nullptr, comp = nullptr;
+	cudaEvent_t landed_a[MG_MAX_SLABS] = {nullptr}, landed_b[MG_MAX_SLABS] = {nullptr};
+	cudaEvent_t e_start = nullptr, e_a_done = nullptr, e_b_done = nullptr, e_g0 = nullptr, e_g1 = nullptr, e_end = nullptr;
+	char *arena = nullptr;
+	size_t arena_bytes = 0;
+};
+struct MgState { int n = 0; MgDev d[MG_MAX_DEV]; } mg;
+
+int mg_arena(int dev, size_t bytes)
+{
+	MgDev &D = mg.d[dev];
+	if (bytes <= D.arena_bytes) return 0;
+	if (D.arena) cudaFree(D.arena);
+	D.arena = nullptr; D.arena_bytes = 0;
+	const size_t want = bytes + (bytes >> 4) + (1u << 20);
+	CU_TRY(cudaMalloc(&D.arena, want), "multi-GPU arena cudaMalloc");
+	D.arena_bytes = want;
+	return 0;
+}
+
+// 2-D copy between any two pointers of the unified address space; lines of `cols` floats, pitches in floats
+cudaError_t mg_copy(float *dst, long long dld, const float *src, long long sld, long long lines, long long cols, cudaStream_t st)
+{
+	if (lines <= 0 || cols <= 0) return cudaSuccess;
+	if (dld == cols && sld == cols) return cudaMemcpyAsync(dst, src, (size_t)lines * cols * 4, cudaMemcpyDefault, st);
+	return cudaMemcpy2DAsync(dst, (size_t)dld * 4, src, (size_t)sld * 4, (size_t)cols * 4, (size_t)lines, cudaMemcpyDefault, st);
+}
+
+} // namespace
+
+int sgemm_cuda_mgpu_init(int ngpus)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (mg.n) return ngpus == mg.n ? 0 : (set_error("sgemm_cuda_mgpu_init: already initialised with %d GPUs", mg.n), 1);
+	if (ensure_init()) return 1;
+	if (g.device != 0) { set_error("sgemm_cuda_mgpu_init: the backend must be initialised on device 0 (it is on %d)", g.device); return 1; }
+	int count = 0;
+	CU_TRY(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
+	if (ngpus < 1 || ngpus > count || ngpus > MG_MAX_DEV) { set_error("sgemm_cuda_mgpu_init: %d GPUs requested, %d visible (max %d)", ngpus, count, MG_MAX_DEV); return 1; }
+	for (int d = 0; d < ngpus; d++) {
+		cudaDeviceProp prop;
+		CU_TRY(cudaGetDeviceProperties(&prop, d), "cudaGetDeviceProperties");
+		if (prop.major != 10) { set_error("device %d (%s) is sm_%d%d; this backend is built for sm_100a only", d, prop.name, prop.major, prop.minor); return 1; }
+		CU_TRY(cudaSetDevice(d), "cudaSetDevice");
+		MgDev &D = mg.d[d];
+		CU_TRY(cudaStreamCreateWithFlags(&D.copy_a, cudaStreamNonBlocking), "cudaStreamCreate");
+		CU_TRY(cudaStreamCreateWithFlags(&D.copy_b, cudaStreamNonBlocking), "cudaStreamCreate");
+		CU_TRY(cudaStreamCreateWithFlags(&D.comp, cudaStreamNonBlocking), "cudaStreamCreate");
+		for (int t = 0; t < MG_MAX_SLABS; t++) {
+			CU_TRY(cudaEventCreateWithFlags(&D.landed_a[t], cudaEventDisableTiming), "cudaEventCreate");
+			CU_TRY(cudaEventCreateWithFlags(&D.landed_b[t], cudaEventDisableTiming), "cudaEventCreate");
+		}
+		cudaEvent_t *timed[] = {&D.e_start, &D.e_a_done, &D.e_b_done, &D.e_g0, &D.e_g1, &D.e_end};
+		for (cudaEvent_t *e : timed) CU_TRY(cudaEventCreate(e), "cudaEventCreate");
+		for (int q = 0; q < ngpus; q++) {
+			if (q == d) continue;
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, d, q);
+			if (!can) { set_error("sgemm_cuda_mgpu_init: device %d cannot access device %d (no NVLink/PCIe peer path)", d, q); cudaSetDevice(g.device); return 1; }
+			cudaError_t e = cudaDeviceEnablePeerAccess(q, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error("cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", d, q, cudaGetErrorString(e)); cudaSetDevice(g.device); return 1; }
+			cudaGetLastError();
+		}
+		cudaMemPool_t pool;   // the repack path's stream-ordered scratch: keep it cached, like on device 0
+		if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) { unsigned long long keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+		cudaGetLastError();
+	}
+	CU_TRY(cudaSetDevice(g.device), "cudaSetDevice");
+	mg.n = ngpus;
+	return 0;
+}
+
+void sgemm_cuda_mgpu_finish(void)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	for (int d = 0; d < mg.n; d++) {
+		MgDev &D = mg.d[d];
+		cudaSetDevice(d);
+		cudaDeviceSynchronize();
+		if (D.arena) cudaFree(D.arena);
+		cudaStreamDestroy(D.copy_a); cudaStreamDestroy(D.copy_b); cudaStreamDestroy(D.comp);
+		for (int t = 0; t < MG_MAX_SLABS; t++) { cudaEventDestroy(D.landed_a[t]); cudaEventDestroy(D.landed_b[t]); }
+		cudaEventDestroy(D.e_start); cudaEventDestroy(D.e_a_done); cudaEventDestroy(D.e_b_done);
+		cudaEventDestroy(D.e_g0); cudaEventDestroy(D.e_g1); cudaEventDestroy(D.e_end);
+		D = MgDev();
+	}
+	if (mg.n) cudaSetDevice(g.device);
+	mg.n = 0;
+}
+
+int sgemm_cuda_mgpu_count(void) { return mg.n; }
+
+int ugemm_cuda_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda,
+                    const float *B, int ldb, float beta, float *C, int ldc, int pr, int pc, int overlap, float *timings_ms)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (timings_ms) for (int i = 0; i < 4; i++) timings_ms[i] = 0.f;
+	if (!mg.n) { set_error("sgemm_cuda_mgpu: call sgemm_cuda_mgpu_init first"); return 1; }
+	if (pr < 1 || pc < 1 || (long long)pr * pc > mg.n) { set_error("sgemm_cuda_mgpu: grid %d x %d needs %lld GPUs, %d initialised", pr, pc, (long long)pr * pc, mg.n); return 1; }
+	Problem p;
+	if (normalise(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, &p)) return 1;
+	if (major == 'C' || major == 'c') { int t = pr; pr = pc; pc = t; }   // the grid follows the row-major view of C
+	if (p.M == 0 || p.N == 0) return 0;
+	const bool scale_only = p.alpha == 0.f || p.K == 0;
+	if (scale_only && p.beta == 1.f) return 0;
+
+	// block sizes (multiples of 4 so local leading dimensions stay TMA-eligible), K slabs (multiples of 32)
+	const int mb = ((p.M + pr - 1) / pr + 3) / 4 * 4, nb = ((p.N + pc - 1) / pc + 3) / 4 * 4;
+	int L = 1, kw = p.K;
+	if (!scale_only && ((overlap && pr * pc > 1) || overlap > 1)) {   // overlap > 1 forces the slab pipeline on a 1 x 1 grid too (tests)
+		L = (p.K + 4095) / 4096;
+		if (L > MG_MAX_SLABS) L = MG_MAX_SLABS;
+		kw = ((p.K + L - 1) / L + 31) / 32 * 32;
+		L = (p.K + kw - 1) / kw;
+	}
+	if (scale_only) L = 0;
+
+	struct Loc { int mi, nj; float *A, *B, *C; long long lda, ldb, ldc; bool on; };
+	Loc loc[MG_MAX_DEV];
+	const int nd = pr * pc;
+	int rc = 0;
+	for (int d = 0; d < nd && !rc; d++) {
+		const int i = d / pc, j = d % pc;
+		Loc &l = loc[d];
+		l.mi = p.M - i * mb < mb ? p.M - i * mb : mb;
+		l.nj = p.N - j * nb < nb ? p.N - j * nb : nb;
+		l.on = l.mi > 0 && l.nj > 0;
+		if (!l.on) continue;
+		// local panels keep the caller's orientation: K-major = lines of K floats, MN-major = K lines of mi (nj) floats
+		l.lda = p.a_kmajor ? (p.K + 3) / 4 * 4 : mb;
+		l.ldb = p.b_kmajor ? (p.K + 3) / 4 * 4 : nb;
+		l.ldc = nb;
+		const size_t a_bytes = align_up_sz((size_t)(p.a_kmajor ? l.mi : p.K) * l.lda * 4, 256);
+		const size_t b_bytes = align_up_sz((size_t)(p.b_kmajor ? l.nj : p.K) * l.ldb * 4, 256);
+		const size_t c_bytes = align_up_sz((size_t)l.mi * l.ldc * 4, 256);
+		if (cudaSetDevice(d) != cudaSuccess || mg_arena(d, a_bytes + b_bytes + c_bytes)) { rc = 1; break; }
+		l.A = reinterpret_cast<float *>(mg.d[d].arena);
+		l.B = reinterpret_cast<float *>(mg.d[d].arena + a_bytes);
+		l.C = reinterpret_cast<float *>(mg.d[d].arena + a_bytes + b_bytes);
+	}
+	cudaError_t e = cudaSuccess;
+	auto ok = [&]() { return rc == 0 && e == cudaSuccess; };
+	timespec ts0, ts1;
+	clock_gettime(CLOCK_MONOTONIC, &ts0);
+
+	// start marks + C blocks in (only when they are read)
+	for (int d = 0; d < nd && ok(); d++) {
+		if (!loc[d].on) continue;
+		const int i = d / pc, j = d % pc;
+		MgDev &D = mg.d[d];
+		e = cudaSetDevice(d);
+		if (e == cudaSuccess) e = cudaEventRecord(D.e_start, D.comp);
+		if (e == cudaSuccess && p.beta != 0.f)
+			e = mg_copy(loc[d].C, loc[d].ldc, p.C + (long long)i * mb * p.ldc + (long long)j * nb, p.ldc, loc[d].mi, loc[d].nj, D.comp);
+	}
+	// panel relay, issued slab-major so that every device sees slab 0 first
+	for (int t = 0; t < L && ok(); t++) {
+		const int k0 = t * kw, kt = p.K - k0 < kw ? p.K - k0 : kw;
+		for (int d = 0; d < nd && ok(); d++) {
+			if (!loc[d].on) continue;
+			const int i = d / pc, j = d % pc;
+			MgDev &D = mg.d[d];
+			const Loc &l = loc[d];
+			e = cudaSetDevice(d);
+			if (e != cudaSuccess) break;
+			{   // A panel i, slab t: from the caller's buffer (j == 0) or from the left neighbour's copy
+				const long long lines = p.a_kmajor ? l.mi : kt, cols = p.a_kmajor ? kt : l.mi;
+				float *dst = l.A + (p.a_kmajor ? (long long)k0 : (long long)k0 * l.lda);
+				if (j == 0) {
+					const float *src = p.A + (p.a_kmajor ? (long long)i * mb * p.lda + k0 : (long long)k0 * p.lda + (long long)i * mb);
+					e = mg_copy(dst, l.lda, src, p.lda, lines, cols, D.copy_a);
+				} else {
+					const Loc &s = loc[d - 1];
+					e = cudaStreamWaitEvent(D.copy_a, mg.d[d - 1].landed_a[t], 0);
+					if (e == cudaSuccess) e = mg_copy(dst, l.lda, s.A + (p.a_kmajor ? (long long)k0 : (long long)k0 * s.lda), s.lda, lines, cols, D.copy_a);
+				}
+				if (e == cudaSuccess) e = cudaEventRecord(D.landed_a[t], D.copy_a);
+				if (e == cudaSuccess && t == L - 1) e = cudaEventRecord(D.e_a_done, D.copy_a);
+			}
+			if (e != cudaSuccess) break;
+			{   // B panel j, slab t: from the caller's buffer (i == 0) or from the upper neighbour's copy
+				const long long lines = p.b_kmajor ? l.nj : kt, cols = p.b_kmajor ? kt : l.nj;
+				float *dst = l.B + (p.b_kmajor ? (long long)k0 : (long long)k0 * l.ldb);
+				if (i == 0) {
+					const float *src = p.B + (p.b_kmajor ? (long long)j * nb * p.ldb + k0 : (long long)k0 * p.ldb + (long long)j * nb);
+					e = mg_copy(dst, l.ldb, src, p.ldb, lines, cols, D.copy_b);
+				} else {
+					const Loc &s = loc[d - pc];
+					e = cudaStreamWaitEvent(D.copy_b, mg.d[d - pc].landed_b[t], 0);
+					if (e == cudaSuccess) e = mg_copy(dst, l.ldb, s.B + (p.b_kmajor ? (long long)k0 : (long long)k0 * s.ldb), s.ldb, lines, cols, D.copy_b);
+				}
+				if (e == cudaSuccess) e = cudaEventRecord(D.landed_b[t], D.copy_b);
+				if (e == cudaSuccess && t == L - 1) e = cudaEventRecord(D.e_b_done, D.copy_b);
+			}
+		}
+	}
+	// local products: slab t starts when ITS two copies have landed
+	for (int d = 0; d < nd && ok(); d++) {
+		if (!loc[d].on) continue;
+		MgDev &D = mg.d[d];
+		const Loc &l = loc[d];
+		e = cudaSetDevice(d);
+		if (e != cudaSuccess) break;
+		Problem q = p;
+		q.M = l.mi; q.N = l.nj; q.lda = l.lda; q.ldb = l.ldb; q.C = l.C; q.ldc = l.ldc;
+		if (scale_only) {
+			e = cudaEventRecord(D.e_g0, D.comp);
+			q.A = l.A; q.B = l.B;
+			if (e == cudaSuccess && run_dev(UGEMM_MODE_AUTO, D.comp, q)) rc = 1;
+		}
+		for (int t = 0; t < L && ok(); t++) {
+			const int k0 = t * kw, kt = p.K - k0 < kw ? p.K - k0 : kw;
+			e = cudaStreamWaitEvent(D.comp, D.landed_a[t], 0);
+			if (e == cudaSuccess) e = cudaStreamWaitEvent(D.comp, D.landed_b[t], 0);
+			if (e == cudaSuccess && t == 0) e = cudaEventRecord(D.e_g0, D.comp);
+			if (e != cudaSuccess) break;
+			q.K = kt;
+			q.A = l.A + (p.a_kmajor ? (long long)k0 : (long long)k0 * l.lda);
+			q.B = l.B + (p.b_kmajor ? (long long)k0 : (long long)k0 * l.ldb);
+			q.beta = t == 0 ? p.beta : 1.f;
+			if (run_dev(UGEMM_MODE_AUTO, D.comp, q)) rc = 1;
+		}
+		if (ok()) e = cudaEventRecord(D.e_g1, D.comp);
+		// the finished block goes back into the caller's C: only its mi x nj region, ld padding is never written
+		const int i = d / pc, j = d % pc;
+		if (ok()) e = mg_copy(p.C + (long long)i * mb * p.ldc + (long long)j * nb, p.ldc, l.C, l.ldc, l.mi, l.nj, D.comp);
+		if (ok()) e = cudaEventRecord(D.e_end, D.comp);
+	}
+	// drain every device (also after an error, so nothing is left in flight on the arenas)
+	float t_span = 0.f, t_dist = 0.f, t_gemm = 0.f;
+	for (int d = 0; d < nd; d++) {
+		if (!loc[d].on) continue;
+		MgDev &D = mg.d[d];
+		cudaSetDevice(d);
+		cudaError_t es = cudaStreamSynchronize(D.copy_a);
+		cudaError_t e2 = cudaStreamSynchronize(D.copy_b); if (es == cudaSuccess) es = e2;
+		e2 = cudaStreamSynchronize(D.comp); if (es == cudaSuccess) es = e2;
+		if (es != cudaSuccess && e == cudaSuccess) e = es;
+		if (ok()) {
+			float ms = 0.f;
+			if (cudaEventElapsedTime(&ms, D.e_start, D.e_end) == cudaSuccess && ms > t_span) t_span = ms;
+			if (L > 0) {
+				if (cudaEventElapsedTime(&ms, D.e_start, D.e_a_done) == cudaSuccess && ms > t_dist) t_dist = ms;
+				if (cudaEventElapsedTime(&ms, D.e_start, D.e_b_done) == cudaSuccess && ms > t_dist) t_dist = ms;
+			}
+			if (cudaEventElapsedTime(&ms, D.e_g0, D.e_g1) == cudaSuccess && ms > t_gemm) t_gemm = ms;
+			cudaGetLastError();
+		}
+	}
+	clock_gettime(CLOCK_MONOTONIC, &ts1);
+	cudaSetDevice(g.device);
+	if (e != cudaSuccess && !g_has_err) {
+		const unsigned *dg = k1_diag_host();
+		if (dg && dg[0]) set_error("sgemm_cuda_mgpu failed: %s (K1 watchdog code %u, block %u, thread %u)", cudaGetErrorString(e), dg[0], dg[1], dg[2]);
+		else set_error("sgemm_cuda_mgpu failed: %s", cudaGetErrorString(e));
+	}
+	if (!ok()) return 1;
+	if (timings_ms) {
+		timings_ms[0] = (float)((ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);   // host wall clock, issue included
+		timings_ms[1] = t_span;    // max over devices: start mark -> C block written back
+		timings_ms[2] = t_dist;    // max over devices: start mark -> last panel slab landed
+		timings_ms[3] = t_gemm;    // max over devices: first product start -> last product end (overlap=0: compute only)
+	}
+	return 0;
 }
 
 } // extern "C"

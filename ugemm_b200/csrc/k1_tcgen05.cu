@@ -776,7 +776,7 @@ unsigned *diag_dev()
 {
 	static std::once_flag once;
 	std::call_once(once, [] {
-		if (cudaHostAlloc(&g_diag_host, 64, cudaHostAllocMapped) == cudaSuccess) {
+		if (cudaHostAlloc(&g_diag_host, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
 			for (int i = 0; i < 16; i++) g_diag_host[i] = 0;
 			if (cudaHostGetDevicePointer(&g_diag_dev, g_diag_host, 0) != cudaSuccess) g_diag_dev = nullptr;
 		}
@@ -794,25 +794,33 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Para
 	P.split = t.split;
 	P.flags = t.flags;
 	P.diag = diag_dev();
+	// Device-resident launch state is kept PER DEVICE (the single-process multi-GPU driver, sgemm_cuda_mgpu, launches this
+	// kernel on every GPU of the box from one host thread): scheduler counters, profiling buffer, function attributes.
+	constexpr int MAX_DEV = 32;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return cudaErrorInvalidDevice;
 	// dynamic-scheduler counters: a small pool so launches on different streams do not share a slot
-	static int *sched_pool = nullptr;
+	static int *sched_pools[MAX_DEV] = {nullptr};
 	static unsigned sched_next = 0;
 	constexpr unsigned SCHED_POOL = 64;
-	if (!sched_pool) {
-		if (cudaMalloc(&sched_pool, SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return cudaErrorMemoryAllocation;
-		cudaMemset(sched_pool, 0, SCHED_POOL * 2 * sizeof(int));
+	if (!sched_pools[dev]) {
+		if (cudaMalloc(&sched_pools[dev], SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return cudaErrorMemoryAllocation;
+		cudaMemset(sched_pools[dev], 0, SCHED_POOL * 2 * sizeof(int));
+		cudaDeviceSynchronize();
 	}
-	P.sched = sched_pool + 2 * (sched_next++ % SCHED_POOL);
+	P.sched = sched_pools[dev] + 2 * (sched_next++ % SCHED_POOL);
 	P.prof = nullptr;
-	static long long *prof_dev = nullptr;
+	static long long *prof_devs[MAX_DEV] = {nullptr};
 	const bool prof = !CONV && !NARROW && (t.flags & 32);
 	if (prof) {
-		if (!prof_dev) cudaMalloc(&prof_dev, 64 * sizeof(long long));
-		cudaMemsetAsync(prof_dev, 0, 64 * sizeof(long long), stream);
-		P.prof = prof_dev;
+		if (!prof_devs[dev]) cudaMalloc(&prof_devs[dev], 64 * sizeof(long long));
+		cudaMemsetAsync(prof_devs[dev], 0, 64 * sizeof(long long), stream);
+		P.prof = prof_devs[dev];
 	}
+	long long *const prof_dev = prof_devs[dev];
 
-	static bool attr_set = false;      // one flag per <CG, CONV, NARROW> instantiation of this function
+	static bool attr_sets[MAX_DEV] = {false};      // per device, one array per <CG, CONV, NARROW> instantiation of this function
+	bool &attr_set = attr_sets[dev];
 	if (!attr_set) {
 		cudaError_t e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, false, CONV, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 		if (e != cudaSuccess) return e;
