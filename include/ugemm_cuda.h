@@ -146,9 +146,12 @@ int   ugemm_cuda_ipc_close(void *mapped);
  *   sgemm_cuda_mgpu(...):    A, B, C are host pointers (pinned for speed) or device pointers of ANY GPU (unified
  *                            addressing); same argument checks, quick returns and alpha/beta/ld semantics as sgemm_cuda;
  *                            blocking; C's ld padding is never written; pr * pc <= n.  Returns 0 / 1 (sticky error).
- *   timings_ms (optional, 4 floats): [0] host wall clock of the call, [1] max over GPUs of start -> C block written back,
+ *                            A block whose source already lives on the GPU that needs it is used in place (no copy): with
+ *                            the operands on GPU 0, GPU 0 multiplies at once and only serves its peers.
+ *   timings_ms (optional, 5 floats): [0] host wall clock of the call, [1] max over GPUs of start -> C block written back,
  *                            [2] max over GPUs of start -> last panel slab landed, [3] max over GPUs of first product
- *                            start -> last product end. */
+ *                            start -> last product end, [4] max over GPUs of start -> last product end (the metric of
+ *                            BASELINE config 5: distribution included, gather of C excluded). */
 int  sgemm_cuda_mgpu_init(int ngpus);
 void sgemm_cuda_mgpu_finish(void);
 int  sgemm_cuda_mgpu_count(void);     /* GPUs initialised by sgemm_cuda_mgpu_init, 0 if none */

@@ -397,8 +397,8 @@ def visible_gpus():
 
 def sgemm_cuda_mgpu(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc, pr, pc, overlap=1):
     """Sharded SGEMM over a pr x pc grid of GPUs from ONE process; A/B/C host arrays or device pointers of any GPU.
-    Returns the 4 timings (ms): host wall, device span, distribution span, product span."""
-    t = (C.c_float * 4)()
+    Returns the 5 timings (ms): host wall, device span, distribution span, product span, span without the C write-back."""
+    t = (C.c_float * 5)()
     rc = lib().sgemm_cuda_mgpu(_b(major), _b(ta), _b(tb), M, N, K, alpha, _ptr(A), lda, _ptr(B), ldb, beta, _ptr(Cm), ldc,
                                int(pr), int(pc), int(overlap), C.cast(t, C.c_void_p))
     if rc:

@@ -1184,7 +1184,7 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
                     const float *B, int ldb, float beta, float *C, int ldc, int pr, int pc, int overlap, float *timings_ms)
 {
 	std::lock_guard<std::mutex> lk(g_mu);
-	if (timings_ms) for (int i = 0; i < 4; i++) timings_ms[i] = 0.f;
+	if (timings_ms) for (int i = 0; i < 5; i++) timings_ms[i] = 0.f;
 	if (!mg.n) { set_error("sgemm_cuda_mgpu: call sgemm_cuda_mgpu_init first"); return 1; }
 	if (pr < 1 || pc < 1 || (long long)pr * pc > mg.n) { set_error("sgemm_cuda_mgpu: grid %d x %d needs %lld GPUs, %d initialised", pr, pc, (long long)pr * pc, mg.n); return 1; }
 	Problem p;
@@ -1198,14 +1198,24 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
 	const int mb = ((p.M + pr - 1) / pr + 3) / 4 * 4, nb = ((p.N + pc - 1) / pc + 3) / 4 * 4;
 	int L = 1, kw = p.K;
 	if (!scale_only && ((overlap && pr * pc > 1) || overlap > 1)) {   // overlap > 1 forces the slab pipeline on a 1 x 1 grid too (tests)
-		L = (p.K + 4095) / 4096;
+		// 8192-wide slabs: every slab after the first is a beta = 1 pass over the C block (+2..6 % per pass at 4096), while the
+		// exposed part of the distribution is only the first slab's transfer
+		L = (p.K + 8191) / 8192;
 		if (L > MG_MAX_SLABS) L = MG_MAX_SLABS;
 		kw = ((p.K + L - 1) / L + 31) / 32 * 32;
 		L = (p.K + kw - 1) / kw;
 	}
 	if (scale_only) L = 0;
 
-	struct Loc { int mi, nj; float *A, *B, *C; long long lda, ldb, ldc; bool on; };
+	// which device (if any) holds a caller pointer: a block whose source already lives on the device that needs it is used
+	// in place (no local copy) -- with the operands on GPU 0, GPU 0 starts multiplying at once and only serves its peers
+	auto home_of = [](const void *ptr) {
+		cudaPointerAttributes at;
+		if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return -1; }
+		return at.type == cudaMemoryTypeDevice ? at.device : -1;
+	};
+	const int home_a = scale_only ? -1 : home_of(p.A), home_b = scale_only ? -1 : home_of(p.B), home_c = home_of(p.C);
+	struct Loc { int mi, nj; float *A, *B, *C; long long lda, ldb, ldc; bool on, a_inplace, b_inplace, c_inplace; };
 	Loc loc[MG_MAX_DEV];
 	const int nd = pr * pc;
 	int rc = 0;
@@ -1220,13 +1230,19 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
 		l.lda = p.a_kmajor ? (p.K + 3) / 4 * 4 : mb;
 		l.ldb = p.b_kmajor ? (p.K + 3) / 4 * 4 : nb;
 		l.ldc = nb;
-		const size_t a_bytes = align_up_sz((size_t)(p.a_kmajor ? l.mi : p.K) * l.lda * 4, 256);
-		const size_t b_bytes = align_up_sz((size_t)(p.b_kmajor ? l.nj : p.K) * l.ldb * 4, 256);
-		const size_t c_bytes = align_up_sz((size_t)l.mi * l.ldc * 4, 256);
-		if (cudaSetDevice(d) != cudaSuccess || mg_arena(d, a_bytes + b_bytes + c_bytes)) { rc = 1; break; }
+		l.a_inplace = j == 0 && home_a == d;
+		l.b_inplace = i == 0 && home_b == d;
+		l.c_inplace = home_c == d;
+		const size_t a_bytes = l.a_inplace ? 0 : align_up_sz((size_t)(p.a_kmajor ? l.mi : p.K) * l.lda * 4, 256);
+		const size_t b_bytes = l.b_inplace ? 0 : align_up_sz((size_t)(p.b_kmajor ? l.nj : p.K) * l.ldb * 4, 256);
+		const size_t c_bytes = l.c_inplace ? 0 : align_up_sz((size_t)l.mi * l.ldc * 4, 256);
+		if (cudaSetDevice(d) != cudaSuccess || mg_arena(d, a_bytes + b_bytes + c_bytes + 256)) { rc = 1; break; }
 		l.A = reinterpret_cast<float *>(mg.d[d].arena);
 		l.B = reinterpret_cast<float *>(mg.d[d].arena + a_bytes);
 		l.C = reinterpret_cast<float *>(mg.d[d].arena + a_bytes + b_bytes);
+		if (l.a_inplace) { l.A = const_cast<float *>(p.A) + (p.a_kmajor ? (long long)i * mb * p.lda : (long long)i * mb); l.lda = p.lda; }
+		if (l.b_inplace) { l.B = const_cast<float *>(p.B) + (p.b_kmajor ? (long long)j * nb * p.ldb : (long long)j * nb); l.ldb = p.ldb; }
+		if (l.c_inplace) { l.C = p.C + (long long)i * mb * p.ldc + (long long)j * nb; l.ldc = p.ldc; }
 	}
 	cudaError_t e = cudaSuccess;
 	auto ok = [&]() { return rc == 0 && e == cudaSuccess; };
@@ -1240,7 +1256,7 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
 		MgDev &D = mg.d[d];
 		e = cudaSetDevice(d);
 		if (e == cudaSuccess) e = cudaEventRecord(D.e_start, D.comp);
-		if (e == cudaSuccess && p.beta != 0.f)
+		if (e == cudaSuccess && p.beta != 0.f && !loc[d].c_inplace)
 			e = mg_copy(loc[d].C, loc[d].ldc, p.C + (long long)i * mb * p.ldc + (long long)j * nb, p.ldc, loc[d].mi, loc[d].nj, D.comp);
 	}
 	// panel relay, issued slab-major so that every device sees slab 0 first
@@ -1256,7 +1272,9 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
 			{   // A panel i, slab t: from the caller's buffer (j == 0) or from the left neighbour's copy
 				const long long lines = p.a_kmajor ? l.mi : kt, cols = p.a_kmajor ? kt : l.mi;
 				float *dst = l.A + (p.a_kmajor ? (long long)k0 : (long long)k0 * l.lda);
-				if (j == 0) {
+				if (l.a_inplace) {
+					// already here: nothing to move, the slab has "landed"
+				} else if (j == 0) {
 					const float *src = p.A + (p.a_kmajor ? (long long)i * mb * p.lda + k0 : (long long)k0 * p.lda + (long long)i * mb);
 					e = mg_copy(dst, l.lda, src, p.lda, lines, cols, D.copy_a);
 				} else {
@@ -1271,7 +1289,8 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
 			{   // B panel j, slab t: from the caller's buffer (i == 0) or from the upper neighbour's copy
 				const long long lines = p.b_kmajor ? l.nj : kt, cols = p.b_kmajor ? kt : l.nj;
 				float *dst = l.B + (p.b_kmajor ? (long long)k0 : (long long)k0 * l.ldb);
-				if (i == 0) {
+				if (l.b_inplace) {
+				} else if (i == 0) {
 					const float *src = p.B + (p.b_kmajor ? (long long)j * nb * p.ldb + k0 : (long long)k0 * p.ldb + (long long)j * nb);
 					e = mg_copy(dst, l.ldb, src, p.ldb, lines, cols, D.copy_b);
 				} else {
@@ -1313,11 +1332,11 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
 		if (ok()) e = cudaEventRecord(D.e_g1, D.comp);
 		// the finished block goes back into the caller's C: only its mi x nj region, ld padding is never written
 		const int i = d / pc, j = d % pc;
-		if (ok()) e = mg_copy(p.C + (long long)i * mb * p.ldc + (long long)j * nb, p.ldc, l.C, l.ldc, l.mi, l.nj, D.comp);
+		if (ok() && !l.c_inplace) e = mg_copy(p.C + (long long)i * mb * p.ldc + (long long)j * nb, p.ldc, l.C, l.ldc, l.mi, l.nj, D.comp);
 		if (ok()) e = cudaEventRecord(D.e_end, D.comp);
 	}
 	// drain every device (also after an error, so nothing is left in flight on the arenas)
-	float t_span = 0.f, t_dist = 0.f, t_gemm = 0.f;
+	float t_span = 0.f, t_dist = 0.f, t_gemm = 0.f, t_done = 0.f;
 	for (int d = 0; d < nd; d++) {
 		if (!loc[d].on) continue;
 		MgDev &D = mg.d[d];
@@ -1334,6 +1353,7 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
 				if (cudaEventElapsedTime(&ms, D.e_start, D.e_b_done) == cudaSuccess && ms > t_dist) t_dist = ms;
 			}
 			if (cudaEventElapsedTime(&ms, D.e_g0, D.e_g1) == cudaSuccess && ms > t_gemm) t_gemm = ms;
+			if (cudaEventElapsedTime(&ms, D.e_start, D.e_g1) == cudaSuccess && ms > t_done) t_done = ms;
 			cudaGetLastError();
 		}
 	}
@@ -1350,6 +1370,7 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
 		timings_ms[1] = t_span;    // max over devices: start mark -> C block written back
 		timings_ms[2] = t_dist;    // max over devices: start mark -> last panel slab landed
 		timings_ms[3] = t_gemm;    // max over devices: first product start -> last product end (overlap=0: compute only)
+		timings_ms[4] = t_done;    // max over devices: start mark -> last product end (distribution in, C write-back out)
 	}
 	return 0;
 }

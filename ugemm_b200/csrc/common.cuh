@@ -50,7 +50,6 @@ struct ConvProblem {
 // 2 transform skips its stores, 4 transform skips loads and stores, 8 only big*big is issued, 16 epilogue skips stores,
 // 32 per-role cycle counters to stderr, 64 MMA free-run (no TMA / transform / stage barriers: raw tensor-pipe ceiling).
 // bits 7-10: L2 eviction hints of the TMA loads (experiments); bit 11 (2048): stream-K tail off (A/B runs, SM-limited launches).
-// bit 12 (4096): narrow-N instantiation off (N < 128 runs the full 128-column tile, A/B runs).
 struct K1Tuning { int kc_blocks; int split; int cta_group; int flags; };
 
 // K2: register-blocked FFMA kernel (k2_simt.cu)

@@ -73,10 +73,6 @@ struct K1Params {
 	// implicit-GEMM convolution (CONV instantiation): padded output width (multiple of 32), output width / height,
 	// kernel size, padding, 32-channel blocks per kernel position, pixels per output plane
 	int cv_wp, cv_wo, cv_ho, cv_k, cv_pad, cv_cblocks, cv_npix, cv_stride;
-	// narrow-N instantiation (NARROW; one 1-CTA tile column, N < 128): UMMA N and the rows of op(B) that are loaded and
-	// transformed (N rounded up to 16, or to 32 for an MN-major B whose swizzle atom is 32 wide); nb_bytes = n_eff * 128 bytes
-	// of each B stage are live, xf_chunks = 2 KiB chunks of the raw stage (A's 8 + B's n_eff/16) the transform warps share
-	int n_eff, nb_bytes, xf_chunks;
 	unsigned *diag;
 	int *sched;        // [0] next tile index (atomic), [1] clusters finished; self-resetting
 	long long *prof;   // flags & 32: per-role cycle counters of the first 4 CTAs (16 slots each), debug only
@@ -184,7 +180,7 @@ __device__ __forceinline__ float tf32_rna(float x)
 // convolution cannot be taken along x of the planar image [measured: illegal instruction]; channels-last puts them on outer
 // dimensions.)  Padding pixels and channels beyond ich are TMA out-of-bounds zero fill; columns jo >= wo are computed and
 // never stored.
-template <int CG, bool PROF, bool CONV, bool NARROW>
+template <int CG, bool PROF, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const K1Params P)
 {
@@ -278,7 +274,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					const long long tw = tick<PROF>();
 					mbar_wait(empty_bar(s), ph ^ 1u, P.diag, 1);
 					w_empty += tick<PROF>() - tw;
-					mbar_arrive_expect_tx(full_bar(s), NARROW ? (uint32_t)(OPER_BYTES + P.nb_bytes) : (uint32_t)RAW_BYTES);
+					mbar_arrive_expect_tx(full_bar(s), RAW_BYTES);
 					const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + OPER_BYTES;
 					const int k0 = kb * BK;
 					if (CONV) {
@@ -293,18 +289,16 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					if (P.a_kmajor) tma_load_3d_hint(sA, &tmA, full_bar(s), k0, a_row0, inst, hintA);
 					else
 						for (int j = 0; j < ROWS / 32; j++) tma_load_3d_hint(sA + j * 4096, &tmA, full_bar(s), a_row0 + 32 * j, k0, inst, hintA);
-					if (P.b_kmajor) tma_load_3d_hint(sB, &tmB, full_bar(s), k0, b_row0, inst, hintB);   // NARROW: the map's box has n_eff rows
-					else {
-						const int nbox = NARROW ? P.n_eff / 32 : ROWS / 32;
-						for (int j = 0; j < nbox; j++) tma_load_3d_hint(sB + j * 4096, &tmB, full_bar(s), b_row0 + 32 * j, k0, inst, hintB);
-					}
+					if (P.b_kmajor) tma_load_3d_hint(sB, &tmB, full_bar(s), k0, b_row0, inst, hintB);
+					else
+						for (int j = 0; j < ROWS / 32; j++) tma_load_3d_hint(sB + j * 4096, &tmB, full_bar(s), b_row0 + 32 * j, k0, inst, hintB);
 				}
 				}
 			}
 			if (prof) { prof[0] = w_empty; prof[1] = tick<PROF>() - t_begin; }
 		} else if (warp == 1 && lane == 0 && cta_rank == 0) {
 			// ================= MMA issuer (leader CTA) =================
-			const uint32_t idesc = idesc_tf32(UMMA_M, NARROW ? P.n_eff : BN, P.a_kmajor ? 0 : 1, P.b_kmajor ? 0 : 1);
+			const uint32_t idesc = idesc_tf32(UMMA_M, BN, P.a_kmajor ? 0 : 1, P.b_kmajor ? 0 : 1);
 			// K-major SW128: LBO(enc)=1, SBO=1024 B, k-step (8 fp32) = +32 B inside the swizzle line.
 			// MN-major SW128/32B-atom: LBO=4096 B between 32-wide mn groups, SBO=512 B between 4-row
 			// k groups, k-step (8 rows) = +1024 B.
@@ -424,19 +418,12 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
 				for (int half = (XF_SPLIT_STAGE ? grp : 0); half < (XF_SPLIT_STAGE ? grp + 1 : 2); half++) {
 					if (P.flags & 4) break;
-					// 2 KiB chunks of the raw stage: this group's half -- or, NARROW (only n_eff rows of B are live, so the stage is
-					// A's 8 chunks + n_eff/16 of B's), every other chunk so the two groups still split the work evenly
 					float4 v[8];
 #pragma unroll
-					for (int i = 0; i < 8; i++) {
-						const int c = NARROW ? grp + 2 * i : half * 8 + i;
-						if (!NARROW || c < P.xf_chunks) v[i] = lds128(raw + (uint32_t)(t + 128 * c) * 16u);
-					}
+					for (int i = 0; i < 8; i++) v[i] = lds128(raw + (uint32_t)(t + 128 * (half * 8 + i)) * 16u);
 #pragma unroll
 					for (int i = 0; i < 8; i++) {
-						const int c = NARROW ? grp + 2 * i : half * 8 + i;
-						if (NARROW && c >= P.xf_chunks) continue;
-						const uint32_t off = (uint32_t)(t + 128 * c) * 16u;
+						const uint32_t off = (uint32_t)(t + 128 * (half * 8 + i)) * 16u;
 						float4 b, sm;
 						if (P.split == 0) {
 							b.x = tf32_trunc(v[i].x); b.y = tf32_trunc(v[i].y); b.z = tf32_trunc(v[i].z); b.w = tf32_trunc(v[i].w);
@@ -519,7 +506,6 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * (BN / 2));
 #pragma unroll
 				for (int g = 0; g < 2 * NG; g++) {
-					if (NARROW && h * (BN / 2) + g * 16 >= P.n_eff) continue;   // columns the narrow MMA never writes (warp-uniform)
 					float v[16];
 					tmem_ld_32x32b_x16(taddr + g * 16, v);
 #pragma unroll
@@ -751,16 +737,15 @@ EncodeTiledFn encode_fn()
 // K-major operand: `rows` lines of `K` contiguous fp32, pitch ld  -> dims {K, rows, batch}, box {32, 128, 1}, SWIZZLE_128B
 // MN-major operand: `K` lines of `rows` contiguous fp32, pitch ld -> dims {rows, K, batch}, box {32, 32, 1}, SWIZZLE_128B_ATOM_32B
 // The third dimension walks the strided batch (extent 1 for a plain GEMM).
-// box_rows: rows of a K-major box (ROWS; the narrow-N instantiation loads only n_eff rows of op(B))
 bool make_operand_map(CUtensorMap *map, const float *base, long long rows, long long K, long long ld, bool kmajor,
-                      int batch, long long stride, int box_rows = ROWS)
+                      int batch, long long stride)
 {
 	EncodeTiledFn fn = encode_fn();
 	if (!fn) return false;
 	cuuint64_t gdim[3], gstride[2];
 	cuuint32_t box[3], estr[3] = {1, 1, 1};
 	CUtensorMapSwizzle sw;
-	if (kmajor) { gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows; box[0] = BK; box[1] = (cuuint32_t)box_rows; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
+	if (kmajor) { gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows; box[0] = BK; box[1] = ROWS; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
 	else        { gdim[0] = (cuuint64_t)rows; gdim[1] = (cuuint64_t)K; box[0] = 32; box[1] = BK; sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; }
 	gdim[2] = (cuuint64_t)(batch > 0 ? batch : 1);
 	box[2] = 1;
@@ -785,7 +770,7 @@ unsigned *diag_dev()
 }
 
 // common tail of the GEMM and convolution launches: scheduler counters, attributes, cluster launch
-template <int CG, bool CONV, bool NARROW>
+template <int CG, bool CONV>
 cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
 	if (nt > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
@@ -811,7 +796,7 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Para
 	P.sched = sched_pools[dev] + 2 * (sched_next++ % SCHED_POOL);
 	P.prof = nullptr;
 	static long long *prof_devs[MAX_DEV] = {nullptr};
-	const bool prof = !CONV && !NARROW && (t.flags & 32);
+	const bool prof = !CONV && (t.flags & 32);
 	if (prof) {
 		if (!prof_devs[dev]) cudaMalloc(&prof_devs[dev], 64 * sizeof(long long));
 		cudaMemsetAsync(prof_devs[dev], 0, 64 * sizeof(long long), stream);
@@ -819,13 +804,13 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Para
 	}
 	long long *const prof_dev = prof_devs[dev];
 
-	static bool attr_sets[MAX_DEV] = {false};      // per device, one array per <CG, CONV, NARROW> instantiation of this function
+	static bool attr_sets[MAX_DEV] = {false};      // per device, one array per <CG, CONV> instantiation of this function
 	bool &attr_set = attr_sets[dev];
 	if (!attr_set) {
-		cudaError_t e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, false, CONV, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+		cudaError_t e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, false, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 		if (e != cudaSuccess) return e;
-		if (!CONV && !NARROW) {
-			e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+		if (!CONV) {
+			e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 			if (e != cudaSuccess) return e;
 		}
 		attr_set = true;
@@ -841,8 +826,8 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Para
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr; cfg.numAttrs = 1;
-	cudaError_t le = prof ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true, false, false>, tmA, tmB, P)
-	                      : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false, CONV, NARROW>, tmA, tmB, P);
+	cudaError_t le = prof ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true, false>, tmA, tmB, P)
+	                      : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false, CONV>, tmA, tmB, P);
 	if (le == cudaSuccess && prof) {   // debug: per-role cycle breakdown of CTAs 0..3 on stderr
 		long long h[64];
 		if (cudaStreamSynchronize(stream) == cudaSuccess && cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -858,7 +843,7 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Para
 // only partly filled (c3: 192 tiles on 74 pairs = 2.6 rounds, 4096^3: 3.5, anything smaller than the machine: < 1), its
 // tiles are cut along K into equal chunk ranges, one per pair, whose partial sums meet in a workspace (decode_item,
 // k1_tail_fixup_kernel).  Taken when it shortens the last round by at least 15 % and the launch by at least 12 %.
-template <int CG, bool CONV, bool NARROW = false>
+template <int CG, bool CONV>
 cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
 	const int kc_eff = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
@@ -882,7 +867,7 @@ cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, K1P
 			} else { cudaGetLastError(); ws = nullptr; }
 		}
 	}
-	cudaError_t e = launch_kernel<CG, CONV, NARROW>(tmA, tmB, P, items, t, stream, sm_count);
+	cudaError_t e = launch_kernel<CG, CONV>(tmA, tmB, P, items, t, stream, sm_count);
 	if (ws) {
 		if (e == cudaSuccess) {
 			k1_tail_fixup_kernel<CG><<<dim3((unsigned)P.sk_rem, FIXUP_SPLIT), 256, 0, stream>>>(P);
@@ -896,16 +881,10 @@ cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, K1P
 template <int CG>
 cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
-	// narrow N (a single 1-CTA tile column, N < 128): UMMA N, the B boxes and the transform shrink to the columns that exist --
-	// the tall-skinny shapes are bound by shared-memory traffic per k-block, not by the tensor pipe, so multiplying and
-	// transforming zero-filled columns is what costs (flags bit 12 = 4096 turns it off for A/B runs)
-	const int n_eff = p.b_kmajor ? (p.N + 15) / 16 * 16 : (p.N + 31) / 32 * 32;
-	const bool narrow = CG == 1 && n_eff < 128 && !(t.flags & 4096);
 	CUtensorMap tmA, tmB;
 	if (!make_operand_map(&tmA, p.A, p.M, p.K, p.lda, p.a_kmajor, p.batch, p.strideA)) return cudaErrorInvalidValue;
-	if (!make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.b_kmajor, p.batch, p.strideB, narrow ? n_eff : ROWS)) return cudaErrorInvalidValue;
+	if (!make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.b_kmajor, p.batch, p.strideB)) return cudaErrorInvalidValue;
 	K1Params P = {};
-	P.n_eff = n_eff; P.nb_bytes = n_eff * 128; P.xf_chunks = 8 + n_eff / 16;
 	P.M = p.M; P.N = p.N; P.K = p.K; P.alpha = p.alpha; P.beta = p.beta; P.C = p.C; P.ldc = p.ldc;
 	P.bias = p.bias; P.slope = p.slope;
 	P.a_kmajor = p.a_kmajor; P.b_kmajor = p.b_kmajor;
@@ -918,7 +897,6 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	P.num_k_blocks = (p.K + BK - 1) / BK;
 	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0) ? 1 : 0;
 
-	if (CG == 1 && narrow) return launch_with_tail<1, false, true>(tmA, tmB, P, nt, t, stream, sm_count);
 	return launch_with_tail<CG, false>(tmA, tmB, P, nt, t, stream, sm_count);
 }
 
