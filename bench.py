@@ -12,7 +12,8 @@ N > 1  workload c5: 32768^3 sharded as a 2-D grid of C tiles (ugemm_b200/dist.py
        H2D of A and B, kernel, D2H of C inside the timed region), wall clock around blocking calls.
 `roofline`     dominant kernel vs the measured tensor peak: MEASURED_PEAKS.json bf16 dense / 2 (TF32) / 3 (3 MMAs).
 `cpu_baseline` the reference's own CPU SGEMM (oracle/_ref: unmodified sgemm_avx on all host cores over disjoint
-       row slabs) on a bounded row-slab sample of the same workload.  --impl reference prints that arm alone.
+       row slabs) on the whole workload when that fits the time budget, else on a bounded row-slab sample (a small
+       sample flatters the reference: its C slab then stays in cache).  --impl reference prints that arm alone.
 The oracle/ directory is only ever executed here as that CPU baseline, never as the thing measured for `value`.
 """
 import argparse
@@ -96,7 +97,7 @@ class ClockSampler:
 
 
 def cpu_reference_arm(wl, seconds_target, steps=1, warmup=0):
-    """Reference CPU SGEMM on all host cores over a bounded row-slab sample of workload `wl`.
+    """Reference CPU SGEMM on all host cores over workload `wl` (whole, or a bounded row-slab sample of it).
     Returns (tflops, cores, kind, sample_description, ms_per_step)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
@@ -114,15 +115,22 @@ def cpu_reference_arm(wl, seconds_target, steps=1, warmup=0):
         fn = lambda M, A, B, Cm: o.oracle_sgemm_banded(cores, b"R", b"N", b"N", M, N, K, 1.0, A, K, B, N, 0.0, Cm, N)
         what = "oracle port of sgemm_avx's 35-band order"
     B = O.fill_uniform(K * N, 2)
-    # calibrate on a small slab, then size the sample for ~seconds_target of CPU work per step
-    m0 = max(2 * cores, 32)
+    # Size the sample.  sgemm_avx re-reads and re-writes its C slab once per 35-wide K band (sgemm_avx256.h:316-390), so its rate
+    # depends on the slab height per thread: 64 rows per thread stay in the core's L2 (1.0-1.1 TFLOP/s on 16 threads), the
+    # 512 rows per thread of the real 8192-row workload do not (0.45 TFLOP/s).  A small sample therefore FLATTERS the reference;
+    # the whole workload is run whenever it fits the time budget, and only otherwise a bounded slab.
+    m0 = 64 * cores
     A = O.fill_uniform(m0 * K, 1)
     Cm = np.zeros(m0 * N, np.float32)
     fn(m0, A, B, Cm)                       # first call pays thread start-up and page faults
     t = time.perf_counter(); fn(m0, A, B, Cm); dt = max(time.perf_counter() - t, 1e-4)
-    rows = int(min(wl["M"], max(64 * cores, (seconds_target / dt) * m0)))
-    rows -= rows % (2 * cores)
-    rows = max(rows, m0)
+    slow = 2.5                             # allowance for the cache effect above when extrapolating from the small slab
+    if wl["M"] / m0 * dt * slow <= seconds_target:
+        rows = wl["M"]
+    else:
+        rows = int(max(m0, seconds_target / (dt * slow) * m0))
+        rows -= rows % (2 * cores)
+        rows = min(max(rows, m0), wl["M"])
     A = O.fill_uniform(rows * K, 1)
     Cm = np.zeros(rows * N, np.float32)
     for _ in range(warmup):
@@ -132,7 +140,8 @@ def cpu_reference_arm(wl, seconds_target, steps=1, warmup=0):
         fn(rows, A, B, Cm)
     dt = (time.perf_counter() - t) / steps
     tflops = 2.0 * rows * N * K / dt / 1e12
-    sample = f"{what}; rows 0..{rows - 1} of C ({rows}x{N}x{K} of the {wl['M']}x{N}x{K} workload), {cores} threads"
+    part = "the whole workload" if rows == wl["M"] else f"rows 0..{rows - 1} of C"
+    sample = f"{what}; {part} ({rows}x{N}x{K} of the {wl['M']}x{N}x{K} workload, {rows // cores} rows per thread), {cores} threads"
     return tflops, cores, kind, sample, dt * 1e3
 
 
@@ -141,11 +150,12 @@ def run_reference_impl(args, wl_name):
     if rank != 0:
         return
     wl = WORKLOADS[wl_name]
-    tflops, cores, kind, sample, ms = cpu_reference_arm(wl, seconds_target=1.5, steps=max(args.steps, 1), warmup=min(args.warmup, 2))
+    tflops, cores, kind, sample, ms = cpu_reference_arm(wl, seconds_target=min(3.0, max(0.3, 150.0 / (max(args.steps, 1) + min(args.warmup, 2)))),
+                                                       steps=max(args.steps, 1), warmup=min(args.warmup, 2))
     line = {"impl": "reference", "metric": "SGEMM TFLOP/s", "value": tflops, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "note": "reference CPU path on the GPU box's host cores; each step is a bounded row-slab sample"},
+            "config": {"workload": wl["desc"], "note": "reference CPU path on the GPU box's host cores; each step is the whole workload when that fits the time budget, else a bounded row-slab sample (see cpu_baseline.sample)"},
             "cpu_baseline": {"value": tflops, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
