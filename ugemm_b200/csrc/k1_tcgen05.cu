@@ -50,7 +50,9 @@ constexpr int XF_GROUPS = 2;                  // transform warpgroups
 constexpr bool XF_SPLIT_STAGE = true;         // true: both groups share every stage (half each); false: groups alternate k-blocks
 constexpr int BAR_BYTES = 256;
 constexpr int SCHED_SLOTS = 4;               // depth of the dynamic tile-index ring
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024; // + slack for 1024-B alignment
+constexpr int CSTAGE_BYTES = 32 * 32 * 4;    // per epilogue warp: one 32-row x 32-column fp32 box staged for a TMA store
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 8 * CSTAGE_BYTES + 1024; // ring | barrier block (padded to 1 KiB) | C staging | slack for 1024-B alignment
+static_assert(BAR_BYTES <= 1024 && SMEM_BYTES <= 232448, "shared-memory budget of one CTA (227 KiB)");
 constexpr long long WATCHDOG_CYCLES = 6000000000LL;
 
 struct K1Params {
@@ -65,6 +67,7 @@ struct K1Params {
 	int a_kmajor, b_kmajor;
 	int tiles_m, tiles_n, num_tiles;
 	int num_k_blocks, kc_blocks, split, vecC, flags;
+	int tma_store;              // epilogue writes C through 32 x 32 TMA box stores (tmC valid: C 16-byte aligned, ldc % 4 == 0)
 	// stream-K tail (sk_q > 0): work items [0, sk_full) are whole tiles; the remaining sk_rem tiles are cut into chunk ranges of
 	// sk_q promotion chunks (kc_blocks k-blocks each, sk_nch per tile), two items per range (a range may straddle one tile
 	// boundary); their raw partial sums go to sk_ws[slot][tile_m x tile_n] and k1_tail_fixup_kernel adds them up in range order
@@ -182,7 +185,7 @@ __device__ __forceinline__ float tf32_rna(float x)
 // never stored.
 template <int CG, bool PROF, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const K1Params P)
+k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const K1Params P)
 {
 	constexpr int BN = 128 * CG;          // accumulator columns (UMMA N)
 	constexpr int UMMA_M = 128 * CG;
@@ -214,6 +217,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 	if (warp == 0 && lane == 0) {
 		prefetch_tmap(&tmA);
 		prefetch_tmap(&tmB);
+		if (P.tma_store) prefetch_tmap(&tmC);
 		for (int s = 0; s < STAGES; s++) {
 			mbar_init(full_bar(s), 1);
 			mbar_init(xf_bar(s), (XF_SPLIT_STAGE ? 4 * XF_GROUPS : 4) * CG);   // transform warps that publish one stage
@@ -532,7 +536,34 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			}
 			// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
 			const float beta = preload_c ? 0.f : P.beta;   // already folded into acc when preloaded
-			if (row < P.M && !(P.flags & 16)) {
+			if (!CONV && P.tma_store && beta == 0.f && !(P.flags & 16)) {
+				// TMA-store epilogue: each warp stages one 32-row x 32-column box at a time in shared memory (128B-swizzled, so a
+				// thread's eight 16-byte stores of its row are conflict-free) and hands it to the TMA unit, which writes whole
+				// 128-byte lines and clips the box at the matrix edge -- instead of 32 row-strided 16-byte stores per instruction.
+				const float slope = P.slope;
+				const bool post = P.bias != nullptr || slope != 1.f;
+				const float bm = (P.bias && row < P.M) ? __ldg(P.bias + row) : 0.f;
+				auto act = [&](float x) { x += bm; return x > 0.f ? x : x * slope; };
+				const uint32_t cst = bar_base + 1024u + (uint32_t)e * CSTAGE_BYTES;
+				const int row0 = tm * UMMA_M + (int)cta_rank * ROWS + q * 32;
+#pragma unroll
+				for (int g = 0; g < NG; g++) {
+					const int col0 = tn * BN + h * (BN / 2) + g * 32;
+					if (row0 >= P.M || col0 >= P.N) continue;          // warp-uniform: the whole box lies outside C
+					if (lane == 0) bulk_wait_group_read0();             // this warp's previous box has left shared memory
+					__syncwarp();
+#pragma unroll
+					for (int i = 0; i < 32; i += 4) {
+						float4 o;
+						o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1]; o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
+						if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
+						sts128(cst + (uint32_t)lane * 128u + (uint32_t)(((i >> 2) ^ (lane & 7)) << 4), o);
+					}
+					fence_proxy_async_smem();
+					__syncwarp();
+					if (lane == 0) { tma_store_3d(&tmC, cst, col0, row0, inst); bulk_commit_group(); }
+				}
+			} else if (row < P.M && !(P.flags & 16)) {
 				const float slope = P.slope;
 				const bool post = P.bias != nullptr || slope != 1.f;   // bias[row] + LeakyReLU (convolution callers)
 				const float bm = P.bias ? __ldg(P.bias + row) : 0.f;
@@ -596,6 +627,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			t_store += tick<PROF>() - ts0;
 			}
 		}
+		if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's TMA stores are complete
 		if (prof && threadIdx.x == 32 * (4 + 4 * XF_GROUPS)) { prof[9] = w_tf; prof[10] = t_drain; prof[11] = t_store; prof[12] = tick<PROF>() - t_begin; }
 	}
 
@@ -756,6 +788,19 @@ bool make_operand_map(CUtensorMap *map, const float *base, long long rows, long 
 	return r == CUDA_SUCCESS;
 }
 
+// C (M lines of N fp32, pitch ldc) as the target of 32-row x 32-column box stores: dims {N, M, batch}, SWIZZLE_128B (the box's
+// 128-byte rows are staged swizzled so the epilogue's per-row 16-byte shared-memory stores are conflict-free)
+bool make_c_map(CUtensorMap *map, float *base, long long M, long long N, long long ldc, int batch, long long strideC)
+{
+	EncodeTiledFn fn = encode_fn();
+	if (!fn) return false;
+	cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)(batch > 0 ? batch : 1)};
+	cuuint64_t gstride[2] = {(cuuint64_t)ldc * 4, (batch > 1) ? (cuuint64_t)strideC * 4 : (cuuint64_t)ldc * 4 * (cuuint64_t)M};
+	cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+	return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 unsigned *g_diag_host = nullptr, *g_diag_dev = nullptr;
 unsigned *diag_dev()
 {
@@ -771,7 +816,7 @@ unsigned *diag_dev()
 
 // common tail of the GEMM and convolution launches: scheduler counters, attributes, cluster launch
 template <int CG, bool CONV>
-cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
+cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
 	if (nt > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
 	P.num_tiles = (int)nt;
@@ -826,8 +871,8 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Para
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr; cfg.numAttrs = 1;
-	cudaError_t le = prof ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true, false>, tmA, tmB, P)
-	                      : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false, CONV>, tmA, tmB, P);
+	cudaError_t le = prof ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true, false>, tmA, tmB, tmC, P)
+	                      : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false, CONV>, tmA, tmB, tmC, P);
 	if (le == cudaSuccess && prof) {   // debug: per-role cycle breakdown of CTAs 0..3 on stderr
 		long long h[64];
 		if (cudaStreamSynchronize(stream) == cudaSuccess && cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -844,7 +889,7 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Para
 // tiles are cut along K into equal chunk ranges, one per pair, whose partial sums meet in a workspace (decode_item,
 // k1_tail_fixup_kernel).  Taken when it shortens the last round by at least 15 % and the launch by at least 12 %.
 template <int CG, bool CONV>
-cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
+cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
 	const int kc_eff = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
 	const int nch = (P.num_k_blocks + kc_eff - 1) / kc_eff;
@@ -867,7 +912,7 @@ cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, K1P
 			} else { cudaGetLastError(); ws = nullptr; }
 		}
 	}
-	cudaError_t e = launch_kernel<CG, CONV>(tmA, tmB, P, items, t, stream, sm_count);
+	cudaError_t e = launch_kernel<CG, CONV>(tmA, tmB, tmC, P, items, t, stream, sm_count);
 	if (ws) {
 		if (e == cudaSuccess) {
 			k1_tail_fixup_kernel<CG><<<dim3((unsigned)P.sk_rem, FIXUP_SPLIT), 256, 0, stream>>>(P);
@@ -896,8 +941,12 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	const long long nt = (long long)P.tiles_m * P.tiles_n * (p.batch > 0 ? p.batch : 1);
 	P.num_k_blocks = (p.K + BK - 1) / BK;
 	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0) ? 1 : 0;
+	// C as a TMA-store target: {N, M, batch} with 32 x 32 boxes (flags bit 13 = 8192 switches the TMA-store epilogue off)
+	CUtensorMap tmC = tmA;
+	P.tma_store = 0;
+	if (P.vecC && !(t.flags & 8192) && (p.batch <= 1 || p.strideC % 4 == 0) && make_c_map(&tmC, p.C, p.M, p.N, p.ldc, p.batch, p.strideC)) P.tma_store = 1;
 
-	return launch_with_tail<CG, false>(tmA, tmB, P, nt, t, stream, sm_count);
+	return launch_with_tail<CG, false>(tmA, tmB, tmC, P, nt, t, stream, sm_count);
 }
 
 // channels-last image as a 4-D tensor {c: cs, x: w, y: h, image: nimg}, box {32 c, 32 x, 1 y, 1}: one box = 32 output pixels of one
@@ -935,7 +984,7 @@ cudaError_t launch_conv_cg(const ConvProblem &c, const K1Tuning &t, cudaStream_t
 	P.num_k_blocks = kk / BK;
 	P.vecC = ((reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && npix % 4 == 0) ? 1 : 0;
 	P.cv_wp = wp; P.cv_wo = c.wo; P.cv_ho = c.ho; P.cv_k = c.k; P.cv_pad = c.pad; P.cv_cblocks = c.ichp / 32; P.cv_npix = npix; P.cv_stride = c.stride;
-	return launch_with_tail<CG, true>(tmA, tmB, P, nt, t, stream, sm_count);
+	return launch_with_tail<CG, true>(tmA, tmB, tmA, P, nt, t, stream, sm_count);
 }
 
 // planar [img][c][y][x] -> channels-last [img][y][x][cs] (cs = ich rounded up to 4, the pad channels zero): one image-sized HBM pass

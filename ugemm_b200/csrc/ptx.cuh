@@ -80,6 +80,18 @@ __device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const void *tmap,
 	             ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint) : "memory");
 }
 
+// ---- TMA store (shared -> global), bulk-group completion ------------------------------------------------
+// 3-D box store: coordinates {c0 = column, c1 = row, c2 = batch instance}; out-of-bounds parts of the box are clipped,
+// so ragged tile edges need no guards.  The source must have been made visible to the async proxy (fence.proxy.async).
+__device__ __forceinline__ void tma_store_3d(const void *tmap, uint32_t src, int c0, int c1, int c2)
+{
+	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+	             ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's committed bulk groups have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // 4-D variant (implicit-GEMM convolution: x, y, channel, image)
 __device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t hint)
 {
