@@ -536,7 +536,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			}
 			// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
 			const float beta = preload_c ? 0.f : P.beta;   // already folded into acc when preloaded
-			if (!CONV && P.tma_store && beta == 0.f && !(P.flags & 16)) {
+			if (P.tma_store && beta == 0.f && !(P.flags & 16)) {
 				// TMA-store epilogue: each warp stages one 32-row x 32-column box at a time in shared memory (128B-swizzled, so a
 				// thread's eight 16-byte stores of its row are conflict-free) and hands it to the TMA unit, which writes whole
 				// 128-byte lines and clips the box at the matrix edge -- instead of 32 row-strided 16-byte stores per instruction.
@@ -550,6 +550,9 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				for (int g = 0; g < NG; g++) {
 					const int col0 = tn * BN + h * (BN / 2) + g * 32;
 					if (row0 >= P.M || col0 >= P.N) continue;          // warp-uniform: the whole box lies outside C
+					// CONV: the 32 columns are one output-row segment (io, jo0 .. jo0+31) of the padded column index
+					const int io = CONV ? col0 / P.cv_wp : 0, jo0 = CONV ? col0 - io * P.cv_wp : 0;
+					if (CONV && (io >= P.cv_ho || jo0 >= P.cv_wo)) continue;
 					if (lane == 0) bulk_wait_group_read0();             // this warp's previous box has left shared memory
 					__syncwarp();
 #pragma unroll
@@ -561,7 +564,11 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					}
 					fence_proxy_async_smem();
 					__syncwarp();
-					if (lane == 0) { tma_store_3d(&tmC, cst, col0, row0, inst); bulk_commit_group(); }
+					if (lane == 0) {
+						if (CONV) tma_store_4d(&tmC, cst, jo0, io, row0, inst);     // clipped at the output width and at the filter count
+						else tma_store_3d(&tmC, cst, col0, row0, inst);
+						bulk_commit_group();
+					}
 				}
 			} else if (row < P.M && !(P.flags & 16)) {
 				const float slope = P.slope;
@@ -984,7 +991,19 @@ cudaError_t launch_conv_cg(const ConvProblem &c, const K1Tuning &t, cudaStream_t
 	P.num_k_blocks = kk / BK;
 	P.vecC = ((reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && npix % 4 == 0) ? 1 : 0;
 	P.cv_wp = wp; P.cv_wo = c.wo; P.cv_ho = c.ho; P.cv_k = c.k; P.cv_pad = c.pad; P.cv_cblocks = c.ichp / 32; P.cv_npix = npix; P.cv_stride = c.stride;
-	return launch_with_tail<CG, true>(tmA, tmB, tmA, P, nt, t, stream, sm_count);
+	// output [img][co][io][jo] as a TMA-store target {wo, ho, ch, img}, box {32 x, 1 y, 32 filters, 1}: needs 16-byte row pitch
+	CUtensorMap tmC = tmA;
+	P.tma_store = 0;
+	if (P.vecC && c.wo % 4 == 0 && !(t.flags & 8192)) {
+		EncodeTiledFn fn = encode_fn();
+		cuuint64_t gdim[4] = {(cuuint64_t)c.wo, (cuuint64_t)c.ho, (cuuint64_t)c.ch, (cuuint64_t)c.nimg};
+		cuuint64_t gstride[3] = {(cuuint64_t)c.wo * 4, (cuuint64_t)npix * 4, (cuuint64_t)c.ch * npix * 4};
+		cuuint32_t box[4] = {32, 1, 32, 1}, estr[4] = {1, 1, 1, 1};
+		if (fn && fn(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+			P.tma_store = 1;
+	}
+	return launch_with_tail<CG, true>(tmA, tmB, tmC, P, nt, t, stream, sm_count);
 }
 
 // planar [img][c][y][x] -> channels-last [img][y][x][cs] (cs = ich rounded up to 4, the pad channels zero): one image-sized HBM pass
