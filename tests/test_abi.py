@@ -60,6 +60,26 @@ def test_no_gpu_means_loud_failure_not_fallback():
         u.sgemm_cuda_simt("R", "N", "N", 2, 2, 2, 1.0, A, 2, A, 2, 0.0, Cm, 2)
 
 
+def test_mgpu_entry_points_fail_loudly_without_init_or_gpu():
+    """sgemm_cuda_mgpu before sgemm_cuda_mgpu_init is an error that leaves C untouched (needs no GPU to check);
+    without a GPU sgemm_cuda_mgpu_init itself fails with the sticky error set -- no CPU path behind it either."""
+    import ugemm_b200 as u
+    L = u.lib()
+    L.sgemm_cuda_clear_error()
+    assert u.sgemm_cuda_mgpu_count() == 0
+    A = np.ones(4, np.float32)
+    Cm = np.full(4, 7.0, np.float32)
+    with pytest.raises(u.UgemmCudaError, match="sgemm_cuda_mgpu_init"):
+        u.sgemm_cuda_mgpu("R", "N", "N", 2, 2, 2, 1.0, A, 2, A, 2, 0.0, Cm, 2, 1, 1)
+    assert np.array_equal(Cm, np.full(4, 7.0, np.float32))
+    assert u.visible_gpus() >= 0
+    if u.visible_gpus() == 0:
+        with pytest.raises(u.UgemmCudaError):
+            u.sgemm_cuda_mgpu_init(1)
+        assert u.sgemm_cuda_mgpu_count() == 0
+    u.sgemm_cuda_mgpu_finish()      # harmless when nothing was initialised
+
+
 def test_product_never_references_the_oracle():
     """Nothing under ugemm_b200/ or include/ may import, link or mention oracle/ (checker isolation)."""
     bad = []
