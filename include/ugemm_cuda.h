@@ -158,6 +158,9 @@ int  sgemm_cuda_mgpu_count(void);     /* GPUs initialised by sgemm_cuda_mgpu_ini
 int  ugemm_cuda_device_count(void);   /* CUDA devices visible to this process (0 without a driver); never an error */
 int  sgemm_cuda_mgpu(char major, char transA, char transB, int M, int N, int K, float alpha, const float *A, int lda,
                      const float *B, int ldb, float beta, float *C, int ldc, int pr, int pc, int overlap, float *timings_ms);
+/* the same call under the init / run / finish naming of the other backends' macro sets (sgemm_test.c:19-33) */
+int  sgemm_cuda_mgpu_run(char major, char transA, char transB, int M, int N, int K, float alpha, const float *A, int lda,
+                         const float *B, int ldb, float beta, float *C, int ldc, int pr, int pc, int overlap, float *timings_ms);
 
 /* ---- counter-based uniform stream, identical on host and device (so a 32768^2 operand can be generated
  * on the GPU and any sampled row regenerated on the host for verification):

@@ -1375,4 +1375,8 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
 	return 0;
 }
 
+int sgemm_cuda_mgpu_run(char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda,
+                        const float *B, int ldb, float beta, float *C, int ldc, int pr, int pc, int overlap, float *timings_ms)
+{ return sgemm_cuda_mgpu(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, pr, pc, overlap, timings_ms); }
+
 } // extern "C"
