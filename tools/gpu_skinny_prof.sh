@@ -16,5 +16,5 @@ for N in (64, 256):
     print("N", N, u.sgemm_cuda_time_dev("3xtf32", 5, 1, "R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N), file=sys.stderr)
     dA.free(); dB.free(); dC.free()
 PY
-UGEMM_K1_FLAGS=$((1|32|4096)) timeout 120 python /tmp/skinny_once.py 2> $OUT/skinny_prof.txt
+UGEMM_K1_FLAGS=$((1|32)) timeout 120 python /tmp/skinny_once.py 2> $OUT/skinny_prof.txt
 grep -E "^N|cta0" $OUT/skinny_prof.txt | tail -8

@@ -836,6 +836,9 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 	constexpr int MAX_DEV = 32;
 	int dev = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return cudaErrorInvalidDevice;
+	// (sgemm_cuda_dev may be called from several host threads on their own streams: the one-time set-up below is serialised)
+	static std::mutex init_mu;
+	std::lock_guard<std::mutex> init_lock(init_mu);
 	// dynamic-scheduler counters: a small pool so launches on different streams do not share a slot
 	static int *sched_pools[MAX_DEV] = {nullptr};
 	static unsigned sched_next = 0;
