@@ -89,6 +89,19 @@ struct Stager {
 			r[i] = __ldg(reinterpret_cast<const float4 *>(fp + i * fstep));
 		}
 	}
+	// the same for an operand that may be only 4-byte aligned (odd leading dimension, sub-view): 128-bit when it can, else
+	// four unguarded 32-bit loads per quad (ANYLD instantiation of the kernel)
+	__device__ __forceinline__ void fast_load_any(long long ld, int tid, bool vec)
+	{
+		fp += KCONTIG ? (long long)K2_BK : K2_BK * ld;
+#pragma unroll
+		for (int i = 0; i < QUADS; i++) {
+			if (NQ % K2_THREADS != 0 && tid + i * K2_THREADS >= NQ) continue;
+			const float *q = fp + i * fstep;
+			if (vec) r[i] = __ldg(reinterpret_cast<const float4 *>(q));
+			else r[i] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+		}
+	}
 	__device__ __forceinline__ void store(float (*s)[BMN + K2_PAD], int tid) const
 	{
 #pragma unroll
@@ -109,7 +122,9 @@ struct Stager {
 	}
 };
 
-template <int BM, int BN, int TM, int TN, bool AK, bool BKM>
+// ANYLD: interior tiles run the unguarded steady-state loop even when an operand is only 4-byte aligned (its quads are
+// then four 32-bit loads); a separate instantiation so that the all-128-bit loop keeps its instruction stream
+template <int BM, int BN, int TM, int TN, bool AK, bool BKM, bool ANYLD = false>
 __global__ void __launch_bounds__(K2_THREADS, (BM >= 128 ? 2 : 3))
 k2_simt_kernel(Problem p, const int tiles_m, const int tiles_n, const bool vecA, const bool vecB, const bool vecC)
 {
@@ -148,7 +163,7 @@ k2_simt_kernel(Problem p, const int tiles_m, const int tiles_n, const bool vecA,
 	const int ktiles = (p.K + K2_BK - 1) / K2_BK;
 
 	// interior tiles of vector-loadable operands take unguarded 128-bit loads for every full k-tile (CTA-uniform test)
-	const bool interior = vecA && vecB && m0 + BM <= p.M && n0 + BN <= p.N;
+	const bool interior = (ANYLD || (vecA && vecB)) && m0 + BM <= p.M && n0 + BN <= p.N;
 	const int fast_tiles = interior ? p.K / K2_BK : 0;
 	sa.fast_init(p.A, p.lda, m0, tid);
 	sb.fast_init(p.B, p.ldb, n0, tid);
@@ -200,8 +215,8 @@ k2_simt_kernel(Problem p, const int tiles_m, const int tiles_n, const bool vecA,
 	// steady state of interior tiles: nothing but 128-bit loads, the FFMA block, the shared-memory stores and one barrier
 	for (; t + 1 < fast_tiles; t++) {
 		const int cur = t & 1;
-		sa.fast_load(p.lda, tid);
-		sb.fast_load(p.ldb, tid);
+		if (ANYLD) { sa.fast_load_any(p.lda, tid, vecA); sb.fast_load_any(p.ldb, tid, vecB); }
+		else { sa.fast_load(p.lda, tid); sb.fast_load(p.ldb, tid); }
 		multiply(cur);
 		sa.store(As[cur ^ 1], tid);
 		sb.store(Bs[cur ^ 1], tid);
@@ -305,8 +320,10 @@ cudaError_t launch_cfg(const Problem &p, cudaStream_t stream)
 	const bool vecC = al16(p.C) && (p.ldc % 4 == 0) && (!multi || p.strideC % 4 == 0);
 	if (p.batch > 65535) return cudaErrorInvalidConfiguration;
 	dim3 grid((unsigned)tiles, (unsigned)(multi ? p.batch : 1)), block(K2_THREADS);
-#define K2_LAUNCH(AK, BKM) \
-	k2_simt_kernel<BM, BN, TM, TN, AK, BKM><<<grid, block, 0, stream>>>(p, tiles_m, tiles_n, vecA, vecB, vecC)
+#define K2_LAUNCH(AK, BKM) do { \
+	if (BM == 128 && BN == 128 && !(vecA && vecB)) \
+		k2_simt_kernel<BM, BN, TM, TN, AK, BKM, (BM == 128 && BN == 128)><<<grid, block, 0, stream>>>(p, tiles_m, tiles_n, vecA, vecB, vecC); \
+	else k2_simt_kernel<BM, BN, TM, TN, AK, BKM><<<grid, block, 0, stream>>>(p, tiles_m, tiles_n, vecA, vecB, vecC); } while (0)
 	if (p.a_kmajor) { if (p.b_kmajor) K2_LAUNCH(true, true); else K2_LAUNCH(true, false); }
 	else            { if (p.b_kmajor) K2_LAUNCH(false, true); else K2_LAUNCH(false, false); }
 #undef K2_LAUNCH
