@@ -155,6 +155,10 @@ int   ugemm_cuda_ipc_close(void *mapped);
 int  sgemm_cuda_mgpu_init(int ngpus);
 void sgemm_cuda_mgpu_finish(void);
 int  sgemm_cuda_mgpu_count(void);     /* GPUs initialised by sgemm_cuda_mgpu_init, 0 if none */
+/* the partition sgemm_cuda_mgpu uses for a row-major M x N x K problem on a pr x pc grid: GPU (i, j) owns rows
+ * [i*block_rows, ...) x columns [j*block_cols, ...) of C (the last blocks may be short or empty); K is cut into k_slabs slabs of
+ * slab_width (the last may be short).  Pure host arithmetic, needs no GPU; 0 = OK, 1 = bad arguments. */
+int  sgemm_cuda_mgpu_plan(int M, int N, int K, int pr, int pc, int overlap, int *block_rows, int *block_cols, int *k_slabs, int *slab_width);
 int  ugemm_cuda_device_count(void);   /* CUDA devices visible to this process (0 without a driver); never an error */
 int  sgemm_cuda_mgpu(char major, char transA, char transB, int M, int N, int K, float alpha, const float *A, int lda,
                      const float *B, int ldb, float beta, float *C, int ldc, int pr, int pc, int overlap, float *timings_ms);

@@ -87,3 +87,34 @@ def test_sharded_schedule_over_gloo(world, M, N, K, L, tmp_path):
         ref = want[i * M // pr:(i + 1) * M // pr, j * N // pc:(j + 1) * N // pc]
         e = np.linalg.norm(blk.astype(np.float64) - ref) / np.linalg.norm(ref.astype(np.float64))
         assert e <= 1e-6, (r, e)
+
+
+def test_single_process_plan_invariants():
+    """The partition sgemm_cuda_mgpu uses (C ABI, sgemm_cuda_mgpu_plan; host arithmetic, no GPU): blocks of a pr x pc grid tile C
+    exactly once, K slabs tile K exactly once, and the sizes keep every local leading dimension TMA-eligible."""
+    import ugemm_b200 as u
+    assert u.sgemm_cuda_mgpu_plan(32768, 32768, 32768, 2, 4, 1) == (16384, 8192, 4, 8192)      # BASELINE config 5 on 8 GPUs
+    assert u.sgemm_cuda_mgpu_plan(32768, 32768, 32768, 1, 1, 1) == (32768, 32768, 1, 32768)    # one GPU: nothing to overlap
+    assert u.sgemm_cuda_mgpu_plan(32768, 32768, 32768, 2, 4, 0) == (16384, 8192, 1, 32768)     # overlap off: one slab
+    rng = np.random.default_rng(5)
+    for _ in range(2000):
+        M, N, K = (int(x) for x in rng.integers(0, 40000, size=3))
+        pr, pc = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+        ov = int(rng.integers(0, 3))
+        mb, nb, L, kw = u.sgemm_cuda_mgpu_plan(M, N, K, pr, pc, ov)
+        assert mb % 4 == 0 and nb % 4 == 0
+        assert pr * mb >= M and pc * nb >= N                       # the grid covers C ...
+        assert mb <= -(-M // pr) + 3 and nb <= -(-N // pc) + 3     # ... with blocks no larger than the even split rounded up to 4
+        rows = [max(0, min(mb, M - i * mb)) for i in range(pr)]
+        cols = [max(0, min(nb, N - j * nb)) for j in range(pc)]
+        assert sum(rows) == M and sum(cols) == N                   # every row and column of C belongs to exactly one block
+        assert 1 <= L <= 64
+        if K > 0:
+            widths = [min(kw, K - t * kw) for t in range(L)]
+            assert all(w > 0 for w in widths) and sum(widths) == K   # every k belongs to exactly one slab
+        if L > 1:
+            assert kw % 32 == 0 and ((ov and pr * pc > 1) or ov > 1)
+        if ov == 0 or (pr * pc == 1 and ov < 2):
+            assert (L, kw) == (1, K)
+    with pytest.raises(u.UgemmCudaError):
+        u.sgemm_cuda_mgpu_plan(8, 8, 8, 0, 1)

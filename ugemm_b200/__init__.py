@@ -11,6 +11,6 @@ from .backend import (  # noqa: F401
     k1_eligible, last_error, last_kernel, last_repacked, launch_count, lib, probe_tf32, set_k1_tuning, set_sm_limit, sgemm_cuda,
     sgemm_cuda_3xtf32, sgemm_cuda_batched, sgemm_cuda_batched_dev, sgemm_cuda_dev, sgemm_cuda_finish, sgemm_cuda_init, sgemm_cuda_simt, sgemm_cuda_time_dev,
     sgemm_finish, sgemm_init, sgemm_rnn, sgemm_rnt, sgemm_rtn, sync,
-    sgemm_cuda_mgpu, sgemm_cuda_mgpu_count, sgemm_cuda_mgpu_finish, sgemm_cuda_mgpu_init, visible_gpus,
+    sgemm_cuda_mgpu, sgemm_cuda_mgpu_count, sgemm_cuda_mgpu_finish, sgemm_cuda_mgpu_init, sgemm_cuda_mgpu_plan, visible_gpus,
     saxpy_cuda, saxpy_cuda_dev, sgemv_cuda, sgemv_cuda_dev, dgemm_cuda, dgemm_cuda_dev, dgemm_cuda_time_dev,
 )

@@ -167,7 +167,7 @@ EXPORTED_SYMBOLS = [
     "sgemm_cuda_set_k1_tuning", "sgemm_cuda_set_sm_limit", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
     "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
     "ugemm_cuda_memcpy_async", "ugemm_cuda_ipc_export", "ugemm_cuda_ipc_import", "ugemm_cuda_ipc_close",
-    "sgemm_cuda_mgpu_init", "sgemm_cuda_mgpu_finish", "sgemm_cuda_mgpu_count", "sgemm_cuda_mgpu", "sgemm_cuda_mgpu_run", "ugemm_cuda_device_count",
+    "sgemm_cuda_mgpu_init", "sgemm_cuda_mgpu_finish", "sgemm_cuda_mgpu_count", "sgemm_cuda_mgpu", "sgemm_cuda_mgpu_run", "sgemm_cuda_mgpu_plan", "ugemm_cuda_device_count",
     "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
     "ugemm_cuda_probe_tf32", "im2col_cuda", "im2col_cuda_dev", "convolution_cuda", "convolution_cuda_LReLU",
     "convolution_cuda_dev", "convolution_cuda_batched_dev", "sgemm_cuda_set_conv_fusion", "sgemm_cuda_last_conv_fused", "saxpy_cuda", "saxpy_cuda_dev", "sgemv_cuda", "sgemv_cuda_dev",
@@ -388,6 +388,14 @@ def sgemm_cuda_mgpu_finish():
 
 def sgemm_cuda_mgpu_count():
     return int(lib().sgemm_cuda_mgpu_count())
+
+
+def sgemm_cuda_mgpu_plan(M, N, K, pr, pc, overlap=1):
+    """(block_rows, block_cols, k_slabs, slab_width) of sgemm_cuda_mgpu's partition; host arithmetic only."""
+    v = [C.c_int(0) for _ in range(4)]
+    if lib().sgemm_cuda_mgpu_plan(M, N, K, pr, pc, overlap, *[C.byref(x) for x in v]):
+        raise UgemmCudaError("sgemm_cuda_mgpu_plan: bad arguments")
+    return tuple(x.value for x in v)
 
 
 def visible_gpus():

@@ -1101,6 +1101,24 @@ int mg_arena(int dev, size_t bytes)
 	return 0;
 }
 
+// The partition of one call (row-major view): block sizes (multiples of 4 so local leading dimensions stay TMA-eligible) and
+// K slabs (multiples of 32).  8192-wide slabs: every slab after the first is a beta = 1 pass over the C block (+2..6 % per pass
+// at 4096), while the exposed part of the distribution is only the first slab's transfer.  overlap > 1 forces the slab pipeline
+// on a 1 x 1 grid too (tests).
+void mg_plan(int M, int N, int K, int pr, int pc, int overlap, int *mb, int *nb, int *slabs, int *kw)
+{
+	*mb = ((M + pr - 1) / pr + 3) / 4 * 4;
+	*nb = ((N + pc - 1) / pc + 3) / 4 * 4;
+	int L = 1, w = K;
+	if (K > 0 && ((overlap && pr * pc > 1) || overlap > 1)) {
+		L = (K + 8191) / 8192;
+		if (L > MG_MAX_SLABS) L = MG_MAX_SLABS;
+		w = ((K + L - 1) / L + 31) / 32 * 32;
+		L = (K + w - 1) / w;
+	}
+	*slabs = L; *kw = w;
+}
+
 // 2-D copy between any two pointers of the unified address space; lines of `cols` floats, pitches in floats
 cudaError_t mg_copy(float *dst, long long dld, const float *src, long long sld, long long lines, long long cols, cudaStream_t st)
 {
@@ -1173,6 +1191,18 @@ void sgemm_cuda_mgpu_finish(void)
 
 int sgemm_cuda_mgpu_count(void) { return mg.n; }
 
+int sgemm_cuda_mgpu_plan(int M, int N, int K, int pr, int pc, int overlap, int *block_rows, int *block_cols, int *k_slabs, int *slab_width)
+{
+	if (M < 0 || N < 0 || K < 0 || pr < 1 || pc < 1 || (long long)pr * pc > MG_MAX_DEV) return 1;
+	int mb, nb, L, kw;
+	mg_plan(M, N, K, pr, pc, overlap, &mb, &nb, &L, &kw);
+	if (block_rows) *block_rows = mb;
+	if (block_cols) *block_cols = nb;
+	if (k_slabs) *k_slabs = L;
+	if (slab_width) *slab_width = kw;
+	return 0;
+}
+
 int ugemm_cuda_device_count(void)
 {
 	int n = 0;
@@ -1194,17 +1224,8 @@ int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alp
 	const bool scale_only = p.alpha == 0.f || p.K == 0;
 	if (scale_only && p.beta == 1.f) return 0;
 
-	// block sizes (multiples of 4 so local leading dimensions stay TMA-eligible), K slabs (multiples of 32)
-	const int mb = ((p.M + pr - 1) / pr + 3) / 4 * 4, nb = ((p.N + pc - 1) / pc + 3) / 4 * 4;
-	int L = 1, kw = p.K;
-	if (!scale_only && ((overlap && pr * pc > 1) || overlap > 1)) {   // overlap > 1 forces the slab pipeline on a 1 x 1 grid too (tests)
-		// 8192-wide slabs: every slab after the first is a beta = 1 pass over the C block (+2..6 % per pass at 4096), while the
-		// exposed part of the distribution is only the first slab's transfer
-		L = (p.K + 8191) / 8192;
-		if (L > MG_MAX_SLABS) L = MG_MAX_SLABS;
-		kw = ((p.K + L - 1) / L + 31) / 32 * 32;
-		L = (p.K + kw - 1) / kw;
-	}
+	int mb, nb, L, kw;
+	mg_plan(p.M, p.N, p.K, pr, pc, overlap, &mb, &nb, &L, &kw);
 	if (scale_only) L = 0;
 
 	// which device (if any) holds a caller pointer: a block whose source already lives on the device that needs it is used
