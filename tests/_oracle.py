@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libugemm_ref.so")
+REF_CONV_SO = os.path.join(ORACLE_DIR, "_ref", "libugemm_ref_conv.so")
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _SIG14 = [C.c_char, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_float,
@@ -30,13 +31,16 @@ def build_oracle(force=False):
     src = os.path.join(ORACLE_DIR, "sgemm_oracle.c")
     if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(src) > os.path.getmtime(ORACLE_SO):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+    def stale(so, *srcs):
+        return not os.path.exists(so) or any(os.path.getmtime(os.path.join(ORACLE_DIR, s)) > os.path.getmtime(so) for s in srcs)
     if os.path.exists(os.environ.get("UGEMM_REF", "/root/reference") + "/ugemm.h") and (
-            force or not os.path.exists(REF_SO) or os.path.getmtime(os.path.join(ORACLE_DIR, "ref_shim.c")) > os.path.getmtime(REF_SO)):
+            force or stale(REF_SO, "ref_shim.c") or stale(REF_CONV_SO, "ref_conv_shim.c")):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
 
 
 _oracle = None
 _ref = None
+_ref_conv = None
 
 
 def oracle():
@@ -98,6 +102,22 @@ def ref():
                 getattr(lib, name).restype = None
         _ref = lib
     return _ref
+
+
+def ref_conv():
+    """The reference's UNMODIFIED convolution host code (sgemm_gl1.h im2col), compiled against GL stubs (None if never built)."""
+    global _ref_conv
+    if _ref_conv is None:
+        build_oracle()
+        if not os.path.exists(REF_CONV_SO):
+            return None
+        lib = C.CDLL(REF_CONV_SO)
+        lib.ref_im2col.argtypes = [_f32p] + [C.c_int] * 9 + [_f32p]
+        lib.ref_im2col.restype = None
+        lib.ref_gl_convolution.argtypes = [C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_void_p]
+        lib.ref_gl_convolution.restype = C.c_int
+        _ref_conv = lib
+    return _ref_conv
 
 
 def b(ch):
