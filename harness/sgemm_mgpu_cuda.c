@@ -29,7 +29,7 @@ static void grid_for(int n, int *pr, int *pc)
 
 int main(int argc, char **argv)
 {
-	int ngpus = argc > 1 ? atoi(argv[1]) : ugemm_cuda_device_count();
+	int ngpus = argc > 1 && atoi(argv[1]) > 0 ? atoi(argv[1]) : ugemm_cuda_device_count();   /* 0 = every visible GPU */
 	const int M = argc > 2 ? atoi(argv[2]) : 32768;
 	const int N = argc > 3 ? atoi(argv[3]) : M;
 	const int K = argc > 4 ? atoi(argv[4]) : M;

@@ -59,6 +59,8 @@ def oracle():
         lib.oracle_cmp_results.restype = C.c_int
         lib.oracle_fill_uniform.argtypes = [_f32p, C.c_size_t, C.c_uint64, C.c_float, C.c_float]
         lib.oracle_fill_uniform.restype = None
+        lib.oracle_fill_uniform_at.argtypes = [_f32p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_float, C.c_float]
+        lib.oracle_fill_uniform_at.restype = None
         lib.oracle_max_threads.restype = C.c_int
         lib.oracle_im2col.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
         lib.oracle_im2col.restype = None
@@ -127,6 +129,13 @@ def b(ch):
 def fill_uniform(n, seed, lo=0.0, hi=1.0):
     x = np.empty(int(n), dtype=np.float32)
     oracle().oracle_fill_uniform(x, x.size, seed, lo, hi)
+    return x
+
+
+def fill_uniform_at(n, seed, offset, lo=0.0, hi=1.0):
+    """Elements [offset, offset + n) of the stream fill_uniform(., seed) produces (a window of a device-generated matrix)."""
+    x = np.empty(int(n), dtype=np.float32)
+    oracle().oracle_fill_uniform_at(x, x.size, seed, int(offset), lo, hi)
     return x
 
 

@@ -301,6 +301,56 @@ def test_config4_tall_skinny_sampled(u):
         assert e <= TOL
 
 
+def test_config5_32768_sampled(u):
+    """BASELINE config 5 (32768^3 NN, alpha=1, beta=0, device-generated operands): 32 sampled rows -- 4 slabs of 8, one of them
+    straddling the M/2 block boundary of every grid -- against the reference's sgemm_avx (sgemm_avx256.h:392) on the same rows
+    regenerated from the shared RNG.  Through sgemm_cuda_dev on one GPU (K1) and through sgemm_cuda_mgpu on the largest
+    BASELINE grid the box holds (1x1, 2x1, 2x2, 2x4)."""
+    r = O.ref()
+    M = N = K = 32768
+    lo, hi = -0.5, 0.5
+    slabs = [(0, 8), (16380, 8), (24571, 8), (32760, 8)]
+    dA = u.DeviceBuffer(M * K).fill_uniform(1, lo, hi)
+    dB = u.DeviceBuffer(K * N).fill_uniform(2, lo, hi)
+    dC = u.DeviceBuffer(M * N)
+    B = O.fill_uniform_at(K * N, 2, 0, lo, hi)                      # 4.3 GB, regenerated on the host (never downloaded)
+    wants = []
+    for r0, nr in slabs:
+        A = O.fill_uniform_at(nr * K, 1, r0 * K, lo, hi)
+        C0 = np.zeros(nr * N, np.float32)
+        if r is not None:
+            wants.append(O.run14(r.ref_sgemm_avx, "R", "N", "N", nr, N, K, 1.0, A, K, B, N, 0.0, C0, N))
+        else:   # GPU box without a prebuilt oracle/_ref: the bit-identical restatement (tests/test_oracle.py pins it to sgemm_avx)
+            wants.append(O.run14(O.oracle().oracle_sgemm_banded, "R", "N", "N", nr, N, K, 1.0, A, K, B, N, 0.0, C0, N, threads=1))
+    del B
+
+    def worst_of(tag):
+        worst = 0.0
+        for (r0, nr), want in zip(slabs, wants):
+            got = dC.download(nr * N, offset=r0 * N)
+            worst = max(worst, O.relerr("R", nr, N, want, got, N))
+        print(f"c5 {tag}: sampled relerr {worst:.3e} over 32 rows ({bounds(K)})")
+        return worst
+
+    try:
+        u.sgemm_cuda_dev("3xtf32", None, "R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N)
+        u.sync()
+        assert u.last_kernel() == "3xtf32"
+        assert worst_of("sgemm_cuda_dev 1 GPU") <= TOL
+        n = min(u.visible_gpus(), 8)
+        pr, pc = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}[8 if n >= 8 else 4 if n >= 4 else 2 if n >= 2 else 1]
+        dC.upload(np.full(1 << 20, np.nan, np.float32))              # poison the head of C so a skipped run cannot pass
+        u.sgemm_cuda_mgpu_init(pr * pc)
+        try:
+            u.sgemm_cuda_mgpu("R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N, pr, pc, 1)
+        finally:
+            u.sgemm_cuda_mgpu_finish()
+        assert worst_of(f"sgemm_cuda_mgpu {pr}x{pc}") <= TOL
+    finally:
+        for d in (dA, dB, dC):
+            d.free()
+
+
 def test_full_size_linearity_property(u):
     """Size-independent property at 4096^3: GEMM(A, B1 + B2) == GEMM(A, B1) + GEMM(A, B2) (beta=1 accumulate path)."""
     M = N = K = 4096
