@@ -29,10 +29,35 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
+    "c1": dict(M=1024, N=1024, K=1024, desc="SGEMM row-major NN 1024x1024x1024 fp32 alpha=1 beta=0 (BASELINE configs[0]: the check_sgemm CPU case)"),
     "c2": dict(M=8192, N=8192, K=8192, desc="SGEMM row-major NN 8192x8192x8192 fp32 alpha=1 beta=0 (BASELINE configs[1])"),
     "c4": dict(M=200704, N=256, K=1152, desc="im2col-shaped SGEMM NN 200704x256x1152 fp32 (BASELINE configs[3])"),
     "c5": dict(M=32768, N=32768, K=32768, desc="SGEMM NN 32768^3 fp32 sharded as a 2-D C-tile grid (BASELINE configs[4])"),
 }
+
+
+def config_for(wl_name, world=1):
+    """The `config` object of the JSON line -- built by ONE function for both arms (--impl ours / reference) so that the two lines
+    describe the same workload with the same keys; everything implementation-specific goes to `details`."""
+    wl = WORKLOADS[wl_name]
+    M, N, K = wl["M"], wl["N"], wl["K"]
+    mb = (M * K + K * N + M * N) * 4 / 1e6
+    if wl_name == "c1":
+        l2 = "inputs (A+B+C = %.1f MB) fit the 126 MB L2: a buffer larger than L2 is rewritten between timed steps (flush)" % mb
+    elif world > 1:
+        l2 = "inputs larger than L2 (per-GPU panels of a %.0f MB problem); no flush needed" % mb
+    else:
+        l2 = "inputs larger than L2 (A+B+C = %.0f MB vs 126 MB L2); no flush needed" % mb
+    return {"workload": wl["desc"], "l2_policy": l2}
+
+
+def host_cores():
+    """Host threads this process may use.  NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers, which made
+    the round-1 reference arm run on one core at N >= 2; the checker libraries take the thread count as an explicit argument."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def measured_peaks():
@@ -96,22 +121,31 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_reference_arm(wl, seconds_target, steps=1, warmup=0):
-    """Reference CPU SGEMM on all host cores over workload `wl` (whole, or a bounded row-slab sample of it).
+REF_BUILD_NOTE = "gcc -O3 -march=x86-64-v3 -funroll-loops -ffp-contract=fast (the reference Makefile asks clang -Ofast -march=native; clang is absent and the .so must run on another host)"
+
+
+def cpu_reference_arm(wl, seconds_target, steps=1, warmup=0, cores=None):
+    """Reference CPU SGEMM on `cores` host threads (default: all this process may use) over workload `wl` (whole, or a bounded
+    row-slab sample of it).  cores == 1 is sgemm_avx exactly as shipped (the reference has no threading).
     Returns (tflops, cores, kind, sample_description, ms_per_step)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
 
     import _oracle as O
     N, K = wl["N"], wl["K"]
+    cores = cores or host_cores()
     r = O.ref()
     if r is not None:
-        kind, cores = "reference", int(r.ref_max_threads())
-        fn = lambda M, A, B, Cm: r.ref_sgemm_avx_mt(cores, b"R", b"N", b"N", M, N, K, 1.0, A, K, B, N, 0.0, Cm, N)
-        what = "unmodified sgemm_avx (sgemm_avx256.h:392) on disjoint row slabs"
+        kind = "reference"
+        if cores == 1:
+            fn = lambda M, A, B, Cm: r.ref_sgemm_avx(b"R", b"N", b"N", M, N, K, 1.0, A, K, B, N, 0.0, Cm, N)
+            what = "unmodified sgemm_avx (sgemm_avx256.h:392) as shipped, one core; built with " + REF_BUILD_NOTE
+        else:
+            fn = lambda M, A, B, Cm: r.ref_sgemm_avx_mt(cores, b"R", b"N", b"N", M, N, K, 1.0, A, K, B, N, 0.0, Cm, N)
+            what = "unmodified sgemm_avx (sgemm_avx256.h:392) on disjoint row slabs; built with " + REF_BUILD_NOTE
     else:
         o = O.oracle()
-        kind, cores = "port", int(o.oracle_max_threads())
+        kind = "port"
         fn = lambda M, A, B, Cm: o.oracle_sgemm_banded(cores, b"R", b"N", b"N", M, N, K, 1.0, A, K, B, N, 0.0, Cm, N)
         what = "oracle port of sgemm_avx's 35-band order"
     B = O.fill_uniform(K * N, 2)
@@ -119,7 +153,7 @@ def cpu_reference_arm(wl, seconds_target, steps=1, warmup=0):
     # depends on the slab height per thread: 64 rows per thread stay in the core's L2 (1.0-1.1 TFLOP/s on 16 threads), the
     # 512 rows per thread of the real 8192-row workload do not (0.45 TFLOP/s).  A small sample therefore FLATTERS the reference;
     # the whole workload is run whenever it fits the time budget, and only otherwise a bounded slab.
-    m0 = 64 * cores
+    m0 = min(64 * cores, wl["M"])
     A = O.fill_uniform(m0 * K, 1)
     Cm = np.zeros(m0 * N, np.float32)
     fn(m0, A, B, Cm)                       # first call pays thread start-up and page faults
@@ -151,23 +185,58 @@ def run_reference_impl(args, wl_name):
         return
     wl = WORKLOADS[wl_name]
     tflops, cores, kind, sample, ms = cpu_reference_arm(wl, seconds_target=min(3.0, max(0.3, 150.0 / (max(args.steps, 1) + min(args.warmup, 2)))),
-                                                       steps=max(args.steps, 1), warmup=min(args.warmup, 2))
+                                                       steps=max(args.steps, 1), warmup=min(args.warmup, 2), cores=1 if wl_name == "c1" else None)
     line = {"impl": "reference", "metric": "SGEMM TFLOP/s", "value": tflops, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "note": "reference CPU path on the GPU box's host cores; each step is the whole workload when that fits the time budget, else a bounded row-slab sample (see cpu_baseline.sample)"},
+            "config": config_for(wl_name, max(args.gpus, 1)),
+            "details": {"note": "reference CPU path on the GPU box's host cores; each step is the whole workload when that fits the time budget, else a bounded row-slab sample (see cpu_baseline.sample)",
+                        "host_cores_used": cores, "OMP_NUM_THREADS_env": os.environ.get("OMP_NUM_THREADS")},
             "cpu_baseline": {"value": tflops, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def k1_traffic_bytes(wl_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture, if any."""
+def k1_traffic_bytes(wl_name, live=True):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on this workload.  Measured live when ncu
+    is on the box: this script re-runs itself (`--traffic-child`: device-resident operands, warm-ups, a few launches) under
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none` after every timed region has finished, so no
+    reported time is taken under the profiler.  Falls back to the committed capture (profiles/traffic.json).
+    Returns (bytes or None, source)."""
+    if live and wl_name in ("c1", "c2", "c4"):
+        try:
+            cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
+                   "-k", "regex:k1_3xtf32|k2_simt", "-s", "3", "-c", "1", "--csv", sys.executable, os.path.abspath(__file__),
+                   "--traffic-child", "--workload", wl_name]
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            import csv
+            import io
+            tot, seen = 0.0, 0
+            for row in csv.reader(io.StringIO(res.stdout)):
+                if len(row) >= 3 and row[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(row[-1].replace(",", ""))
+                    seen += 1
+            if seen == 2 and tot > 0:
+                return int(tot), "live: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum on one launch, run by bench.py after the timed regions"
+        except Exception:  # noqa: BLE001
+            pass
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(path)).get(wl_name)
+        j = json.load(open(path))
+        return j.get(wl_name), "committed capture: " + j.get("source", path)
     except Exception:
-        return None
+        return None, "unavailable"
+
+
+def run_traffic_child(wl_name):
+    """Body of the ncu child process: nothing is timed or printed here."""
+    import ugemm_b200 as u
+    wl = WORKLOADS[wl_name]
+    M, N, K = wl["M"], wl["N"], wl["K"]
+    u.sgemm_cuda_init(0)
+    dA, dB, dC = u.DeviceBuffer(M * K).fill_uniform(1), u.DeviceBuffer(K * N).fill_uniform(2), u.DeviceBuffer(M * N).fill_uniform(3)
+    u.sgemm_cuda_time_dev("auto", 3, 3, "R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N)
+    u.sync()
 
 
 def other_shapes(u, peaks, info):
@@ -278,8 +347,21 @@ def run_single(args, wl_name):
     sampler = ClockSampler(0)
     sampler.start()
     l0 = u.launch_count()
-    avg_ms, min_ms, total_ms = u.sgemm_cuda_time_dev("auto", args.steps, args.warmup, "R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N, total=True)
-    launches = u.launch_count() - l0 - args.warmup
+    if (M * K + K * N + M * N) * 4 > 126e6:
+        avg_ms, min_ms, total_ms = u.sgemm_cuda_time_dev("auto", args.steps, args.warmup, "R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N, total=True)
+        launches = u.launch_count() - l0 - args.warmup
+    else:
+        # the operands fit the L2: rewrite a 256 MB buffer (larger than L2) before every timed launch, time each launch alone
+        flush = u.DeviceBuffer(64 << 20)
+        u.sgemm_cuda_time_dev("auto", 1, args.warmup, "R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N)
+        l0 = u.launch_count()
+        per = []
+        for _ in range(args.steps):
+            flush.fill_uniform(9)
+            per.append(u.sgemm_cuda_time_dev("auto", 1, 0, "R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N)[0])
+        launches = u.launch_count() - l0 - args.steps          # the flush fills are not GEMM launches
+        flush.free()
+        avg_ms, min_ms, total_ms = sum(per) / len(per), min(per), sum(per)
     kernel = u.last_kernel()
     clocks = sampler.stop()
     ms_per_step = total_ms / args.steps
@@ -308,29 +390,76 @@ def run_single(args, wl_name):
         L.ugemm_cuda_free_host(h)
 
     peaks = measured_peaks()
-    shapes = other_shapes(u, peaks, info) if (wl_name == "c2" and not args.no_shapes) else None
+    side = wl_name == "c2" and not args.no_shapes
+    sustained = c5_1gpu = config1 = None
+    shapes = other_shapes(u, peaks, info) if side else None
+    if side:
+        # the same kernel back to back for >= 4 s: the power-capped rate, against the SUSTAINED measured peak
+        iters = int(min(4096, max(args.steps, 4300.0 / avg_ms)))
+        smp = ClockSampler(0)
+        smp.start()
+        s_avg, s_min, s_total = u.sgemm_cuda_time_dev("auto", iters, 1, "R", "N", "N", M, N, K, 1.0, dA, K, dB, N, 0.0, dC, N, total=True)
+        s_clk = smp.stop()
+        s_tf = flops * iters / s_total / 1e9
+        sustained = {"tflops": s_tf, "seconds": s_total / 1e3, "launches": iters, "ms_avg": s_avg, "peak": peaks["bf16_sustained"] / 6.0,
+                     "frac": s_tf / (peaks["bf16_sustained"] / 6.0), "nominal_frac": s_tf / 375.0,
+                     "peak_basis": f"{peaks['source']} bf16 dense sustained {peaks['bf16_sustained']:.1f} TFLOP/s / 6", "clocks": s_clk}
+    for b in (dA, dB, dC):
+        b.free()
+    if side:
+        # BASELINE config 5 on ONE GPU: the same-problem anchor of the 1/2/4/8-GPU scaling curve (operands 3 x 4.29 GB, device-generated)
+        n5 = 32768
+        d5 = [u.DeviceBuffer(n5 * n5).fill_uniform(s) for s in (1, 2)] + [u.DeviceBuffer(n5 * n5)]
+        a5, m5 = u.sgemm_cuda_time_dev("auto", 2, 1, "R", "N", "N", n5, n5, n5, 1.0, d5[0], n5, d5[1], n5, 0.0, d5[2], n5)
+        c5_1gpu = {"workload": WORKLOADS["c5"]["desc"], "ms_avg": a5, "ms_min": m5, "tflops": 2.0 * n5 ** 3 / a5 / 1e9, "launches": 2}
+        for b in d5:
+            b.free()
+        # BASELINE config 1 on this box's host: sgemm_avx as shipped (ONE core, the reference has no threading) at 1024^3,
+        # beside K1 on the same problem (L2 flushed between launches)
+        c1_tf, _, c1_kind, c1_sample, c1_ms = cpu_reference_arm(WORKLOADS["c1"], seconds_target=2.0, steps=5, warmup=1, cores=1)
+        config1 = {"workload": WORKLOADS["c1"]["desc"], "cpu_1core_gflops": c1_tf * 1e3, "cpu_ms": c1_ms, "kind": c1_kind, "sample": c1_sample}
+        d1 = [u.DeviceBuffer(1 << 20).fill_uniform(s) for s in (1, 2, 3)]
+        flush = u.DeviceBuffer(64 << 20)
+        u.sgemm_cuda_time_dev("auto", 1, 3, "R", "N", "N", 1024, 1024, 1024, 1.0, d1[0], 1024, d1[1], 1024, 0.0, d1[2], 1024)
+        per = []
+        for _ in range(10):
+            flush.fill_uniform(9)
+            per.append(u.sgemm_cuda_time_dev("auto", 1, 0, "R", "N", "N", 1024, 1024, 1024, 1.0, d1[0], 1024, d1[1], 1024, 0.0, d1[2], 1024)[0])
+        config1.update({"gpu_ms_avg_l2_cold": sum(per) / len(per), "gpu_tflops_l2_cold": 2.0 * 1024 ** 3 / (sum(per) / len(per)) / 1e9, "gpu_kernel": u.last_kernel()})
+        for b in d1 + [flush]:
+            b.free()
     # a kernel timed alone over a short burst of steps -> burst peak; TF32 dense = bf16 dense / 2; 3 MMAs per product
     peak = peaks["bf16_burst"] / 6.0
+    if kernel != "3xtf32":
+        peak = info["sm_count"] * 128 * 2 * info["sm_clock_khz"] * 1e3 / 1e12
     achieved = flops / avg_ms / 1e9
-    cpu_tf, cores, kind, sample, _ = cpu_reference_arm(wl, seconds_target=12.0)
+    cpu_tf, cores, kind, sample, _ = cpu_reference_arm(wl, seconds_target=12.0, cores=1 if wl_name == "c1" else None)
+    traffic, traffic_source = k1_traffic_bytes(wl_name, live=not args.no_ncu)
     line = {
         "metric": "SGEMM TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": wl["desc"], "kernel": f"{kernel} (auto dispatch)", "device": info["name"],
-                   "l2_policy": "inputs larger than L2 (A+B+C = %.0f MB vs 126 MB L2); no flush needed" % ((M * K + K * N + M * N) * 4 / 1e6),
-                   "accuracy": "3xTF32 with fp32 promotion every 128 k: normwise relerr <= 2.6e-6 vs fp64 on U[0,1) inputs (gate 1e-5)"},
+        "config": config_for(wl_name, 1),
+        "details": {"kernel": f"{kernel} (auto dispatch)", "device": info["name"],
+                    "accuracy": "3xTF32 with fp32 promotion every 128 k: normwise relerr <= 2.6e-6 vs fp64 on U[0,1) inputs (gate 1e-5)"},
         "e2e": {"value": flops / e2e_ms / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": (M * K + K * N) * 4, "d2h_bytes_per_step": M * N * 4,
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "sgemm_cuda(host pointers, pinned)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": k1_traffic_bytes(wl_name),
-                     "peak_basis": f"{peaks['source']} bf16 dense burst {peaks['bf16_burst']:.1f} TFLOP/s / 2 (TF32) / 3 (3xTF32)",
+                     "traffic": traffic, "traffic_source": traffic_source, "algorithmic_bytes": 4 * (M * K + K * N + M * N),
+                     "peak_basis": (f"{peaks['source']} bf16 dense burst {peaks['bf16_burst']:.1f} TFLOP/s / 2 (TF32) / 3 (3xTF32)" if kernel == "3xtf32"
+                                    else "FP32 FFMA: SMs x 128 lanes x 2 flop x max SM clock"),
                      "kernel_ms_avg": avg_ms, "kernel_ms_min": min_ms,
                      "nominal_frac": achieved / 375.0},
         "cpu_baseline": {"value": cpu_tf, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
     }
+    if sustained is not None:
+        line["sustained"] = sustained
+    if c5_1gpu is not None:
+        line["c5_1gpu"] = c5_1gpu
+    if config1 is not None:
+        line["config1_host"] = config1
     if shapes is not None:
         line["other_shapes"] = shapes
     print(json.dumps(line), flush=True)
@@ -468,13 +597,13 @@ def run_multi(args, wl_name):
             "metric": "SGEMM TFLOP/s", "value": flops / ms / 1e9, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "grid": f"{plan.pr}x{plan.pc}", "k_slabs": plan.L,
+            "config": config_for(wl_name, world),
+            "details": {"grid": f"{plan.pr}x{plan.pc}", "k_slabs": plan.L,
                        "transport": sg.transport,
                        "timed_region": "owner-rooted panel distribution (%s) + local GEMMs, distribution included, max over ranks"
                                        % ("NCCL broadcast" if sg.transport == "nccl" else "copy-engine peer pull over NVLink"),
                        "compute_only_tflops": flops / ms_compute / 1e9, "compute_only_ms": ms_compute,
-                       "recv_bytes_per_rank": plan.recv_bytes(), "verified_sampled_relerr_max_over_ranks": verr,
-                       "l2_policy": "inputs larger than L2 (per-GPU panels %.1f GB)" % ((plan.mloc * K + K * plan.nloc) * 4 / 1e9)},
+                       "recv_bytes_per_rank": plan.recv_bytes(), "verified_sampled_relerr_max_over_ranks": verr},
             "e2e": {"value": flops / e2e_ms / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": int(tsum[1].item()),
                     "d2h_bytes_per_step": int(tsum[2].item()), "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "api": "ShardedGemm.run with owned slabs uploaded from pinned host memory and the C block downloaded each step"},
@@ -497,12 +626,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None] + list(WORKLOADS))
     ap.add_argument("--no-shapes", action="store_true", help="skip the side table of the other BASELINE shapes (N = 1 only)")
+    ap.add_argument("--no-ncu", action="store_true", help="do not re-run under ncu for roofline.traffic (use the committed capture)")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--dist", default=os.environ.get("UGEMM_BENCH_DIST", "p2p"), choices=["nccl", "p2p"],
                     help="panel transport for --gpus N > 1: NCCL broadcast or copy-engine peer pull")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl_name = args.workload or ("c2" if max(args.gpus, world) == 1 else "c5")
+    if args.traffic_child:
+        return run_traffic_child(wl_name)
     if args.impl == "reference":
         return run_reference_impl(args, wl_name)
     if world > 1:
