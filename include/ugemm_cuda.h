@@ -21,6 +21,15 @@
  *   Elements of C outside the M x N region (ld padding) are never written.
  *   Dimensions and leading dimensions stay `int` for drop-in compatibility; all internal
  *   offsets are 64-bit (32768 x 32768 operands are supported).
+ *   Non-finite inputs: K2 (plain fp32) propagates NaN / +-Inf exactly like the reference's loops.  K1 (3xTF32) marks the same
+ *   entries of C non-finite, but an entry the reference reports as +-Inf may come out as NaN: the error-compensation term
+ *   a_big * b_small is Inf * 0 whenever the other operand is exactly representable in TF32 (tests/test_parity_gpu.py::
+ *   test_non_finite_inputs).  Entries whose inputs are all finite are unaffected.
+ *
+ * Threading: the backend is process-global and lives on ONE device (like the reference's single cl context, ocl.h:141-193).
+ * The host-pointer entry points serialise on an internal lock (they share the staging arena).  The *_dev entry points may be
+ * called from several host threads on their own streams; each call binds the calling thread to the backend's device.
+ * sgemm_cuda_last_kernel / _last_repacked / _launch_count / _last_error report the most recent call of ANY thread.
  */
 #ifndef UGEMM_CUDA_H
 #define UGEMM_CUDA_H
@@ -43,7 +52,10 @@ enum {
  * device setup in ocl.h:141-249 (oclSetup / oclKernel / oclKernelArgs) and gpgpu_gl4.h:142-169 (coInit).
  * `device` = CUDA ordinal (-1: $UGEMM_CUDA_DEVICE or 0).  `arena_bytes` = initial size of the device
  * staging arena used by the host-pointer entry points (0: grow on demand), like the single cl buffer the
- * OpenCL backend sizes up front.  Returns 0 on success; on failure returns non-zero and sets last_error. */
+ * OpenCL backend sizes up front.  Returns 0 on success; on failure returns non-zero and sets last_error.
+ * Calling it again is a no-op for the same device (the arena grows if asked) and an ERROR for another device: call
+ * sgemm_cuda_finish first.  $UGEMM_K1_FLAGS (tuning / A-B switches of K1) is read here; its ablation bits, which make
+ * results wrong, are rejected unless $UGEMM_K1_ABLATION=1. */
 int  sgemm_cuda_init(int device, size_t arena_bytes);
 void sgemm_cuda_finish(void);
 
@@ -70,7 +82,8 @@ int sgemm_cuda_dev(int mode, void *stream, char major, char transA, char transB,
 /* ---- strided batch: `batch` problems of one shape in ONE launch; instance b uses A + b*strideA, B + b*strideB,
  * C + b*strideC (strides in elements).  This is the stacked-instance layout of the reference's test_sgemm (11 instances,
  * a is (11*M) x lda etc., check_sgemm.c:111-124,242-246), which the reference walks one call at a time.  K1 needs
- * strideA and strideB to be multiples of 4 in addition to the usual rule; otherwise K2.  No operand repacking here. */
+ * strideA and strideB to be multiples of 4 in addition to the usual rule; otherwise K2.  No operand repacking here.
+ * Strides must be non-negative and strideC must keep the instances of C apart; with alpha == 0 or K == 0 A and B are not read. */
 void sgemm_cuda_batched(char major, char transA, char transB, int M, int N, int K, float alpha,
                         const float *A, int lda, long long strideA, const float *B, int ldb, long long strideB,
                         float beta, float *C, int ldc, long long strideC, int batch);             /* host pointers, blocking */

@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 U = 2.0 ** -24
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ugemm_golden.npz")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def bounds(K):
@@ -301,6 +302,59 @@ def test_config4_tall_skinny_sampled(u):
         assert e <= TOL
 
 
+def test_non_finite_inputs(u):
+    """Inf / NaN in A or B (include/ugemm_cuda.h, "Non-finite inputs").  K2 propagates them like the reference's loops: the same
+    entries are NaN, +Inf, -Inf.  K1 marks the same entries non-finite (an Inf of the reference may be a NaN there) and leaves
+    every entry with finite inputs within the gate."""
+    M, N, K = 256, 256, 128
+    A, lda, B, ldb, Cm, ldc = O.make_problem("R", "N", "N", M, N, K, seed=77, lo=-0.5, hi=0.5)
+    A = A.copy(); B = B.copy()
+    A[3 * lda + 5] = np.inf           # row 3 of C
+    A[100 * lda + 64] = -np.inf       # row 100
+    A[200 * lda + 127] = np.nan       # row 200
+    B[17 * ldb + 9] = np.inf          # column 9
+    B[40 * ldb + 130] = 1.0           # exactly representable in TF32: b_small == 0 -> K1's Inf * 0
+    with np.errstate(invalid="ignore", over="ignore"):
+        want = oracle14("R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc).reshape(M, ldc)[:, :N]
+    fin = np.isfinite(want)
+    assert not fin[3].any() and not fin[100].any() and not fin[200].any() and not fin[:, 9].any() and fin.sum() == (M - 3) * (N - 1)
+    for mode in ("simt", "3xtf32"):
+        got = gpu14(u, mode, "R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc).reshape(M, ldc)[:, :N]
+        assert u.last_kernel() == mode
+        assert np.array_equal(np.isfinite(got), fin), mode
+        e = np.linalg.norm(got[fin].astype(np.float64) - want[fin]) / np.linalg.norm(want[fin].astype(np.float64))
+        assert e <= TOL, (mode, e)
+        if mode == "simt":
+            assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.sign(got[np.isinf(got)]), np.sign(want[np.isinf(want)]))
+        else:   # K1: at least the entries of row 3 whose other factors have a non-zero small part keep their Inf
+            assert np.isinf(got[3]).sum() > 0 and np.isnan(got[200]).all()
+
+
+def test_second_init_on_another_device_is_an_error(u):
+    """One backend, one device: sgemm_cuda_init on a different ordinal while initialised must fail loudly."""
+    u.sgemm_cuda_init(0)                      # same device: fine
+    with pytest.raises(u.UgemmCudaError):
+        u.sgemm_cuda_init(1)
+    u.sgemm_cuda_init(0)
+    A, lda, B, ldb, Cm, ldc = O.make_problem("R", "N", "N", 64, 64, 64, seed=5)
+    gpu14(u, "auto", "R", "N", "N", 64, 64, 64, 1.0, A, lda, B, ldb, 0.0, Cm, ldc)   # the backend is still usable
+
+
+def test_ablation_flags_need_an_opt_in():
+    """UGEMM_K1_FLAGS with result-corrupting bits is rejected at init unless UGEMM_K1_ABLATION=1 (fresh process each)."""
+    import subprocess
+    import sys
+    code = "import ugemm_b200 as u\ntry:\n    u.sgemm_cuda_init(0); print('INIT-OK')\nexcept u.UgemmCudaError as e:\n    print('INIT-ERR', e)\n"
+    env = dict(os.environ, UGEMM_K1_FLAGS="9")
+    env.pop("UGEMM_K1_ABLATION", None)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=ROOT).stdout
+    assert "INIT-ERR" in out and "ablation" in out
+    out = subprocess.run([sys.executable, "-c", code], env=dict(env, UGEMM_K1_ABLATION="1"), capture_output=True, text=True, cwd=ROOT).stdout
+    assert "INIT-OK" in out
+    out = subprocess.run([sys.executable, "-c", code], env=dict(env, UGEMM_K1_FLAGS="2049"), capture_output=True, text=True, cwd=ROOT).stdout
+    assert "INIT-OK" in out                    # tuning bits (collector, stream-K off) are always allowed
+
+
 def test_config5_32768_sampled(u):
     """BASELINE config 5 (32768^3 NN, alpha=1, beta=0, device-generated operands): 32 sampled rows -- 4 slabs of 8, one of them
     straddling the M/2 block boundary of every grid -- against the reference's sgemm_avx (sgemm_avx256.h:392) on the same rows
@@ -397,6 +451,52 @@ def test_batched_stacked_instances(u, case):
         assert e <= TOL, (b, e)
         if pad[2]:
             assert np.array_equal(got[b * sC:(b + 1) * sC].reshape(cr, ldc)[:, cc:], C0[b * sC:(b + 1) * sC].reshape(cr, ldc)[:, cc:])
+
+
+def test_batched_host_scale_only_and_stride_checks(u):
+    """sgemm_cuda_batched (host pointers): K == 0 / alpha == 0 never read A or B (NULL is legal, transposed operands included);
+    bad strides are an error that leaves C untouched."""
+    M, N, batch, ldc = 37, 29, 3, 32
+    sC = M * ldc
+    C0 = O.fill_uniform(batch * sC, 911, -0.5, 0.5)
+    for K, alpha, ta in ((0, 1.5, "T"), (16, 0.0, "N"), (0, 0.0, "T")):
+        got = C0.copy()
+        u.sgemm_cuda_batched("R", ta, "N", M, N, K, alpha, None, max(M, K, 1), 0, None, N, 0, 0.5, got, ldc, sC, batch)
+        want = C0.copy().reshape(batch, M, ldc)
+        want[:, :, :N] *= np.float32(0.5)
+        assert np.array_equal(got.reshape(batch, M, ldc), want)
+    A = O.fill_uniform(batch * M * 16, 912)
+    B = O.fill_uniform(batch * 16 * N, 913)
+    for strides in ((-1, 16 * N, sC), (M * 16, -5, sC), (M * 16, 16 * N, sC - 40)):
+        got = C0.copy()
+        with pytest.raises(u.UgemmCudaError):
+            u.sgemm_cuda_batched("R", "N", "N", M, N, 16, 1.0, A, 16, strides[0], B, N, strides[1], 0.0, got, ldc, strides[2], batch)
+        assert np.array_equal(got, C0)
+    got = C0.copy()   # K == 0 and beta == 1: quick return
+    u.sgemm_cuda_batched("R", "N", "N", M, N, 0, 1.0, None, 1, 0, None, N, 0, 1.0, got, ldc, sC, batch)
+    assert np.array_equal(got, C0)
+
+
+def test_pipelined_host_path_uses_one_kernel_for_every_panel(u):
+    """M = 4097 on the panel-pipelined host path (>= 64 MB in flight): the one-row tail joins the previous panel and every panel runs
+    the kernel chosen for the whole problem (K1).  (Not bit-identical to the one-shot launch: the stream-K tail cuts
+    different tiles along K in the two launches, which regroups -- not changes -- the fp32 partial sums.)"""
+    M, N, K = 4097, 2048, 2048
+    A, lda, B, ldb, Cm, ldc = O.make_problem("R", "N", "N", M, N, K, seed=321, lo=-0.5, hi=0.5)
+    piped = gpu14(u, "auto", "R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc)
+    assert u.last_kernel() == "3xtf32"
+    dA, dB, dC = u.DeviceBuffer(A.size).upload(A), u.DeviceBuffer(B.size).upload(B), u.DeviceBuffer(Cm.size)
+    u.sgemm_cuda_dev("3xtf32", None, "R", "N", "N", M, N, K, 1.0, dA, lda, dB, ldb, 0.0, dC, ldc)
+    u.sync()
+    whole = dC.download()
+    rows = np.r_[0:8, 2040:2056, 4088:4097]
+    want = (A.reshape(M, K)[rows].astype(np.float64) @ B.reshape(K, N).astype(np.float64))
+    for got in (piped, whole):
+        g = got.reshape(M, N)[rows]
+        assert np.linalg.norm(g - want) / np.linalg.norm(want) <= TOL
+    assert O.relerr("R", M, N, whole, piped, N) <= 2e-6
+    for d in (dA, dB, dC):
+        d.free()
 
 
 @pytest.mark.parametrize("ta", ["N", "T"])

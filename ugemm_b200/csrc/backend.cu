@@ -9,6 +9,7 @@
 #include "../../include/ugemm_cuda.h"
 #include "common.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -20,7 +21,7 @@ using namespace ugemm;
 namespace {
 
 struct State {
-	bool ready = false;
+	std::atomic<bool> ready{false};
 	int device = 0;
 	int sm_count = 0;
 	int clock_khz = 0;
@@ -34,20 +35,25 @@ struct State {
 	char *arena = nullptr;
 	size_t arena_bytes = 0;
 	K1Tuning tuning = {4, 0, 0, 1};   // promote every 4 k-blocks (128 k), truncation split, CTA pairing by problem size, A collector
-	int last_kernel = 0;
-	int last_conv_fused = 0;         // last convolution ran as an implicit GEMM (no column matrix)
+	// reports: written by whichever host thread launched last, read through the sgemm_cuda_last_* getters
+	std::atomic<int> last_kernel{0};
+	std::atomic<int> last_conv_fused{0};   // last convolution ran as an implicit GEMM (no column matrix)
 	int conv_fusion = -1;            // -1 by rule, 0 never, 1 whenever the hard constraints allow
-	int last_repacked = 0;           // last auto launch copied an operand to an aligned leading dimension first
+	std::atomic<int> last_repacked{0};     // last auto launch copied an operand to an aligned leading dimension first
 	int sm_limit = 0;                // 0 = all SMs; otherwise K1's persistent grid is capped (leaves SMs to NCCL)
-	unsigned long long launches = 0;
+	std::atomic<unsigned long long> launches{0};
 } g;
 
-std::mutex g_mu;
+// serialises init / finish and the host-pointer entry points (they share the staging arena and the three streams); recursive
+// because a host-pointer call initialises the library lazily while it already holds the lock
+std::recursive_mutex g_mu;
+std::mutex g_err_mu;    // the sticky error string
 char g_err[512];
-bool g_has_err = false;
+std::atomic<bool> g_has_err{false};
 
 void set_error(const char *fmt, ...)
 {
+	std::lock_guard<std::mutex> lk(g_err_mu);
 	va_list ap;
 	va_start(ap, fmt);
 	vsnprintf(g_err, sizeof g_err, fmt, ap);
@@ -65,10 +71,14 @@ void set_error(const char *fmt, ...)
 		}                                                                                    \
 	} while (0)
 
+// Every entry point starts here: lazy init, then bind the CALLING thread to the backend's device (a host thread other than
+// the one that initialised the library starts on device 0, whatever device the backend lives on).
 int ensure_init()
 {
-	if (g.ready) return 0;
-	return sgemm_cuda_init(-1, 0);
+	if (!g.ready.load(std::memory_order_acquire) && sgemm_cuda_init(-1, 0)) return 1;
+	int cur = -1;
+	if (cudaGetDevice(&cur) != cudaSuccess || cur != g.device) CU_TRY(cudaSetDevice(g.device), "cudaSetDevice");
+	return 0;
 }
 
 size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -225,8 +235,12 @@ cudaError_t copy2d(float *dst, const float *src, long long ld, long long lines, 
 // timed region is dominated by the two PCIe transfers.  Here op(B) goes up first, then row panels of op(A) (and of C
 // when beta != 0) stream up on one stream while the GEMM of the previous panel runs on a second and the finished C
 // panel streams down on a third (PCIe is full duplex).  Same device layout and leading dimensions as the one-shot
-// path, so kernel choice and results are identical.  Host buffers should be pinned (ugemm_cuda_malloc_host) for the
+// path.  The kernel is chosen ONCE, on the whole problem, and forced for every panel (a ragged last panel must not fall to
+// another kernel with another rounding than the rest of C), and a last panel of fewer than 256 rows is merged into the
+// one before it.  Host buffers should be pinned (ugemm_cuda_malloc_host) for the
 // copies to be truly asynchronous; pageable memory still works, just without the overlap.
+// On a failure in the middle of the pipeline the panels already downloaded stay in the caller's C (partial result; the
+// error is reported): a CUDA failure at that point leaves the context unusable anyway.
 void run_host_pipelined(int mode, const Problem &p, float *dA, float *dB, float *dC)
 {
 	const long long b_lines = p.b_kmajor ? p.N : p.K, b_cols = p.b_kmajor ? p.K : p.N;
@@ -235,11 +249,19 @@ void run_host_pipelined(int mode, const Problem &p, float *dA, float *dB, float 
 	if (panels > 16) panels = 16;
 	long long mb = ((p.M + panels - 1) / panels + 255) / 256 * 256;
 	panels = (int)((p.M + mb - 1) / mb);
+	if (panels > 1 && p.M - (long long)(panels - 1) * mb < 256) panels--;      // the ragged tail joins the previous panel
+	if (mode == UGEMM_MODE_AUTO) {
+		Problem whole = p; whole.A = dA; whole.B = dB; whole.C = dC;
+		// rule (1) -> K1 for every panel; rule (2) (repack) stays per panel in auto mode: every panel then has >= 256 rows,
+		// so all of them repack and run K1; rule (3) -> K2 for every panel
+		if (auto_prefers_k1(whole)) mode = UGEMM_MODE_3XTF32;
+		else if (!auto_wants_repack(whole)) mode = UGEMM_MODE_SIMT;
+	}
 	cudaStream_t s_up = g.stream_h2d, s_cmp = g.stream, s_dn = g.stream_d2h;
 	cudaError_t e = copy2d(dB, p.B, p.ldb, b_lines, b_cols, cudaMemcpyHostToDevice, s_up);
 	int rc = 0;
 	for (int i = 0; i < panels && e == cudaSuccess && !rc; i++) {
-		const long long m0 = i * mb, mm = (p.M - m0 < mb) ? p.M - m0 : mb;
+		const long long m0 = i * mb, mm = (i == panels - 1) ? p.M - m0 : mb;
 		// panel i of op(A): rows m0.. of an M x K array (k-major) or columns m0.. of a K x M array
 		if (p.a_kmajor) e = copy2d(dA + m0 * p.lda, p.A + m0 * p.lda, p.lda, mm, p.K, cudaMemcpyHostToDevice, s_up);
 		else e = cudaMemcpy2DAsync(dA + m0, (size_t)p.lda * 4, p.A + m0, (size_t)p.lda * 4, (size_t)mm * 4, (size_t)p.K, cudaMemcpyHostToDevice, s_up);
@@ -272,7 +294,7 @@ void run_host_pipelined(int mode, const Problem &p, float *dA, float *dB, float 
 void run_host(int mode, char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda,
               const float *B, int ldb, float beta, float *C, int ldc)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	if (ensure_init()) return;
 	Problem p;
 	if (normalise(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, &p)) return;
@@ -360,10 +382,17 @@ extern "C" {
 
 int sgemm_cuda_init(int device, size_t arena_bytes)
 {
-	if (g.ready) return 0;
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	if (device < 0) {
 		const char *env = getenv("UGEMM_CUDA_DEVICE");
-		device = env ? atoi(env) : 0;
+		device = env ? atoi(env) : (g.ready ? g.device : 0);
+	}
+	if (g.ready) {
+		// one backend, one device (like the reference's process-global cl context, ocl.h:141-193): a second init on ANOTHER
+		// device is an error, not a silent no-op that leaves the caller's buffers on the wrong GPU
+		if (device != g.device) { set_error("sgemm_cuda_init(%d): the backend is already initialised on device %d; call sgemm_cuda_finish first", device, g.device); return 1; }
+		if (arena_bytes) return ensure_arena(arena_bytes);
+		return 0;
 	}
 	int count = 0;
 	CU_TRY(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
@@ -397,15 +426,27 @@ int sgemm_cuda_init(int device, size_t arena_bytes)
 		}
 		cudaGetLastError();
 	}
-	if (const char *f = getenv("UGEMM_K1_FLAGS")) g.tuning.flags = atoi(f);   // overrides the default (bit0 = A collector on)   // debug / ablation, see common.cuh
-	g.ready = true;
+	if (const char *f = getenv("UGEMM_K1_FLAGS")) {
+		// overrides the default (bit0 = A collector on).  Bits 1-6 are ablation / profiling switches that make K1's RESULTS WRONG
+		// (common.cuh): a stray environment variable must not silently corrupt a production run, so they need an explicit opt-in.
+		const int flags = atoi(f), unsafe = flags & (2 | 4 | 8 | 16 | 32 | 64);
+		const char *opt = getenv("UGEMM_K1_ABLATION");
+		if (unsafe && !(opt && atoi(opt) == 1)) {
+			set_error("UGEMM_K1_FLAGS=%d sets ablation bits 0x%x that corrupt results; set UGEMM_K1_ABLATION=1 to allow them (bottleneck analysis only)", flags, unsafe);
+			return 1;
+		}
+		g.tuning.flags = flags;
+	}
+	g.ready.store(true, std::memory_order_release);
 	if (arena_bytes && ensure_arena(arena_bytes)) { g.ready = false; return 1; }
 	return 0;
 }
 
 void sgemm_cuda_finish(void)
 {
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	if (!g.ready) return;
+	cudaSetDevice(g.device);
 	cudaStreamSynchronize(g.stream);
 	if (g.arena) cudaFree(g.arena);
 	g.arena = nullptr; g.arena_bytes = 0;
@@ -466,23 +507,36 @@ int sgemm_cuda_batched_dev(int mode, void *stream, char major, char ta, char tb,
 void sgemm_cuda_batched(char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda, long long strideA,
                         const float *B, int ldb, long long strideB, float beta, float *C, int ldc, long long strideC, int batch)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
-	if (ensure_init() || batch <= 0) return;
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
+	if (ensure_init()) return;
+	if (batch < 0) { set_error("negative batch count"); return; }
+	if (batch == 0) return;
 	Problem p;
 	if (normalise(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, &p)) return;
 	if (p.M == 0 || p.N == 0) return;
+	if ((p.alpha == 0.f || p.K == 0) && p.beta == 1.f) return;          // quick return of the reference (sgemm_avx256.h:410)
 	const bool swapped = (major == 'C' || major == 'c');
 	const long long sA = swapped ? strideB : strideA, sB = swapped ? strideA : strideB;
+	// same stride rules as the device-pointer entry point, checked BEFORE any size arithmetic uses them
+	if (batch > 1 && (sA < 0 || sB < 0 || strideC < (long long)(p.M - 1) * p.ldc + p.N)) {
+		set_error("batch strides must be non-negative and strideC must not make instances of C overlap");
+		return;
+	}
+	// alpha == 0 or K == 0: A and B are never read (the caller may pass NULL), only C <- beta*C happens -- like run_host
+	const bool need_ab = !(p.alpha == 0.f || p.K == 0);
 	const long long a_lines = p.a_kmajor ? p.M : p.K, a_cols = p.a_kmajor ? p.K : p.M;
 	const long long b_lines = p.b_kmajor ? p.N : p.K, b_cols = p.b_kmajor ? p.K : p.N;
-	const size_t a_n = (size_t)((batch - 1) * sA + (a_lines - 1) * p.lda + a_cols);
-	const size_t b_n = (size_t)((batch - 1) * sB + (b_lines - 1) * p.ldb + b_cols);
+	const size_t a_n = need_ab ? (size_t)((batch - 1) * sA + (a_lines - 1) * p.lda + a_cols) : 0;
+	const size_t b_n = need_ab ? (size_t)((batch - 1) * sB + (b_lines - 1) * p.ldb + b_cols) : 0;
 	const size_t c_n = (size_t)((batch - 1) * strideC + (long long)(p.M - 1) * p.ldc + p.N);
 	const size_t offB = align_up(a_n * 4, 256), offC = align_up(offB + b_n * 4, 256);
 	if (ensure_arena(offC + c_n * 4)) return;
 	float *dA = reinterpret_cast<float *>(g.arena), *dB = reinterpret_cast<float *>(g.arena + offB), *dC = reinterpret_cast<float *>(g.arena + offC);
-	cudaError_t e = cudaMemcpyAsync(dA, p.A, a_n * 4, cudaMemcpyHostToDevice, g.stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(dB, p.B, b_n * 4, cudaMemcpyHostToDevice, g.stream);
+	cudaError_t e = cudaSuccess;
+	if (need_ab) {
+		e = cudaMemcpyAsync(dA, p.A, a_n * 4, cudaMemcpyHostToDevice, g.stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(dB, p.B, b_n * 4, cudaMemcpyHostToDevice, g.stream);
+	}
 	// C travels whole (padding included, so the download restores it bit for bit); needed up front when beta != 0
 	if (e == cudaSuccess) e = cudaMemcpyAsync(dC, p.C, c_n * 4, cudaMemcpyHostToDevice, g.stream);
 	if (e != cudaSuccess) { set_error("batched H2D failed: %s", cudaGetErrorString(e)); return; }
@@ -558,7 +612,7 @@ int sgemm_cuda_time_dev(int mode, int iters, int warmup, char major, char ta, ch
 }
 
 const char *sgemm_cuda_last_error(void) { return g_has_err ? g_err : nullptr; }
-void sgemm_cuda_clear_error(void) { g_has_err = false; g_err[0] = 0; }
+void sgemm_cuda_clear_error(void) { std::lock_guard<std::mutex> lk(g_err_mu); g_has_err = false; g_err[0] = 0; }
 int sgemm_cuda_last_kernel(void) { return g.last_kernel; }
 int sgemm_cuda_last_repacked(void) { return g.last_repacked; }
 int sgemm_cuda_last_conv_fused(void) { return g.last_conv_fused; }
@@ -804,7 +858,7 @@ int convolution_cuda_dev(int mode, void *stream, const float *d_inputs, int ich,
 static void conv_host(const float *inputs, int ich, int w, int h, const float *weights, int k, int pad, int stride, float *outputs,
                       int ch, const float *bias, float slope)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	if (ensure_init()) return;
 	if (ich <= 0 || ch <= 0 || k <= 0 || stride <= 0 || pad < 0 || h + 2 * pad < k || w + 2 * pad < k) { set_error("convolution: bad geometry"); return; }
 	const long long ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1, npix = ho * wo, kk = (long long)ich * k * k;
@@ -826,7 +880,7 @@ static void conv_host(const float *inputs, int ich, int w, int h, const float *w
 
 void im2col_cuda(const float *im, int channels, int height, int width, int k, int pad, int stride, float *col)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	if (ensure_init()) return;
 	if (k <= 0 || stride <= 0 || pad < 0 || height + 2 * pad < k || width + 2 * pad < k) { set_error("im2col: bad geometry"); return; }
 	const long long ho = (height + 2 * pad - k) / stride + 1, wo = (width + 2 * pad - k) / stride + 1;
@@ -862,7 +916,7 @@ int saxpy_cuda_dev(void *stream, int N, float alpha, const float *dx, int incx, 
 
 void saxpy_cuda(int N, float alpha, const float *x, int incx, float *y, int incy)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	if (ensure_init()) return;
 	if (N < 0 || incx < 1 || incy < 1) { set_error("saxpy: N must be >= 0 and incx, incy >= 1 (N=%d incx=%d incy=%d)", N, incx, incy); return; }
 	if (N == 0 || alpha == 0.f) return;
@@ -906,7 +960,7 @@ int sgemv_cuda_dev(void *stream, char trans, int M, int N, float alpha, const fl
 
 void sgemv_cuda(char trans, int M, int N, float alpha, const float *A, int lda, const float *x, int incx, float beta, float *y, int incy)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	if (ensure_init()) return;
 	if (gemv_check(&trans, M, N, lda, incx, incy)) return;
 	if (M == 0) return;
@@ -978,7 +1032,7 @@ int dgemm_cuda_dev(void *stream, char major, char ta, char tb, int M, int N, int
 void dgemm_cuda(char major, char ta, char tb, int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb,
                 double beta, double *C, int ldc)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	if (ensure_init()) return;
 	DProblem p;
 	if (dnormalise(major, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, &p)) return;
@@ -1131,7 +1185,7 @@ cudaError_t mg_copy(float *dst, long long dld, const float *src, long long sld, 
 
 int sgemm_cuda_mgpu_init(int ngpus)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	if (mg.n) return ngpus == mg.n ? 0 : (set_error("sgemm_cuda_mgpu_init: already initialised with %d GPUs", mg.n), 1);
 	if (ensure_init()) return 1;
 	if (g.device != 0) { set_error("sgemm_cuda_mgpu_init: the backend must be initialised on device 0 (it is on %d)", g.device); return 1; }
@@ -1173,7 +1227,7 @@ int sgemm_cuda_mgpu_init(int ngpus)
 
 void sgemm_cuda_mgpu_finish(void)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	for (int d = 0; d < mg.n; d++) {
 		MgDev &D = mg.d[d];
 		cudaSetDevice(d);
@@ -1213,7 +1267,7 @@ int ugemm_cuda_device_count(void)
 int sgemm_cuda_mgpu(char major, char ta, char tb, int M, int N, int K, float alpha, const float *A, int lda,
                     const float *B, int ldb, float beta, float *C, int ldc, int pr, int pc, int overlap, float *timings_ms)
 {
-	std::lock_guard<std::mutex> lk(g_mu);
+	std::lock_guard<std::recursive_mutex> lk(g_mu);
 	if (timings_ms) for (int i = 0; i < 5; i++) timings_ms[i] = 0.f;
 	if (!mg.n) { set_error("sgemm_cuda_mgpu: call sgemm_cuda_mgpu_init first"); return 1; }
 	if (pr < 1 || pc < 1 || (long long)pr * pc > mg.n) { set_error("sgemm_cuda_mgpu: grid %d x %d needs %lld GPUs, %d initialised", pr, pc, (long long)pr * pc, mg.n); return 1; }

@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda.h>
+#include <cstring>
 #include <mutex>
 
 namespace ugemm {
@@ -77,7 +78,11 @@ struct K1Params {
 	// kernel size, padding, 32-channel blocks per kernel position, pixels per output plane
 	int cv_wp, cv_wo, cv_ho, cv_k, cv_pad, cv_cblocks, cv_npix, cv_stride;
 	unsigned *diag;
-	int *sched;        // [0] next tile index (atomic), [1] clusters finished; self-resetting
+	// dynamic scheduler: *sched is a device counter that only ever grows; a launch claims the values [sched_base, sched_base +
+	// num_tiles + clusters) (every cluster makes exactly one claim past the end), so the host knows the base of the next launch
+	// on this slot without any reset on the device (nothing to leave dirty, nothing for the last cluster to re-arm)
+	unsigned *sched;
+	unsigned sched_base;
 	long long *prof;   // flags & 32: per-role cycle counters of the first 4 CTAs (16 slots each), debug only
 };
 
@@ -166,6 +171,10 @@ __device__ __forceinline__ int next_tile(uint32_t bar_base, int &n, bool warp_co
 template <bool PROF> __device__ __forceinline__ long long tick() { return PROF ? clock64() : 0LL; }
 
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float small_part(float x, float big)
+{
+	return (__float_as_uint(x) & 0x7FFFFFFFu) == 0x7F800000u ? 0.f : x - big;
+}
 __device__ __forceinline__ float tf32_rna(float x)
 {
 	uint32_t r;
@@ -379,7 +388,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					const int rounds = P.sk_full / num_clusters;
 					tile = n < rounds ? n * num_clusters + cluster_id : (n == rounds && P.sk_full + cluster_id < P.num_tiles ? P.sk_full + cluster_id : -1);
 				} else {
-					tile = atomicAdd(P.sched, 1);
+					tile = (int)(atomicAdd(P.sched, 1u) - P.sched_base);
 					if (tile >= P.num_tiles) tile = -1;
 				}
 				asm volatile("st.shared.b32 [%0], %1;" ::"r"(slots + 4u * slot), "r"(tile) : "memory");
@@ -391,11 +400,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				} else {
 					mbar_arrive(full);
 				}
-				if (tile < 0) {
-					// the last cluster to run dry re-arms the counters for the next launch using this slot
-					if (atomicAdd(P.sched + 1, 1) == num_clusters - 1) { P.sched[0] = 0; P.sched[1] = 0; __threadfence(); }
-					break;
-				}
+				if (tile < 0) break;
 			}
 		}
 		__syncwarp();   // reconverge before the .aligned teardown barrier
@@ -434,7 +439,8 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 						} else {
 							b.x = tf32_rna(v[i].x); b.y = tf32_rna(v[i].y); b.z = tf32_rna(v[i].z); b.w = tf32_rna(v[i].w);
 						}
-						sm.x = v[i].x - b.x; sm.y = v[i].y - b.y; sm.z = v[i].z - b.z; sm.w = v[i].w - b.w;
+						// x = +-Inf: Inf - Inf would make `small` NaN and turn the reference's +-Inf results into NaN; its small part is 0
+						sm.x = small_part(v[i].x, b.x); sm.y = small_part(v[i].y, b.y); sm.z = small_part(v[i].z, b.z); sm.w = small_part(v[i].w, b.w);
 						if (P.flags & 2) continue;
 						sts128(raw + RAW_BYTES + off, sm);
 						if (P.split != 0) sts128(raw + off, b);
@@ -773,14 +779,48 @@ EncodeTiledFn encode_fn()
 	return fn;
 }
 
+// Tensor-map cache.  A descriptor is a pure function of (base, extents, pitches, box, swizzle); GEMM callers launch the same
+// operands again and again (every step of a benchmark loop, every K slab of the sharded driver, every instance walk of the
+// harness), so the encoded 128-byte maps are kept in a small per-thread table (no lock, no sharing) keyed by exactly those
+// arguments and cuTensorMapEncodeTiled runs only on a miss.
+struct MapKey {
+	const void *base; unsigned long long d0, d1, d2, d3, s0, s1, s2; unsigned b0, b1, b2, b3, e1, rank, swizzle, l2;
+	bool operator==(const MapKey &o) const { return memcmp(this, &o, sizeof *this) == 0; }
+};
+struct MapCache {
+	static constexpr int N = 64;
+	MapKey key[N]; CUtensorMap map[N]; bool used[N]; unsigned long long hits, misses;
+	MapCache() : hits(0), misses(0) { memset(key, 0, sizeof key); memset(used, 0, sizeof used); }
+};
+bool cached_encode(CUtensorMap *out, unsigned rank, const void *base, const cuuint64_t *gdim, const cuuint64_t *gstride, const cuuint32_t *box,
+                   const cuuint32_t *estr, CUtensorMapSwizzle sw, CUtensorMapL2promotion l2)
+{
+	EncodeTiledFn fn = encode_fn();
+	if (!fn) return false;
+	thread_local MapCache cache;
+	MapKey k;
+	memset(&k, 0, sizeof k);            // padding bytes too: the key is compared with memcmp
+	k.base = base; k.rank = rank; k.swizzle = (unsigned)sw; k.l2 = (unsigned)l2;
+	k.d0 = gdim[0]; k.d1 = gdim[1]; k.d2 = rank > 2 ? gdim[2] : 0; k.d3 = rank > 3 ? gdim[3] : 0;
+	k.s0 = gstride[0]; k.s1 = rank > 2 ? gstride[1] : 0; k.s2 = rank > 3 ? gstride[2] : 0;
+	k.b0 = box[0]; k.b1 = box[1]; k.b2 = rank > 2 ? box[2] : 0; k.b3 = rank > 3 ? box[3] : 0; k.e1 = estr[1];
+	unsigned long long h = reinterpret_cast<uintptr_t>(base) >> 4;
+	h = mix64(h ^ (k.d0 * 0x9E3779B97F4A7C15ull) ^ (k.d1 << 17) ^ (k.s0 << 29) ^ (k.s1 << 3) ^ ((unsigned long long)k.b1 << 50) ^ k.swizzle);
+	const int slot = (int)(h % MapCache::N);
+	if (cache.used[slot] && cache.key[slot] == k) { *out = cache.map[slot]; cache.hits++; return true; }
+	if (fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2,
+	       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+		return false;
+	cache.key[slot] = k; cache.map[slot] = *out; cache.used[slot] = true; cache.misses++;
+	return true;
+}
+
 // K-major operand: `rows` lines of `K` contiguous fp32, pitch ld  -> dims {K, rows, batch}, box {32, 128, 1}, SWIZZLE_128B
 // MN-major operand: `K` lines of `rows` contiguous fp32, pitch ld -> dims {rows, K, batch}, box {32, 32, 1}, SWIZZLE_128B_ATOM_32B
 // The third dimension walks the strided batch (extent 1 for a plain GEMM).
 bool make_operand_map(CUtensorMap *map, const float *base, long long rows, long long K, long long ld, bool kmajor,
                       int batch, long long stride)
 {
-	EncodeTiledFn fn = encode_fn();
-	if (!fn) return false;
 	cuuint64_t gdim[3], gstride[2];
 	cuuint32_t box[3], estr[3] = {1, 1, 1};
 	CUtensorMapSwizzle sw;
@@ -790,22 +830,17 @@ bool make_operand_map(CUtensorMap *map, const float *base, long long rows, long 
 	box[2] = 1;
 	gstride[0] = (cuuint64_t)ld * 4;
 	gstride[1] = (batch > 1) ? (cuuint64_t)stride * 4 : gstride[0] * gdim[1];   // any legal value when there is one instance
-	CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), gdim, gstride, box, estr,
-	                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-	return r == CUDA_SUCCESS;
+	return cached_encode(map, 3, base, gdim, gstride, box, estr, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
 // C (M lines of N fp32, pitch ldc) as the target of 32-row x 32-column box stores: dims {N, M, batch}, SWIZZLE_128B (the box's
 // 128-byte rows are staged swizzled so the epilogue's per-row 16-byte shared-memory stores are conflict-free)
 bool make_c_map(CUtensorMap *map, float *base, long long M, long long N, long long ldc, int batch, long long strideC)
 {
-	EncodeTiledFn fn = encode_fn();
-	if (!fn) return false;
 	cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)(batch > 0 ? batch : 1)};
 	cuuint64_t gstride[2] = {(cuuint64_t)ldc * 4, (batch > 1) ? (cuuint64_t)strideC * 4 : (cuuint64_t)ldc * 4 * (cuuint64_t)M};
 	cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
-	return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-	          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+	return cached_encode(map, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE);
 }
 
 unsigned *g_diag_host = nullptr, *g_diag_dev = nullptr;
@@ -840,15 +875,18 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 	static std::mutex init_mu;
 	std::lock_guard<std::mutex> init_lock(init_mu);
 	// dynamic-scheduler counters: a small pool so launches on different streams do not share a slot
-	static int *sched_pools[MAX_DEV] = {nullptr};
+	static unsigned *sched_pools[MAX_DEV] = {nullptr};
+	static unsigned sched_claimed[MAX_DEV][64] = {{0}};     // host shadow: value each device counter will have after the launches queued so far
 	static unsigned sched_next = 0;
 	constexpr unsigned SCHED_POOL = 64;
 	if (!sched_pools[dev]) {
-		if (cudaMalloc(&sched_pools[dev], SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return cudaErrorMemoryAllocation;
-		cudaMemset(sched_pools[dev], 0, SCHED_POOL * 2 * sizeof(int));
+		if (cudaMalloc(&sched_pools[dev], SCHED_POOL * sizeof(unsigned)) != cudaSuccess) return cudaErrorMemoryAllocation;
+		cudaMemset(sched_pools[dev], 0, SCHED_POOL * sizeof(unsigned));
 		cudaDeviceSynchronize();
 	}
-	P.sched = sched_pools[dev] + 2 * (sched_next++ % SCHED_POOL);
+	const unsigned sched_slot = sched_next++ % SCHED_POOL;
+	P.sched = sched_pools[dev] + sched_slot;
+	P.sched_base = sched_claimed[dev][sched_slot];
 	P.prof = nullptr;
 	static long long *prof_devs[MAX_DEV] = {nullptr};
 	const bool prof = !CONV && (t.flags & 32);
@@ -883,6 +921,9 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 	cfg.attrs = attr; cfg.numAttrs = 1;
 	cudaError_t le = prof ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true, false>, tmA, tmB, tmC, P)
 	                      : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false, CONV>, tmA, tmB, tmC, P);
+	// a dynamically scheduled launch advances its counter by one claim per tile plus one failed claim per cluster (a launch that
+	// the runtime rejected never ran; a kernel that trapped poisons the context, so no later launch can observe the slot)
+	if (le == cudaSuccess && P.sk_q <= 0) sched_claimed[dev][sched_slot] += (unsigned)P.num_tiles + (unsigned)clusters;
 	if (le == cudaSuccess && prof) {   // debug: per-role cycle breakdown of CTAs 0..3 on stderr
 		long long h[64];
 		if (cudaStreamSynchronize(stream) == cudaSuccess && cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -963,15 +1004,12 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 // output row x 32 input channels at one kernel position = 32 rows of 128 B, laid out like 32 rows of a dense K-major tile
 bool make_image_map(CUtensorMap *map, const ConvProblem &c)
 {
-	EncodeTiledFn fn = encode_fn();
-	if (!fn) return false;
 	cuuint64_t gdim[4] = {(cuuint64_t)c.cs, (cuuint64_t)c.w, (cuuint64_t)c.h, (cuuint64_t)c.nimg};
 	cuuint64_t gstride[3] = {(cuuint64_t)c.cs * 4, (cuuint64_t)c.cs * c.w * 4, (cuuint64_t)c.cs * c.w * c.h * 4};
 	// a strided convolution reads every stride-th pixel of the row: the box spans 32*stride pixels and the TMA element stride
 	// picks 32 of them
 	cuuint32_t box[4] = {32, (cuuint32_t)(32 * c.stride), 1, 1}, estr[4] = {1, (cuuint32_t)c.stride, 1, 1};
-	return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(c.in_hwc), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-	          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+	return cached_encode(map, 4, c.in_hwc, gdim, gstride, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
 template <int CG>
@@ -998,13 +1036,10 @@ cudaError_t launch_conv_cg(const ConvProblem &c, const K1Tuning &t, cudaStream_t
 	CUtensorMap tmC = tmA;
 	P.tma_store = 0;
 	if (P.vecC && c.wo % 4 == 0 && !(t.flags & 8192)) {
-		EncodeTiledFn fn = encode_fn();
 		cuuint64_t gdim[4] = {(cuuint64_t)c.wo, (cuuint64_t)c.ho, (cuuint64_t)c.ch, (cuuint64_t)c.nimg};
 		cuuint64_t gstride[3] = {(cuuint64_t)c.wo * 4, (cuuint64_t)npix * 4, (cuuint64_t)c.ch * npix * 4};
 		cuuint32_t box[4] = {32, 1, 32, 1}, estr[4] = {1, 1, 1, 1};
-		if (fn && fn(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-		             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-			P.tma_store = 1;
+		if (cached_encode(&tmC, 4, c.out, gdim, gstride, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE)) P.tma_store = 1;
 	}
 	return launch_with_tail<CG, true>(tmA, tmB, tmC, P, nt, t, stream, sm_count);
 }
