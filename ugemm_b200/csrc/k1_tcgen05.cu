@@ -33,6 +33,7 @@
 #include <cuda.h>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 namespace ugemm {
 
@@ -146,13 +147,25 @@ __device__ __host__ __forceinline__ Item decode_item(int item, int h, int sk_ful
 	return it;
 }
 
+// Arrive on a barrier that lives in the LEADER CTA of the pair, from either CTA, without a cluster-scope fence (see
+// ptx.cuh: mbar_arrive_remote): the leader arrives locally, the peer through the cluster address.  `heavy` (UGEMM_K1_FLAGS bit 14,
+// A/B runs) restores the round-1 form, a .release.cluster arrive from both CTAs.
+template <int CG>
+__device__ __forceinline__ void arrive_on_leader(uint32_t bar, uint32_t cta_rank, bool heavy)
+{
+	if (CG == 1) { mbar_arrive(bar); return; }
+	if (heavy) mbar_arrive_cluster(bar, 0);
+	else if (cta_rank == 0) mbar_arrive(bar);
+	else mbar_arrive_remote(bar, 0);
+}
+
 // ---- dynamic tile scheduler ------------------------------------------------------------------------------------
 // One thread per cluster (leader CTA, warp 2) claims tile indices from a global atomic counter and publishes them
 // through a 4-deep shared-memory ring to every role of both CTAs; a CTA pair that starts late (SMs busy with another
 // kernel, e.g. NCCL) simply claims fewer tiles.  sched_full[slot] (count 1, one per CTA) / sched_empty[slot] (leader
 // only; one arrival per consuming role) are mbarriers; a negative index ends the kernel.
 template <int CG>
-__device__ __forceinline__ int next_tile(uint32_t bar_base, int &n, bool warp_collective, int lane, unsigned *diag)
+__device__ __forceinline__ int next_tile(uint32_t bar_base, int &n, bool warp_collective, int lane, unsigned *diag, uint32_t cta_rank, bool heavy)
 {
 	const int slot = n & (SCHED_SLOTS - 1);
 	const uint32_t ph = (n / SCHED_SLOTS) & 1;
@@ -163,7 +176,7 @@ __device__ __forceinline__ int next_tile(uint32_t bar_base, int &n, bool warp_co
 	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tile) : "r"(bar_base + 8u * (14 + 2 * SCHED_SLOTS) + 4u * slot) : "memory");
 	if (warp_collective) __syncwarp();
 	if (!warp_collective || lane == 0) {
-		if (CG == 2) mbar_arrive_cluster(empty, 0); else mbar_arrive(empty);
+		arrive_on_leader<CG>(empty, cta_rank, heavy);
 	}
 	return tile;
 }
@@ -221,6 +234,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 	const int nkb = P.num_k_blocks;
 	const int kc = P.kc_blocks;
 	long long *prof = (PROF && P.prof && blockIdx.x < 4) ? P.prof + 16 * blockIdx.x : nullptr;
+	const bool heavy = (P.flags & 16384) != 0;
 
 	// ---- one-time setup --------------------------------------------------------------------------------
 	if (warp == 0 && lane == 0) {
@@ -262,7 +276,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			const uint64_t hintA = (P.flags & 128) ? L2_EVICT_LAST : (P.flags & 1024) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
 			const uint64_t hintB = (P.flags & 512) ? L2_EVICT_LAST : (P.flags & 256) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
 			int nt = 0;
-			for (int item; (item = next_tile<CG>(bar_base, nt, false, 0, P.diag)) >= 0;) {
+			for (int item; (item = next_tile<CG>(bar_base, nt, false, 0, P.diag, cta_rank, heavy)) >= 0;) {
 				for (int sg = 0; sg < 2; sg++) {
 				const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
 				if (wi.kb1 <= wi.kb0) continue;
@@ -321,7 +335,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			int it = 0, ci = 0;
 			long long w_xf = 0, w_te = 0; const long long t_begin = tick<PROF>();
 			int nt = 0;
-			for (int item; (item = next_tile<CG>(bar_base, nt, false, 0, P.diag)) >= 0;) {
+			for (int item; (item = next_tile<CG>(bar_base, nt, false, 0, P.diag, cta_rank, heavy)) >= 0;) {
 				for (int sg = 0; sg < 2; sg++) {
 				const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
 				if (wi.kb1 <= wi.kb0) continue;
@@ -412,7 +426,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		int it = 0;
 		long long w_full = 0, t_work = 0, t_fence = 0; const long long t_begin = tick<PROF>();
 		int nt = 0;
-		for (int item; (item = next_tile<CG>(bar_base, nt, true, lane, P.diag)) >= 0;) {
+		for (int item; (item = next_tile<CG>(bar_base, nt, true, lane, P.diag, cta_rank, heavy)) >= 0;) {
 			for (int sg = 0; sg < 2; sg++) {
 			const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
 			if (wi.kb1 <= wi.kb0) continue;
@@ -430,29 +444,37 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 					float4 v[8];
 #pragma unroll
 					for (int i = 0; i < 8; i++) v[i] = lds128(raw + (uint32_t)(t + 128 * (half * 8 + i)) * 16u);
+					// x = +-Inf: Inf - Inf would make `small` NaN and turn the reference's +-Inf results into NaN; its small part is 0.
+					// One test per thread and stage instead of a compare + select per element: the OR of all 32 bit patterns has an
+					// all-ones exponent whenever one of them has (false positives only cost the guarded path, which is exact too).
+					uint32_t ored = 0;
 #pragma unroll
-					for (int i = 0; i < 8; i++) {
-						const uint32_t off = (uint32_t)(t + 128 * (half * 8 + i)) * 16u;
-						float4 b, sm;
-						if (P.split == 0) {
-							b.x = tf32_trunc(v[i].x); b.y = tf32_trunc(v[i].y); b.z = tf32_trunc(v[i].z); b.w = tf32_trunc(v[i].w);
-						} else {
-							b.x = tf32_rna(v[i].x); b.y = tf32_rna(v[i].y); b.z = tf32_rna(v[i].z); b.w = tf32_rna(v[i].w);
+					for (int i = 0; i < 8; i++)
+						ored |= __float_as_uint(v[i].x) | __float_as_uint(v[i].y) | __float_as_uint(v[i].z) | __float_as_uint(v[i].w);
+					const bool guard = (ored & 0x7F800000u) == 0x7F800000u;
+					auto pass = [&](auto guarded) {
+#pragma unroll
+						for (int i = 0; i < 8; i++) {
+							const uint32_t off = (uint32_t)(t + 128 * (half * 8 + i)) * 16u;
+							float4 b, sm;
+							if (P.split == 0) {
+								b.x = tf32_trunc(v[i].x); b.y = tf32_trunc(v[i].y); b.z = tf32_trunc(v[i].z); b.w = tf32_trunc(v[i].w);
+							} else {
+								b.x = tf32_rna(v[i].x); b.y = tf32_rna(v[i].y); b.z = tf32_rna(v[i].z); b.w = tf32_rna(v[i].w);
+							}
+							if (decltype(guarded)::value) { sm.x = small_part(v[i].x, b.x); sm.y = small_part(v[i].y, b.y); sm.z = small_part(v[i].z, b.z); sm.w = small_part(v[i].w, b.w); }
+							else { sm.x = v[i].x - b.x; sm.y = v[i].y - b.y; sm.z = v[i].z - b.z; sm.w = v[i].w - b.w; }
+							if (P.flags & 2) continue;
+							sts128(raw + RAW_BYTES + off, sm);
+							if (P.split != 0) sts128(raw + off, b);
 						}
-						// x = +-Inf: Inf - Inf would make `small` NaN and turn the reference's +-Inf results into NaN; its small part is 0
-						sm.x = small_part(v[i].x, b.x); sm.y = small_part(v[i].y, b.y); sm.z = small_part(v[i].z, b.z); sm.w = small_part(v[i].w, b.w);
-						if (P.flags & 2) continue;
-						sts128(raw + RAW_BYTES + off, sm);
-						if (P.split != 0) sts128(raw + off, b);
-					}
+					};
+					if (guard) pass(std::true_type{}); else pass(std::false_type{});
 				}
 				const long long t2 = tick<PROF>();
 				fence_proxy_async_smem();
 				__syncwarp();
-				if (lane == 0) {
-					if (CG == 2) mbar_arrive_cluster(xf_bar(s), 0);
-					else mbar_arrive(xf_bar(s));
-				}
+				if (lane == 0) arrive_on_leader<CG>(xf_bar(s), cta_rank, heavy);
 				const long long t3 = tick<PROF>();
 				w_full += t1 - t0; t_work += t2 - t1; t_fence += t3 - t2;
 			}
@@ -471,7 +493,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 		int ci = 0;
 		long long w_tf = 0, t_drain = 0, t_store = 0; const long long t_begin = tick<PROF>();
 		int nt = 0;
-		for (int item; (item = next_tile<CG>(bar_base, nt, true, lane, P.diag)) >= 0;) {
+		for (int item; (item = next_tile<CG>(bar_base, nt, true, lane, P.diag, cta_rank, heavy)) >= 0;) {
 			for (int sg = 0; sg < 2; sg++) {
 			const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
 			if (wi.kb1 <= wi.kb0) continue;
@@ -523,10 +545,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				}
 				tc_fence_before();
 				__syncwarp();
-				if (lane == 0) {
-					if (CG == 2) mbar_arrive_cluster(tempty_bar(ab), 0);
-					else mbar_arrive(tempty_bar(ab));
-				}
+				if (lane == 0) arrive_on_leader<CG>(tempty_bar(ab), cta_rank, heavy);
 				w_tf += t1 - t0; t_drain += tick<PROF>() - t1;
 			}
 			const long long ts0 = tick<PROF>();

@@ -29,6 +29,18 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
 	             "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
 	             ::"r"(bar), "r"(rank) : "memory");
 }
+// Same arrive WITHOUT the cluster-scope release: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, a
+// fence that waits for every outstanding memory operation of the thread (hundreds of cycles; 43 % of a transform warp's time in
+// the round-1 kernel, ncu source page).  The default (.release at CTA scope) is enough wherever the data being handed over
+// does not travel through the generic proxy to the other CTA: shared-memory stages made visible by fence.proxy.async and read by
+// the tensor core of the CTA that wrote them, TMEM buffers ordered by tcgen05.fence, plain "slot consumed" notifications.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank)
+{
+	asm volatile("{\n\t.reg .b32 ra;\n\t"
+	             "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+	             "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+	             ::"r"(bar), "r"(rank) : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 {
 	uint32_t ok;
