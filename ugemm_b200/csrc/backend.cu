@@ -429,7 +429,7 @@ int sgemm_cuda_init(int device, size_t arena_bytes)
 	if (const char *f = getenv("UGEMM_K1_FLAGS")) {
 		// overrides the default (bit0 = A collector on).  Bits 1-6 are ablation / profiling switches that make K1's RESULTS WRONG
 		// (common.cuh): a stray environment variable must not silently corrupt a production run, so they need an explicit opt-in.
-		const int flags = atoi(f), unsafe = flags & (2 | 4 | 8 | 16 | 32 | 64);
+		const int flags = atoi(f), unsafe = flags & (2 | 4 | 8 | 16 | 32 | 64 | 65536);
 		const char *opt = getenv("UGEMM_K1_ABLATION");
 		if (unsafe && !(opt && atoi(opt) == 1)) {
 			set_error("UGEMM_K1_FLAGS=%d sets ablation bits 0x%x that corrupt results; set UGEMM_K1_ABLATION=1 to allow them (bottleneck analysis only)", flags, unsafe);

@@ -195,6 +195,217 @@ __device__ __forceinline__ float tf32_rna(float x)
 	return __uint_as_float(r);
 }
 
+// ---- epilogue pieces shared by the SS kernel (k1_3xtf32_kernel) and the TS kernel (k1ts_kernel) -------------------------------
+// An epilogue thread (lane quarter q, column half h) owns row `row` of the tile and NG = 2 * CG groups of 32 accumulator
+// columns.  Tile-relative first column of group g: SS kernel -- the thread's half of the tile is contiguous, h * BN/2 + 32 g;
+// TS kernel -- group g is the thread's half of 64-column accumulator slice g, 64 g + 32 h.
+template <int CG, bool TS>
+__device__ __forceinline__ int group_col(int h, int g) { return TS ? g * 64 + h * 32 : h * (64 * CG) + g * 32; }
+
+// one group's running sums at the start of a tile (TS kernel: groups are re-armed one by one while the previous tile is stored)
+template <int CG, bool TS>
+__device__ __forceinline__ void epi_init_group(float (&a)[32], int g, const K1Params &P, bool from_c, float bs, const float *crow, int tn, int h)
+{
+	constexpr int BN = 128 * CG;
+	if (from_c) {
+		const long long col0 = (long long)tn * BN + group_col<CG, TS>(h, g);
+		if (P.vecC && col0 + 31 < P.N) {
+#pragma unroll
+			for (int i = 0; i < 32; i += 4) {
+				const float4 cv = *reinterpret_cast<const float4 *>(crow + col0 + i);
+				a[i + 0] = bs * cv.x; a[i + 1] = bs * cv.y; a[i + 2] = bs * cv.z; a[i + 3] = bs * cv.w;
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < 32; i++) a[i] = (col0 + i < P.N) ? bs * crow[col0 + i] : 0.f;
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < 32; i++) a[i] = 0.f;
+	}
+}
+
+// running sums at the start of a tile: (beta/alpha) * C when the old C can be folded in up front, else 0
+template <int CG, bool CONV, bool TS>
+__device__ __forceinline__ void epi_init_acc(float (&acc)[2 * CG][32], const K1Params &P, const Item &wi, bool preload_c, float bs, long long row,
+                                             const float *crow, int tn, int h)
+{
+	constexpr int BN = 128 * CG, NG = 2 * CG;
+	// beta != 0: the old C is folded in UP FRONT -- the running sums start at (beta/alpha)*C, loaded while the
+	// tile's first MMAs run and the epilogue warps would idle anyway -- so the tile end is store-only and
+	// never stalls the accumulator hand-over on a global-load round trip.
+	if (!CONV && preload_c && wi.slot < 0 && row < P.M) {
+#pragma unroll
+		for (int g = 0; g < NG; g++) {
+			const long long col0 = (long long)tn * BN + group_col<CG, TS>(h, g);
+			if (P.vecC && col0 + 31 < P.N) {
+#pragma unroll
+				for (int i = 0; i < 32; i += 4) {
+					const float4 cv = *reinterpret_cast<const float4 *>(crow + col0 + i);
+					acc[g][i + 0] = bs * cv.x; acc[g][i + 1] = bs * cv.y; acc[g][i + 2] = bs * cv.z; acc[g][i + 3] = bs * cv.w;
+				}
+			} else {
+#pragma unroll
+				for (int i = 0; i < 32; i++) acc[g][i] = (col0 + i < P.N) ? bs * crow[col0 + i] : 0.f;
+			}
+		}
+	} else {
+#pragma unroll
+		for (int g = 0; g < NG; g++)
+#pragma unroll
+			for (int i = 0; i < 32; i++) acc[g][i] = 0.f;
+	}
+}
+
+// tile end: stream-K part -> raw partial sums to the workspace; whole tile -> fused alpha/beta(/bias/LeakyReLU) and the store
+// `after(g)` is called once per group, as soon as acc[g] has been consumed (staged for its TMA store / stored): the TS kernel
+// re-arms the group for the next tile there and takes early hand-overs, so that the MMAs never wait for a tile store.
+struct NoHook { __device__ __forceinline__ void operator()(int) const {} };
+template <int CG, bool CONV, bool TS, class After = NoHook>
+__device__ __forceinline__ void epi_store_tile(float (&acc)[2 * CG][32], const K1Params &P, const CUtensorMap *tmCp, const Item &wi, bool preload_c, float alpha,
+                                               long long row, float *crow, int tm, int tn, int inst, int q, int h, int e, int lane, uint32_t cta_rank, uint32_t bar_base,
+                                               After after = After(), const CUtensorMap *tmWp = nullptr)
+{
+	constexpr int BN = 128 * CG, UMMA_M = 128 * CG, NG = 2 * CG;
+	if (wi.slot >= 0 && tmWp != nullptr && (P.flags & 16)) {      // ablation: parts not stored
+#pragma unroll
+		for (int g = 0; g < NG; g++) after(g);
+		return;
+	}
+	if (wi.slot >= 0 && tmWp != nullptr) {
+		// stream-K part through the TMA unit: the workspace is a {BN, slots * UMMA_M} tensor, the part's tile starts at row slot * UMMA_M
+		const uint32_t cst = bar_base + 1024u + (uint32_t)e * CSTAGE_BYTES;
+		const int row0 = wi.slot * UMMA_M + (int)cta_rank * ROWS + q * 32;
+#pragma unroll
+		for (int g = 0; g < NG; g++) {
+			if (lane == 0) bulk_wait_group_read0();
+			__syncwarp();
+#pragma unroll
+			for (int i = 0; i < 32; i += 4)
+				sts128(cst + (uint32_t)lane * 128u + (uint32_t)(((i >> 2) ^ (lane & 7)) << 4), make_float4(acc[g][i], acc[g][i + 1], acc[g][i + 2], acc[g][i + 3]));
+			fence_proxy_async_smem();
+			__syncwarp();
+			if (lane == 0) { tma_store_2d(tmWp, cst, group_col<CG, TS>(h, g), row0); bulk_commit_group(); }
+			after(g);
+		}
+		return;
+	}
+	if (wi.slot >= 0) {
+		// stream-K part: raw partial sums to the workspace tile of this item (tile-local layout, UMMA_M x BN floats)
+		float *wrow = P.sk_ws + (long long)wi.slot * (UMMA_M * BN) + (long long)((int)cta_rank * ROWS + q * 32 + lane) * BN;
+#pragma unroll
+		for (int g = 0; g < NG; g++)
+#pragma unroll
+			for (int i = 0; i < 32; i += 4)
+				*reinterpret_cast<float4 *>(wrow + group_col<CG, TS>(h, g) + i) = make_float4(acc[g][i], acc[g][i + 1], acc[g][i + 2], acc[g][i + 3]);
+#pragma unroll
+		for (int g = 0; g < NG; g++) after(g);
+		return;
+	}
+	// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
+	const float beta = preload_c ? 0.f : P.beta;   // already folded into acc when preloaded
+	if (P.tma_store && beta == 0.f && !(P.flags & 16)) {
+		// TMA-store epilogue: each warp stages one 32-row x 32-column box at a time in shared memory (128B-swizzled, so a
+		// thread's eight 16-byte stores of its row are conflict-free) and hands it to the TMA unit, which writes whole
+		// 128-byte lines and clips the box at the matrix edge -- instead of 32 row-strided 16-byte stores per instruction.
+		const float slope = P.slope;
+		const bool post = P.bias != nullptr || slope != 1.f;
+		const float bm = (P.bias && row < P.M) ? __ldg(P.bias + row) : 0.f;
+		auto act = [&](float x) { x += bm; return x > 0.f ? x : x * slope; };
+		const uint32_t cst = bar_base + 1024u + (uint32_t)e * CSTAGE_BYTES;
+		const int row0 = tm * UMMA_M + (int)cta_rank * ROWS + q * 32;
+#pragma unroll
+		for (int g = 0; g < NG; g++) {
+			const int col0 = tn * BN + group_col<CG, TS>(h, g);
+			// CONV: the 32 columns are one output-row segment (io, jo0 .. jo0+31) of the padded column index
+			const int io = CONV ? col0 / P.cv_wp : 0, jo0 = CONV ? col0 - io * P.cv_wp : 0;
+			// warp-uniform: the whole box lies outside C
+			if (row0 >= P.M || col0 >= P.N || (CONV && (io >= P.cv_ho || jo0 >= P.cv_wo))) { after(g); continue; }
+			if (lane == 0) bulk_wait_group_read0();             // this warp's previous box has left shared memory
+			__syncwarp();
+#pragma unroll
+			for (int i = 0; i < 32; i += 4) {
+				float4 o;
+				o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1]; o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
+				if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
+				sts128(cst + (uint32_t)lane * 128u + (uint32_t)(((i >> 2) ^ (lane & 7)) << 4), o);
+			}
+			fence_proxy_async_smem();
+			__syncwarp();
+			if (lane == 0) {
+				if (CONV) tma_store_4d(tmCp, cst, jo0, io, row0, inst);     // clipped at the output width and at the filter count
+				else tma_store_3d(tmCp, cst, col0, row0, inst);
+				bulk_commit_group();
+			}
+			after(g);
+		}
+		return;
+	}
+	if (row < P.M && !(P.flags & 16)) {
+		const float slope = P.slope;
+		const bool post = P.bias != nullptr || slope != 1.f;   // bias[row] + LeakyReLU (convolution callers)
+		const float bm = P.bias ? __ldg(P.bias + row) : 0.f;
+		auto act = [&](float x) { x += bm; return x > 0.f ? x : x * slope; };
+		if (CONV) {
+			// each 32-column group is one output-row segment: map it back from the padded column index
+#pragma unroll
+			for (int g = 0; g < NG; g++) {
+				const int n0 = tn * BN + group_col<CG, TS>(h, g);
+				const int io = n0 / P.cv_wp, jo0 = n0 - io * P.cv_wp;
+				const int valid = io < P.cv_ho ? P.cv_wo - jo0 : 0;      // columns of this group that exist (may be <= 0 or >= 32)
+				const int off = io * P.cv_wo + jo0;
+				float *dst = crow + off;
+				const bool vec = P.vecC && (off & 3) == 0;
+#pragma unroll
+				for (int i = 0; i < 32; i += 4) {
+					float4 o;
+					o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1]; o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
+					if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
+					if (vec && i + 3 < valid) *reinterpret_cast<float4 *>(dst + i) = o;
+					else {
+						if (i + 0 < valid) dst[i + 0] = o.x;
+						if (i + 1 < valid) dst[i + 1] = o.y;
+						if (i + 2 < valid) dst[i + 2] = o.z;
+						if (i + 3 < valid) dst[i + 3] = o.w;
+					}
+				}
+			}
+		} else
+#pragma unroll
+		for (int g = 0; g < NG; g++) {
+			const long long col0 = (long long)tn * BN + group_col<CG, TS>(h, g);
+			if (P.vecC && col0 + 31 < P.N) {
+#pragma unroll
+				for (int i = 0; i < 32; i += 4) {
+					float4 *cp = reinterpret_cast<float4 *>(crow + col0 + i);
+					float4 o;
+					if (beta != 0.f) {
+						const float4 cv = *cp;
+						o.x = fmaf(alpha, acc[g][i + 0], beta * cv.x); o.y = fmaf(alpha, acc[g][i + 1], beta * cv.y);
+						o.z = fmaf(alpha, acc[g][i + 2], beta * cv.z); o.w = fmaf(alpha, acc[g][i + 3], beta * cv.w);
+					} else {
+						o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1];
+						o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
+					}
+					if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
+					*cp = o;
+				}
+			} else {
+#pragma unroll
+				for (int i = 0; i < 32; i++) {
+					if (col0 + i < P.N) {
+						float o = alpha * acc[g][i];
+						if (beta != 0.f) o = fmaf(alpha, acc[g][i], beta * crow[col0 + i]);
+						crow[col0 + i] = post ? act(o) : o;
+					}
+				}
+			}
+		}
+	}
+#pragma unroll
+	for (int g = 0; g < NG; g++) after(g);
+}
+
 // PROF compiles the per-role cycle counters in (UGEMM_K1_FLAGS bit 5); the production instantiation has none, which
 // keeps ~10 registers out of the epilogue's hot drain loop.
 // CONV: the B operand is an image gathered by 4-D TMA boxes (implicit im2col; strides 1..8 through the TMA element stride).  GEMM column n' = io * cv_wp + jo
@@ -504,30 +715,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 			float acc[NG][32];
 			const long long row = (long long)tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane;
 			float *crow = P.C + (long long)inst * P.strideC + row * (CONV ? (long long)P.cv_npix : P.ldc);
-			// beta != 0: the old C is folded in UP FRONT -- the running sums start at (beta/alpha)*C, loaded while the
-			// tile's first MMAs run and the epilogue warps would idle anyway -- so the tile end is store-only and
-			// never stalls the accumulator hand-over on a global-load round trip.
-			if (!CONV && preload_c && wi.slot < 0 && row < P.M) {
-#pragma unroll
-				for (int g = 0; g < NG; g++) {
-					const long long col0 = (long long)tn * BN + h * (BN / 2) + g * 32;
-					if (P.vecC && col0 + 31 < P.N) {
-#pragma unroll
-						for (int i = 0; i < 32; i += 4) {
-							const float4 cv = *reinterpret_cast<const float4 *>(crow + col0 + i);
-							acc[g][i + 0] = bs * cv.x; acc[g][i + 1] = bs * cv.y; acc[g][i + 2] = bs * cv.z; acc[g][i + 3] = bs * cv.w;
-						}
-					} else {
-#pragma unroll
-						for (int i = 0; i < 32; i++) acc[g][i] = (col0 + i < P.N) ? bs * crow[col0 + i] : 0.f;
-					}
-				}
-			} else {
-#pragma unroll
-				for (int g = 0; g < NG; g++)
-#pragma unroll
-					for (int i = 0; i < 32; i++) acc[g][i] = 0.f;
-			}
+			epi_init_acc<CG, CONV, false>(acc, P, wi, preload_c, bs, row, crow, tn, h);
 			for (int kb0 = wi.kb0; kb0 < wi.kb1; kb0 += kc, ci++) {
 				const int ab = ci & 1;
 				const uint32_t aph = (ci >> 1) & 1;
@@ -549,113 +737,7 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 				w_tf += t1 - t0; t_drain += tick<PROF>() - t1;
 			}
 			const long long ts0 = tick<PROF>();
-			if (wi.slot >= 0) {
-				// stream-K part: raw partial sums to the workspace tile of this item (tile-local layout, UMMA_M x BN floats)
-				float *wrow = P.sk_ws + (long long)wi.slot * (UMMA_M * BN) + (long long)((int)cta_rank * ROWS + q * 32 + lane) * BN + h * (BN / 2);
-#pragma unroll
-				for (int g = 0; g < NG; g++)
-#pragma unroll
-					for (int i = 0; i < 32; i += 4)
-						*reinterpret_cast<float4 *>(wrow + g * 32 + i) = make_float4(acc[g][i], acc[g][i + 1], acc[g][i + 2], acc[g][i + 3]);
-				continue;
-			}
-			// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
-			const float beta = preload_c ? 0.f : P.beta;   // already folded into acc when preloaded
-			if (P.tma_store && beta == 0.f && !(P.flags & 16)) {
-				// TMA-store epilogue: each warp stages one 32-row x 32-column box at a time in shared memory (128B-swizzled, so a
-				// thread's eight 16-byte stores of its row are conflict-free) and hands it to the TMA unit, which writes whole
-				// 128-byte lines and clips the box at the matrix edge -- instead of 32 row-strided 16-byte stores per instruction.
-				const float slope = P.slope;
-				const bool post = P.bias != nullptr || slope != 1.f;
-				const float bm = (P.bias && row < P.M) ? __ldg(P.bias + row) : 0.f;
-				auto act = [&](float x) { x += bm; return x > 0.f ? x : x * slope; };
-				const uint32_t cst = bar_base + 1024u + (uint32_t)e * CSTAGE_BYTES;
-				const int row0 = tm * UMMA_M + (int)cta_rank * ROWS + q * 32;
-#pragma unroll
-				for (int g = 0; g < NG; g++) {
-					const int col0 = tn * BN + h * (BN / 2) + g * 32;
-					if (row0 >= P.M || col0 >= P.N) continue;          // warp-uniform: the whole box lies outside C
-					// CONV: the 32 columns are one output-row segment (io, jo0 .. jo0+31) of the padded column index
-					const int io = CONV ? col0 / P.cv_wp : 0, jo0 = CONV ? col0 - io * P.cv_wp : 0;
-					if (CONV && (io >= P.cv_ho || jo0 >= P.cv_wo)) continue;
-					if (lane == 0) bulk_wait_group_read0();             // this warp's previous box has left shared memory
-					__syncwarp();
-#pragma unroll
-					for (int i = 0; i < 32; i += 4) {
-						float4 o;
-						o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1]; o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
-						if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
-						sts128(cst + (uint32_t)lane * 128u + (uint32_t)(((i >> 2) ^ (lane & 7)) << 4), o);
-					}
-					fence_proxy_async_smem();
-					__syncwarp();
-					if (lane == 0) {
-						if (CONV) tma_store_4d(&tmC, cst, jo0, io, row0, inst);     // clipped at the output width and at the filter count
-						else tma_store_3d(&tmC, cst, col0, row0, inst);
-						bulk_commit_group();
-					}
-				}
-			} else if (row < P.M && !(P.flags & 16)) {
-				const float slope = P.slope;
-				const bool post = P.bias != nullptr || slope != 1.f;   // bias[row] + LeakyReLU (convolution callers)
-				const float bm = P.bias ? __ldg(P.bias + row) : 0.f;
-				auto act = [&](float x) { x += bm; return x > 0.f ? x : x * slope; };
-				if (CONV) {
-					// each 32-column group is one output-row segment: map it back from the padded column index
-#pragma unroll
-					for (int g = 0; g < NG; g++) {
-						const int n0 = tn * BN + h * (BN / 2) + g * 32;
-						const int io = n0 / P.cv_wp, jo0 = n0 - io * P.cv_wp;
-						const int valid = io < P.cv_ho ? P.cv_wo - jo0 : 0;      // columns of this group that exist (may be <= 0 or >= 32)
-						const int off = io * P.cv_wo + jo0;
-						float *dst = crow + off;
-						const bool vec = P.vecC && (off & 3) == 0;
-#pragma unroll
-						for (int i = 0; i < 32; i += 4) {
-							float4 o;
-							o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1]; o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
-							if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
-							if (vec && i + 3 < valid) *reinterpret_cast<float4 *>(dst + i) = o;
-							else {
-								if (i + 0 < valid) dst[i + 0] = o.x;
-								if (i + 1 < valid) dst[i + 1] = o.y;
-								if (i + 2 < valid) dst[i + 2] = o.z;
-								if (i + 3 < valid) dst[i + 3] = o.w;
-							}
-						}
-					}
-				} else
-#pragma unroll
-				for (int g = 0; g < NG; g++) {
-					const long long col0 = (long long)tn * BN + h * (BN / 2) + g * 32;
-					if (P.vecC && col0 + 31 < P.N) {
-#pragma unroll
-						for (int i = 0; i < 32; i += 4) {
-							float4 *cp = reinterpret_cast<float4 *>(crow + col0 + i);
-							float4 o;
-							if (beta != 0.f) {
-								const float4 cv = *cp;
-								o.x = fmaf(alpha, acc[g][i + 0], beta * cv.x); o.y = fmaf(alpha, acc[g][i + 1], beta * cv.y);
-								o.z = fmaf(alpha, acc[g][i + 2], beta * cv.z); o.w = fmaf(alpha, acc[g][i + 3], beta * cv.w);
-							} else {
-								o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1];
-								o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
-							}
-							if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
-							*cp = o;
-						}
-					} else {
-#pragma unroll
-						for (int i = 0; i < 32; i++) {
-							if (col0 + i < P.N) {
-								float o = alpha * acc[g][i];
-								if (beta != 0.f) o = fmaf(alpha, acc[g][i], beta * crow[col0 + i]);
-								crow[col0 + i] = post ? act(o) : o;
-							}
-						}
-					}
-				}
-			}
+			epi_store_tile<CG, CONV, false>(acc, P, &tmC, wi, preload_c, alpha, row, crow, tm, tn, inst, q, h, e, lane, cta_rank, bar_base);
 			t_store += tick<PROF>() - ts0;
 			}
 		}
@@ -669,34 +751,498 @@ k1_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 	if (warp == 1) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
 }
 
+// ===============================================================================================================
+// K1-TS: the same 3xTF32 product with the A operand in TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc, ...).
+//
+// Why (tools/mma_rate.cu, profiles/r2f_mma_rate3.jsonl): issued back to back, a TF32 MMA whose A operand comes from shared
+// memory takes 145 cycles at UMMA 256x256x8 (81-86 at N = 128) -- the rate the SS kernel above runs at -- while the same MMA
+// with A in TMEM runs at the instruction floor for every N (128 / 96 / 64 / 32 cycles at N = 256 / 192 / 128 / 64), under
+// shared-memory and tcgen05.ld traffic.  So here the transform warps write op(A) -- raw (its TF32 truncation is A_big) and
+// small -- straight from registers into TMEM with tcgen05.st; only B keeps a shared-memory "small" copy.
+//
+// TMEM budget (512 columns).  A stages take 64 columns each (32 raw + 32 small), which leaves no room for two 256-column
+// accumulators.  The accumulator is therefore cut into 64-COLUMN SLICES, each accumulated by its own UMMA 256x64x8 (32-cycle
+// floor: same tensor throughput as one 256-column MMA), and the promotion schedule of the slices is STAGGERED: with promotion
+// every kc = 4 k-blocks, slice j hands its partial sums to the epilogue after k-blocks j, j+4, j+8, ... -- one 64-column slice
+// per k-block instead of 256 columns every fourth.  A slice that has been handed over continues in a free buffer, so
+// NSL + 1 slice buffers in a FIFO ring (5 x 64 = 320 columns for a 256-wide tile) replace 2 x 256, and 3 A stages fit.
+// Both sides count hand-overs with one running index: buffer = index % (NSL + 1).
+//
+// Shared memory: 4 stages of 48 KiB (A raw | B raw | B small).  With cta_group::2 an N = 64 MMA takes accumulator columns
+// 0..31 from the leader's B rows and 32..63 from the peer's, so CTA r loads B in 32-row groups: shared-memory rows 32g..32g+31
+// hold columns n0 + 64g + 32r .. +31 of the tile, and accumulator column c of slice g is tile column 64g + c.
+// Roles and barriers as in the SS kernel, plus afree[] (TMEM A stage consumed) and per-buffer tfull[] / tempty[].
+// ===============================================================================================================
+namespace tsk {
+constexpr int TS_STAGES = 4;
+constexpr int TS_STAGE_BYTES = 3 * OPER_BYTES;         // A raw | B raw | B small = 48 KiB
+constexpr int SLICE = 64;                             // accumulator columns per MMA (UMMA N)
+constexpr int TS_SMEM_BYTES = TS_STAGES * TS_STAGE_BYTES + 1024 + 8 * CSTAGE_BYTES + 1024;   // ring | barriers | C staging | alignment slack
+static_assert(TS_SMEM_BYTES <= 232448, "shared-memory budget of one CTA (227 KiB)");
+// barrier block: 8-byte slots counted from bar_base
+constexpr int B_FULL = 0, B_XF = 4, B_EMPTY = 8, B_AFREE = 12, B_TFULL = 16, B_TEMPTY = 21;
+constexpr int B_SCHED = 26;                           // tile-index ring: full[4], empty[4], 4 x 4-byte slots (next_tile's layout, rebased)
+constexpr int B_TMEM = 37;
+}
+
+template <int CG, bool PROF>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmW, const K1Params P)
+{
+	using namespace tsk;
+	constexpr int BN = 128 * CG, UMMA_M = 128 * CG;
+	constexpr int NSL = BN / SLICE, NBUF = NSL + 1;                      // slices per tile, slice buffers in the ring
+	constexpr int NA = (512 - NBUF * SLICE) / 64 < TS_STAGES ? (512 - NBUF * SLICE) / 64 : TS_STAGES;   // TMEM A stages: 3 (CG = 2), 4 (CG = 1)
+	constexpr uint32_t A_COL0 = NBUF * SLICE;
+	constexpr uint32_t SL16 = (SLICE / CG) * 128 / 16;                   // one slice's B rows in this CTA's stage, in 16-byte units
+	static_assert(NA >= 2, "need at least two TMEM A stages");
+
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const uint32_t bar_base = smem_base + TS_STAGES * TS_STAGE_BYTES;
+	auto bar = [&](int idx) { return bar_base + 8u * (uint32_t)idx; };
+	const uint32_t sched_bars = bar_base + 8u * (B_SCHED - 14);          // next_tile() addresses its ring at slots 14.. of the base it is given
+	const uint32_t tmem_slot = bar(B_TMEM);
+	volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+	const int warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+	const int cluster_id = (CG == 2) ? (int)cluster_id_x() : (int)blockIdx.x;
+	const int num_clusters = (CG == 2) ? (int)num_clusters_x() : (int)gridDim.x;
+	const int nkb = P.num_k_blocks;
+	const int kc = P.kc_blocks;                       // multiple of NSL, or >= nkb (no promotion inside a tile)
+	const int step = kc / NSL > 0 ? kc / NSL : 1;     // k-blocks between two hand-overs
+	constexpr bool heavy = false;
+	long long *prof = (PROF && P.prof && blockIdx.x < 4) ? P.prof + 16 * blockIdx.x : nullptr;   // per-role cycle counters (UGEMM_K1_FLAGS bit 5)
+
+	if (warp == 0 && lane == 0) {
+		prefetch_tmap(&tmA);
+		prefetch_tmap(&tmB);
+		if (P.tma_store) prefetch_tmap(&tmC);
+		if (P.sk_q > 0) prefetch_tmap(&tmW);
+		for (int s = 0; s < TS_STAGES; s++) {
+			mbar_init(bar(B_FULL + s), 1);
+			mbar_init(bar(B_XF + s), 8 * CG);        // 8 transform warps per CTA of the pair
+			mbar_init(bar(B_EMPTY + s), 1);
+			mbar_init(bar(B_AFREE + s), 1);
+		}
+		for (int b = 0; b < NBUF; b++) {
+			mbar_init(bar(B_TFULL + b), 1);
+			mbar_init(bar(B_TEMPTY + b), 8 * CG);    // 8 epilogue warps per CTA of the pair
+		}
+		for (int d = 0; d < SCHED_SLOTS; d++) {
+			mbar_init(bar(B_SCHED + d), 1);
+			mbar_init(bar(B_SCHED + SCHED_SLOTS + d), (1 + 8 + 8) * CG + 1);   // TMA thread, 8 transform + 8 epilogue warps per CTA, the MMA thread
+		}
+		fence_mbar_init();
+	}
+	__syncwarp();
+	if (warp == 1) {
+		tmem_alloc<CG>(tmem_slot, 512);
+		tmem_relinquish<CG>();
+	}
+	tc_fence_before();
+	if (CG == 2) { cluster_arrive(); cluster_wait(); } else __syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot_ptr;
+
+	if (warp < 4) {
+		reg_dec<48>();
+		if (warp == 0 && lane == 0) {
+			// ================= TMA producer =================
+			int s = 0; uint32_t ph = 0;
+			int nt = 0;
+			long long w_empty = 0; const long long t_begin = tick<PROF>();
+			for (int item; (item = next_tile<CG>(sched_bars, nt, false, 0, P.diag, cta_rank, heavy)) >= 0;) {
+				for (int sg = 0; sg < 2; sg++) {
+				const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
+				if (wi.kb1 <= wi.kb0) continue;
+				int tm, tn;
+				const int inst = wi.tile / P.tiles_per_batch;
+				decode_tile(wi.tile - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
+				const int a_row0 = tm * UMMA_M + (int)cta_rank * ROWS;
+				const int b_col0 = tn * BN + (CG == 2 ? 32 * (int)cta_rank : 0);    // group g: + 64 g (pair) / + 32 g (single CTA)
+				for (int kb = wi.kb0; kb < wi.kb1; kb++) {
+					const long long tw = tick<PROF>();
+					mbar_wait(bar(B_EMPTY + s), ph ^ 1u, P.diag, 1);
+					w_empty += tick<PROF>() - tw;
+					mbar_arrive_expect_tx(bar(B_FULL + s), RAW_BYTES);
+					const uint32_t sA = smem_base + s * TS_STAGE_BYTES, sB = sA + OPER_BYTES, fb = bar(B_FULL + s);
+					const int k0 = kb * BK;
+					if (P.a_kmajor) tma_load_3d_hint(sA, &tmA, fb, k0, a_row0, inst, L2_EVICT_NORMAL);
+					else
+						for (int j = 0; j < ROWS / 32; j++) tma_load_3d_hint(sA + j * 4096, &tmA, fb, a_row0 + 32 * j, k0, inst, L2_EVICT_NORMAL);
+#pragma unroll
+					for (int g = 0; g < ROWS / 32; g++) {
+						const int n = b_col0 + (CG == 2 ? 64 : 32) * g;
+						if (P.b_kmajor) tma_load_3d_hint(sB + g * 4096, &tmB, fb, k0, n, inst, L2_EVICT_NORMAL);
+						else tma_load_3d_hint(sB + g * 4096, &tmB, fb, n, k0, inst, L2_EVICT_NORMAL);
+					}
+					if (++s == TS_STAGES) { s = 0; ph ^= 1u; }
+				}
+				}
+			}
+			if (prof) { prof[0] = w_empty; prof[1] = tick<PROF>() - t_begin; }
+		} else if (warp == 1 && cta_rank == 0) {
+			// ================= MMA issuer (leader CTA): the warp stays converged, one elected lane issues =================
+			if (elect_one()) {
+				const uint32_t idesc = idesc_tf32(UMMA_M, SLICE, 0, P.b_kmajor ? 0 : 1);
+				// B descriptors: K-major SW128 (LBO enc 1, SBO 1024 B, k-step +32 B) or MN-major SW128 / 32-byte atom (LBO 4096 B between
+				// 32-wide mn groups, SBO 512 B, k-step +1024 B); the high word is constant, the low word carries the start address
+				const uint64_t d0 = P.b_kmajor ? smem_desc(0, 1, 64, 2) : smem_desc(0, 256, 32, 1);
+				const uint32_t b_hi = (uint32_t)(d0 >> 32), b_lo0 = (uint32_t)d0 + (((smem_base + OPER_BYTES) & 0x3FFFFu) >> 4);
+				const uint32_t b_kstep = (P.b_kmajor ? 32u : 1024u) >> 4;
+				int s = 0; uint32_t ph = 0;            // shared-memory stage of the next k-block and its phase
+				int a = 0;                             // TMEM A stage of the next k-block
+				int ab = 0; uint32_t aph = 0;          // next slice buffer of the ring and its phase
+				int nt = 0;
+				long long w_xf = 0, w_te = 0; const long long t_begin = tick<PROF>();
+				for (int item; (item = next_tile<CG>(sched_bars, nt, false, 0, P.diag, cta_rank, heavy)) >= 0;) {
+					for (int sg = 0; sg < 2; sg++) {
+					const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
+					if (wi.kb1 <= wi.kb0) continue;
+					const int nseg = wi.kb1 - wi.kb0;
+					int buf[NSL];                      // ring buffer of each slice
+					uint32_t fresh = (1u << NSL) - 1u; // slices whose next MMA starts a new chunk (overwrites its buffer)
+					auto take_buffer = [&]() {
+						const long long tw = tick<PROF>();
+						if (CG == 2) mbar_wait_cluster(bar(B_TEMPTY + ab), aph ^ 1u, P.diag, 2); else mbar_wait(bar(B_TEMPTY + ab), aph ^ 1u, P.diag, 2);
+						w_te += tick<PROF>() - tw;
+						const int b = ab;
+						if (++ab == NBUF) { ab = 0; aph ^= 1u; }
+						return b;
+					};
+					// (the slices take their first buffers one by one inside the first k-block, each just before its first MMA: the previous
+					// tile's last hand-overs are still being promoted, and waiting for four free buffers up front would idle the tensor pipe)
+#pragma unroll
+					for (int j = 0; j < NSL; j++) buf[j] = 0;
+					// slice that hands over next, and the k-block after which it does.  The first hand-over of a tile waits kc k-blocks (then one
+					// slice every `step`): the epilogue warps are still storing the previous tile, and a full chunk of slack is what the
+					// 2 x 256-column scheme gave them.  A slice's first chunk is therefore kc + j * step <= 2 kc - step k-blocks long, all others kc.
+					int jo = 0, next_evt = kc - 1;
+					for (int t = 0; t < nseg; t++) {
+						const long long tw = tick<PROF>();
+						if (CG == 2) mbar_wait_cluster(bar(B_XF + s), ph, P.diag, 3); else mbar_wait(bar(B_XF + s), ph, P.diag, 3);
+						w_xf += tick<PROF>() - tw;
+						tc_fence_after();
+						const uint32_t lo_b = b_lo0 + (uint32_t)s * (TS_STAGE_BYTES >> 4);
+						const uint32_t a_raw = tmem_base + A_COL0 + (uint32_t)a * 64u, a_small = a_raw + 32u;
+#pragma unroll
+						for (int j = 0; j < NSL; j++) {
+							if (t == 0) { buf[j] = take_buffer(); tc_fence_after(); }
+							const uint32_t d_tmem = tmem_base + (uint32_t)buf[j] * SLICE;
+#pragma unroll
+							for (int k4 = 0; k4 < BK / 8; k4++) {
+								const uint64_t dBb = desc64(lo_b + (uint32_t)j * SL16 + (uint32_t)k4 * b_kstep, b_hi);
+								const uint64_t dBs = desc64(lo_b + (uint32_t)j * SL16 + (uint32_t)k4 * b_kstep + (OPER_BYTES >> 4), b_hi);
+								mma_tf32_ts<CG>(d_tmem, a_small + 8u * k4, dBb, idesc, (k4 == 0 && ((fresh >> j) & 1u)) ? 0u : 1u);
+								mma_tf32_ts<CG>(d_tmem, a_raw + 8u * k4, dBs, idesc, 1u);
+								mma_tf32_ts<CG>(d_tmem, a_raw + 8u * k4, dBb, idesc, 1u);
+							}
+						}
+						fresh = 0;
+						mma_commit<CG>(bar(B_EMPTY + s));        // shared-memory stage free once these MMAs have read it
+						mma_commit<CG>(bar(B_AFREE + a));        // and so is the TMEM A stage
+						if (++s == TS_STAGES) { s = 0; ph ^= 1u; }
+						if (++a == NA) a = 0;
+						if (t == nseg - 1) {
+							// end of the tile (or stream-K part): every slice hands over, oldest buffer first
+#pragma unroll
+							for (int n = 0; n < NSL; n++) {
+								const int j = (jo + n) % NSL;
+								int b = buf[0];
+#pragma unroll
+								for (int jj = 1; jj < NSL; jj++) b = (jj == j) ? buf[jj] : b;
+								mma_commit<CG>(bar(B_TFULL + b));
+							}
+						} else if (t == next_evt) {
+							// slice jo hands its chunk to the epilogue and continues in the next buffer of the ring
+							int b = buf[0];
+#pragma unroll
+							for (int jj = 1; jj < NSL; jj++) b = (jj == jo) ? buf[jj] : b;
+							mma_commit<CG>(bar(B_TFULL + b));
+							const int nb = take_buffer();
+							tc_fence_after();
+#pragma unroll
+							for (int jj = 0; jj < NSL; jj++) buf[jj] = (jj == jo) ? nb : buf[jj];
+							fresh |= 1u << jo;
+							jo = (jo + 1 == NSL) ? 0 : jo + 1;
+							next_evt += step;
+						}
+					}
+					}
+				}
+				if (prof) { prof[2] = w_xf; prof[3] = w_te; prof[4] = tick<PROF>() - t_begin; }
+			}
+			__syncwarp();
+		} else if (warp == 2 && lane == 0 && cta_rank == 0) {
+			// ================= tile scheduler (leader CTA) =================
+			// Item n is claimed once every role has picked up item n-1: a pair never holds more than the tile it works on plus one,
+			// so a problem with only a few tiles per pair is shared out evenly (claiming as far ahead as the ring allows let the first
+			// pairs to start take four tiles each), while a pair that runs late -- its SMs busy with another kernel -- still claims less.
+			// Stream-K launches claim their whole tiles the same way; the pair's own tail range follows when the counter runs dry.
+			const uint32_t slots = sched_bars + 8u * (14 + 2 * SCHED_SLOTS);
+			const int limit = P.sk_q > 0 ? P.sk_full : P.num_tiles;
+			bool tail_given = false;
+			for (int n = 0;; n++) {
+				const int slot = n & (SCHED_SLOTS - 1);
+				const uint32_t full = sched_bars + 8u * (14 + slot);
+				if (n >= 1) {
+					const uint32_t pempty = sched_bars + 8u * (14 + SCHED_SLOTS + ((n - 1) & (SCHED_SLOTS - 1))), pph = ((n - 1) / SCHED_SLOTS) & 1;
+					if (CG == 2) mbar_wait_cluster(pempty, pph, P.diag, 7); else mbar_wait(pempty, pph, P.diag, 7);
+				}
+				int tile = -1;
+				if (!tail_given) {
+					tile = (int)(atomicAdd(P.sched, 1u) - P.sched_base);
+					if (tile >= limit) {
+						tile = (P.sk_q > 0 && P.sk_full + cluster_id < P.num_tiles) ? P.sk_full + cluster_id : -1;
+						tail_given = true;
+					}
+				}
+				asm volatile("st.shared.b32 [%0], %1;" ::"r"(slots + 4u * slot), "r"(tile) : "memory");
+				if (CG == 2) {
+					asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 1;\n\t"
+					             "st.shared::cluster.b32 [ra], %1;\n\t}" ::"r"(slots + 4u * slot), "r"(tile) : "memory");
+					mbar_arrive_cluster(full, 0);      // release at cluster scope: the peer reads the slot written above
+					mbar_arrive_cluster(full, 1);
+				} else {
+					mbar_arrive(full);
+				}
+				if (tile < 0) break;
+			}
+		}
+		__syncwarp();   // reconverge before the .aligned teardown barrier
+	} else if (warp < 12) {
+		// ================= transform warps: op(A) raw + small -> TMEM, B small -> shared memory =================
+		reg_dec<56>();
+		const int t = (int)threadIdx.x - 128;              // 0..255
+		const int grp = t >> 7;                            // warpgroup: k columns [16 grp, 16 grp + 16) of A, half of B
+		const int w4 = (t >> 5) & 3;                       // TMEM lane quarter of this warp (= warp % 4)
+		const int r = w4 * 32 + lane;                      // row of the A tile this thread moves
+		const uint32_t a_tmem = tmem_base + ((uint32_t)(w4 * 32) << 16) + A_COL0 + 16u * (uint32_t)grp;
+		int s = 0; uint32_t ph = 0;
+		int a = 0; uint32_t aph = 0;
+		int nt = 0;
+		long long w_full = 0, w_afree = 0, t_fence = 0; const long long t_begin = tick<PROF>();
+		for (int item; (item = next_tile<CG>(sched_bars, nt, true, lane, P.diag, cta_rank, heavy)) >= 0;) {
+			for (int sg = 0; sg < 2; sg++) {
+			const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
+			if (wi.kb1 <= wi.kb0) continue;
+			for (int kb = wi.kb0; kb < wi.kb1; kb++) {
+				const long long t0 = tick<PROF>();
+				mbar_wait(bar(B_FULL + s), ph, P.diag, 4);                 // raw tiles have landed
+				w_full += tick<PROF>() - t0;
+				const uint32_t raw = smem_base + s * TS_STAGE_BYTES;
+				float av[16];
+				if (P.a_kmajor) {
+					// K-major SW128: row r at r * 128, 16-byte chunk c at (c ^ (r & 7)) * 16
+#pragma unroll
+					for (int c = 0; c < 4; c++) {
+						const float4 v = lds128(raw + (uint32_t)r * 128u + (uint32_t)(((4 * grp + c) ^ (r & 7)) << 4));
+						av[4 * c + 0] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
+					}
+				} else {
+					// MN-major SW128 / 32-byte atom: 32-row group w4 at w4 * 4096, k line at k * 128, 32-byte atom (lane / 8) ^ (k & 3)
+#pragma unroll
+					for (int kk = 0; kk < 16; kk++) {
+						const int k = 16 * grp + kk;
+						av[kk] = lds32(raw + (uint32_t)w4 * 4096u + (uint32_t)k * 128u + (uint32_t)((((lane >> 3) ^ (k & 3)) << 5) + ((lane & 7) << 2)));
+					}
+				}
+				float4 bv[4];
+#pragma unroll
+				for (int i = 0; i < 4; i++) bv[i] = lds128(raw + OPER_BYTES + (uint32_t)(t + 256 * i) * 16u);
+				// x = +-Inf: Inf - Inf would make `small` NaN; its small part is 0.  One test per operand, thread and stage (see the SS kernel).
+				uint32_t ored = 0;
+#pragma unroll
+				for (int i = 0; i < 16; i++) ored |= __float_as_uint(av[i]);
+				const bool guard_a = (ored & 0x7F800000u) == 0x7F800000u;
+				const long long t1 = tick<PROF>();
+				mbar_wait(bar(B_AFREE + a), aph ^ 1u, P.diag, 8);          // the MMAs that read this TMEM A stage last have retired
+				w_afree += tick<PROF>() - t1;
+				tc_fence_after();
+				tmem_st_32x32b_x16(a_tmem + (uint32_t)a * 64u, av);        // raw: the tensor core truncates it to A_big itself
+				if (guard_a) {
+#pragma unroll
+					for (int i = 0; i < 16; i++) av[i] = small_part(av[i], tf32_trunc(av[i]));
+				} else {
+#pragma unroll
+					for (int i = 0; i < 16; i++) av[i] -= tf32_trunc(av[i]);
+				}
+				tmem_st_32x32b_x16(a_tmem + (uint32_t)a * 64u + 32u, av);
+				ored = 0;
+#pragma unroll
+				for (int i = 0; i < 4; i++) ored |= __float_as_uint(bv[i].x) | __float_as_uint(bv[i].y) | __float_as_uint(bv[i].z) | __float_as_uint(bv[i].w);
+				const bool guard_b = (ored & 0x7F800000u) == 0x7F800000u;
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					float4 sm;
+					if (guard_b) {
+						sm.x = small_part(bv[i].x, tf32_trunc(bv[i].x)); sm.y = small_part(bv[i].y, tf32_trunc(bv[i].y));
+						sm.z = small_part(bv[i].z, tf32_trunc(bv[i].z)); sm.w = small_part(bv[i].w, tf32_trunc(bv[i].w));
+					} else {
+						sm.x = bv[i].x - tf32_trunc(bv[i].x); sm.y = bv[i].y - tf32_trunc(bv[i].y);
+						sm.z = bv[i].z - tf32_trunc(bv[i].z); sm.w = bv[i].w - tf32_trunc(bv[i].w);
+					}
+					sts128(raw + 2 * OPER_BYTES + (uint32_t)(t + 256 * i) * 16u, sm);
+				}
+				const long long t2 = tick<PROF>();
+				tmem_st_wait();
+				fence_proxy_async_smem();
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0) arrive_on_leader<CG>(bar(B_XF + s), cta_rank, heavy);
+				t_fence += tick<PROF>() - t2;
+				if (++s == TS_STAGES) { s = 0; ph ^= 1u; }
+				if (++a == NA) { a = 0; aph ^= 1u; }
+			}
+			}
+		}
+		if (prof && threadIdx.x == 128) { prof[5] = w_full; prof[6] = w_afree; prof[7] = t_fence; prof[8] = tick<PROF>() - t_begin; }
+	} else {
+		// ================= epilogue warps =================
+		reg_inc<160>();
+		constexpr int NG = NSL;                            // one 32-column group per slice and thread
+		const int e = warp - 12;
+		const int q = e & 3;        // TMEM lane quarter (must equal warp % 4)
+		const int h = e >> 2;       // column half of every slice
+		const float alpha = P.alpha;
+		const float bs = P.beta / P.alpha;
+		const bool preload_c = P.beta != 0.f && fabsf(bs) < 1e18f && fabsf(bs) > 1e-18f;
+		int db = 0; uint32_t dph = 0;                      // next slice buffer to be handed over, and its phase
+		long long w_tf = 0, t_store = 0; const long long t_begin = tick<PROF>();
+		float acc[NG][32];
+		// promote slice j: add the 32 columns of this thread's half of the handed-over buffer into the running fp32 sums
+		auto drain = [&](int j) {
+			const long long tw = tick<PROF>();
+			mbar_wait(bar(B_TFULL + db), dph, P.diag, 5);
+			w_tf += tick<PROF>() - tw;
+			tc_fence_after();
+			const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(db * SLICE + h * 32);
+#pragma unroll
+			for (int half = 0; half < 2; half++) {
+				float v[16];
+				tmem_ld_32x32b_x16(taddr + 16 * half, v);
+#pragma unroll
+				for (int jj = 0; jj < NSL; jj++)
+					if (jj == j) {
+#pragma unroll
+						for (int i = 0; i < 16; i++) acc[jj][16 * half + i] += v[i];   // fp32 round-to-nearest promotion
+					}
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) arrive_on_leader<CG>(bar(B_TEMPTY + db), cta_rank, heavy);
+			if (++db == NBUF) { db = 0; dph ^= 1u; }
+		};
+		// The work items of this CTA as a stream of segments (a whole tile, or one part of a stream-K range).  Hand-over number ev of
+		// a segment always belongs to slice ev % NSL (natural hand-overs go round the slices, the final ones continue the round).
+		struct Seg { Item wi; int tm, tn, inst; };          // (kept small: two of them live beside 128 accumulator registers)
+		int nt = 0, item = -1, sgn = 2;
+		auto fetch = [&](Seg &sg) -> bool {
+			for (;;) {
+				if (sgn >= 2) {
+					item = next_tile<CG>(sched_bars, nt, true, lane, P.diag, cta_rank, heavy);
+					sgn = 0;
+					if (item < 0) return false;
+				}
+				sg.wi = decode_item(item, sgn++, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
+				if (sg.wi.kb1 > sg.wi.kb0) break;
+			}
+			sg.inst = sg.wi.tile / P.tiles_per_batch;
+			decode_tile(sg.wi.tile - sg.inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, sg.tm, sg.tn);
+			return true;
+		};
+		auto row_of = [&](const Seg &sg) { return (long long)sg.tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane; };
+		auto crow_of = [&](const Seg &sg) { return P.C + (long long)sg.inst * P.strideC + row_of(sg) * P.ldc; };
+		// hand-overs of a segment: after k-blocks kc-1, kc-1+step, ... (not the last one), and NSL at the end
+		auto nev_of = [&](const Seg &sg) { const int nseg = sg.wi.kb1 - sg.wi.kb0; return (nseg - 1 >= kc ? (nseg - 1 - kc) / step + 1 : 0) + NSL; };
+		// beta != 0: the old C is folded in up front (running sums start at (beta/alpha) * C), see the SS kernel
+		auto from_c = [&](const Seg &sg) { return preload_c && sg.wi.slot < 0 && row_of(sg) < P.M; };
+		Seg cur, nxt;
+		bool have = fetch(cur);
+		if (have) {
+#pragma unroll
+			for (int g = 0; g < NG; g++) epi_init_group<CG, true>(acc[g], g, P, from_c(cur), bs, crow_of(cur), cur.tn, h);
+		}
+		int done = 0;                 // hand-overs of `cur` taken early, while the previous segment was being stored
+		while (have) {
+			const int nev = nev_of(cur);
+			for (int ev = done; ev < nev; ev++) drain(ev % NSL);
+			const bool have_next = fetch(nxt);
+			done = 0;
+			if (have_next && from_c(nxt)) {
+				// beta != 0: the next segment's old C is needed group by group during the store below; start it towards L2 now, so that
+				// those loads are L2 hits instead of four DRAM round trips in a row on the path that gives slice buffers back
+				const float *c0 = crow_of(nxt) + (long long)nxt.tn * BN;
+#pragma unroll
+				for (int g = 0; g < NG; g++) {
+					const long long col0 = (long long)nxt.tn * BN + group_col<CG, true>(h, g);
+					if (col0 < P.N) { prefetch_l2(c0 + group_col<CG, true>(h, g)); if (col0 + 31 < P.N) prefetch_l2(c0 + group_col<CG, true>(h, g) + 31); }
+				}
+			}
+			// Store `cur` one 32-column group at a time.  As soon as group g has been staged its registers are re-armed for the next
+			// segment, and hand-overs of the next segment that are already waiting (slice <= g) are taken at once: the MMA thread
+			// needs their buffers back within a few k-blocks, a whole-tile store takes longer than that.
+			auto after_group = [&](int g) {
+				if (!have_next) return;
+#pragma unroll
+				for (int gg = 0; gg < NG; gg++)
+					if (gg == g) epi_init_group<CG, true>(acc[gg], gg, P, from_c(nxt), bs, crow_of(nxt), nxt.tn, h);
+				while (done <= g && mbar_try_wait(bar(B_TFULL + db), dph)) { drain(done % NSL); done++; }   // (a segment has >= NSL hand-overs)
+			};
+			const long long ts0 = tick<PROF>();
+			epi_store_tile<CG, false, true>(acc, P, &tmC, cur.wi, preload_c, alpha, row_of(cur), crow_of(cur), cur.tm, cur.tn, cur.inst, q, h, e, lane, cta_rank, bar_base, after_group, P.sk_q > 0 ? &tmW : nullptr);
+			t_store += tick<PROF>() - ts0;
+			cur = nxt;
+			have = have_next;
+		}
+		if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's TMA stores are complete
+		if (prof && threadIdx.x == 32 * 12) { prof[9] = w_tf; prof[10] = 0; prof[11] = t_store; prof[12] = tick<PROF>() - t_begin; }
+	}
+
+	tc_fence_before();
+	if (CG == 2) { cluster_arrive(); cluster_wait(); } else __syncthreads();
+	if (warp == 1) tmem_dealloc<CG>(tmem_base, 512);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Stream-K fix-up: C tile = alpha * (sum of the tile's partial-sum parts, in range order) + beta * C (+ bias, LeakyReLU).
 // FIXUP_SPLIT CTAs per tail tile; the parts are L2-resident (just written by K1).  Deterministic: no atomics, fixed order.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int FIXUP_SPLIT = 8;       // CTAs per tail tile
+constexpr int FIXUP_ROWS = 4;        // tile rows per CTA: every thread owns ONE 16-byte quad of C, so that all loads of the pass are in flight at once
 template <int CG>
 __global__ void __launch_bounds__(256)
 k1_tail_fixup_kernel(const K1Params P)
 {
-	constexpr int TM_ = 128 * CG, TN_ = 128 * CG, Q = TN_ / 4, ROWS_PER_CTA = TM_ / FIXUP_SPLIT;
+	constexpr int TM_ = 128 * CG, TN_ = 128 * CG, Q = TN_ / 4;
+	static_assert(FIXUP_ROWS * Q % 256 == 0 || FIXUP_ROWS * Q <= 256, "one quad per thread");
 	const int r = blockIdx.x;
 	int tm, tn;
 	const int inst = (P.sk_full + r) / P.tiles_per_batch;
 	decode_tile(P.sk_full + r - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
 	const bool conv = P.cv_wp > 0;
-	const int r_lo = (r * P.sk_nch) / P.sk_q, r_hi = ((r + 1) * P.sk_nch - 1) / P.sk_q;
+	const int r_lo = (r * P.sk_nch) / P.sk_q, r_hi = ((r + 1) * P.sk_nch - 1) / P.sk_q;   // chunk ranges that hold a part of this tile
 	const float alpha = P.alpha, beta = P.beta, slope = P.slope;
 	const bool post = P.bias != nullptr || slope != 1.f;
-#pragma unroll 4
-	for (int idx = threadIdx.x; idx < ROWS_PER_CTA * Q; idx += blockDim.x) {
-		const int row = blockIdx.y * ROWS_PER_CTA + idx / Q, c4 = (idx % Q) * 4;
+	// a range's part of this tile is its first item (h = 0) if the range starts inside the tile, else its second
+	auto slot_of = [&](int rr) { return 2 * rr + (((rr * P.sk_q) / P.sk_nch == r) ? 0 : 1); };
+	for (int idx = threadIdx.x; idx < FIXUP_ROWS * Q; idx += blockDim.x) {
+		const int row = blockIdx.y * FIXUP_ROWS + idx / Q, c4 = (idx % Q) * 4;
 		const long long gm = (long long)tm * TM_ + row, gn = (long long)tn * TN_ + c4;
 		if (gm >= P.M || gn >= P.N) continue;
+		const float *part = P.sk_ws + (long long)row * TN_ + c4;
+		// the parts are added in range order (bit-reproducible); four independent loads at a time
 		float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-		for (int rr = r_lo; rr <= r_hi; rr++) {
-			const int slot = 2 * rr + (((rr * P.sk_q) / P.sk_nch == r) ? 0 : 1);
-			const float4 v = *reinterpret_cast<const float4 *>(P.sk_ws + (long long)slot * (TM_ * TN_) + (long long)row * TN_ + c4);
-			sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+		for (int rr = r_lo; rr <= r_hi; rr += 4) {
+			float4 v[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+				v[u] = rr + u <= r_hi ? *reinterpret_cast<const float4 *>(part + (long long)slot_of(rr + u) * (TM_ * TN_)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+				if (rr + u <= r_hi) { sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w; }
 		}
 		float *cp = P.C + (long long)inst * P.strideC + gm * P.ldc + gn;
 		int valid = 4;                              // elements of this quad that exist in C
@@ -838,12 +1384,12 @@ bool cached_encode(CUtensorMap *out, unsigned rank, const void *base, const cuui
 // MN-major operand: `K` lines of `rows` contiguous fp32, pitch ld -> dims {rows, K, batch}, box {32, 32, 1}, SWIZZLE_128B_ATOM_32B
 // The third dimension walks the strided batch (extent 1 for a plain GEMM).
 bool make_operand_map(CUtensorMap *map, const float *base, long long rows, long long K, long long ld, bool kmajor,
-                      int batch, long long stride)
+                      int batch, long long stride, int box_rows = ROWS)
 {
 	cuuint64_t gdim[3], gstride[2];
 	cuuint32_t box[3], estr[3] = {1, 1, 1};
 	CUtensorMapSwizzle sw;
-	if (kmajor) { gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows; box[0] = BK; box[1] = ROWS; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
+	if (kmajor) { gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows; box[0] = BK; box[1] = (cuuint32_t)box_rows; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
 	else        { gdim[0] = (cuuint64_t)rows; gdim[1] = (cuuint64_t)K; box[0] = 32; box[1] = BK; sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; }
 	gdim[2] = (cuuint64_t)(batch > 0 ? batch : 1);
 	box[2] = 1;
@@ -876,8 +1422,8 @@ unsigned *diag_dev()
 }
 
 // common tail of the GEMM and convolution launches: scheduler counters, attributes, cluster launch
-template <int CG, bool CONV>
-cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
+template <int CG, bool CONV, bool TS = false>
+cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, const CUtensorMap &tmW, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
 	if (nt > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
 	P.num_tiles = (int)nt;
@@ -916,13 +1462,16 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 	}
 	long long *const prof_dev = prof_devs[dev];
 
-	static bool attr_sets[MAX_DEV] = {false};      // per device, one array per <CG, CONV> instantiation of this function
+	static bool attr_sets[MAX_DEV] = {false};      // per device, one array per <CG, CONV, TS> instantiation of this function
 	bool &attr_set = attr_sets[dev];
+	constexpr int smem_bytes = TS ? tsk::TS_SMEM_BYTES : SMEM_BYTES;
 	if (!attr_set) {
-		cudaError_t e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, false, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+		cudaError_t e = TS ? cudaFuncSetAttribute(k1ts_kernel<CG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+		                   : cudaFuncSetAttribute(k1_3xtf32_kernel<CG, false, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 		if (e != cudaSuccess) return e;
 		if (!CONV) {
-			e = cudaFuncSetAttribute(k1_3xtf32_kernel<CG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+			e = TS ? cudaFuncSetAttribute(k1ts_kernel<CG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+			       : cudaFuncSetAttribute(k1_3xtf32_kernel<CG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 			if (e != cudaSuccess) return e;
 		}
 		attr_set = true;
@@ -932,17 +1481,19 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned)(clusters * CG));
 	cfg.blockDim = dim3(NUM_THREADS);
-	cfg.dynamicSmemBytes = SMEM_BYTES;
+	cfg.dynamicSmemBytes = smem_bytes;
 	cfg.stream = stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr; cfg.numAttrs = 1;
-	cudaError_t le = prof ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true, false>, tmA, tmB, tmC, P)
+	cudaError_t le = TS   ? (prof ? cudaLaunchKernelEx(&cfg, k1ts_kernel<CG, true>, tmA, tmB, tmC, tmW, P) : cudaLaunchKernelEx(&cfg, k1ts_kernel<CG, false>, tmA, tmB, tmC, tmW, P))
+	               : prof ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true, false>, tmA, tmB, tmC, P)
 	                      : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false, CONV>, tmA, tmB, tmC, P);
 	// a dynamically scheduled launch advances its counter by one claim per tile plus one failed claim per cluster (a launch that
 	// the runtime rejected never ran; a kernel that trapped poisons the context, so no later launch can observe the slot)
-	if (le == cudaSuccess && P.sk_q <= 0) sched_claimed[dev][sched_slot] += (unsigned)P.num_tiles + (unsigned)clusters;
+	// (TS kernel, stream-K launch: the whole tiles are claimed dynamically too -- sk_full successful claims, one failed claim per cluster)
+	if (le == cudaSuccess && (P.sk_q <= 0 || TS)) sched_claimed[dev][sched_slot] += (unsigned)(P.sk_q > 0 ? P.sk_full : P.num_tiles) + (unsigned)clusters;
 	if (le == cudaSuccess && prof) {   // debug: per-role cycle breakdown of CTAs 0..3 on stderr
 		long long h[64];
 		if (cudaStreamSynchronize(stream) == cudaSuccess && cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -958,7 +1509,7 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 // only partly filled (c3: 192 tiles on 74 pairs = 2.6 rounds, 4096^3: 3.5, anything smaller than the machine: < 1), its
 // tiles are cut along K into equal chunk ranges, one per pair, whose partial sums meet in a workspace (decode_item,
 // k1_tail_fixup_kernel).  Taken when it shortens the last round by at least 15 % and the launch by at least 12 %.
-template <int CG, bool CONV>
+template <int CG, bool CONV, bool TS = false>
 cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
 	const int kc_eff = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
@@ -974,7 +1525,12 @@ cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, con
 		// (parts of one tile run at different k offsets) cost a few percent of a round, so small savings are not worth it
 		const double saved_rounds = 1.0 - (double)q / nch, rounds = (double)((nt + pairs - 1) / pairs);
 		// (measured: a modelled saving of 7-11 % of the launch came out as a 2-4 % loss, 13 % as a 10 % gain)
-		if (saved_rounds >= 0.15 && saved_rounds / rounds >= 0.12 && rem * nch < 0x3fffffffLL) {
+		// TS kernel [measured, profiles/r2n_sk_sweep.jsonl, r2o_sk_ablate.txt]: once at least one full round precedes the tail, the part
+		// stores, the fix-up pass and the tail's colder start cost about as much as 30 k-blocks of a pair; below that the tail is a loss
+		// (4096 x 3072 x 2048: 24 k-blocks saved, 219 vs 209 us), above it a gain (2560^3: 48 saved, 155 vs 175 us; 4096^3: 68, 494 vs 522)
+		const bool worth = TS ? (full == 0 ? saved_rounds >= 0.15 : (nch - q) * (long long)kc_eff >= 32)
+		                      : (saved_rounds >= 0.15 && saved_rounds / rounds >= 0.12);
+		if (worth && rem * nch < 0x3fffffffLL) {
 			const size_t tile_bytes = (size_t)tile_m * tile_n * sizeof(float);
 			if (cudaMallocAsync(reinterpret_cast<void **>(&ws), (size_t)(2 * ranges) * tile_bytes, stream) == cudaSuccess) {
 				P.sk_full = (int)full; P.sk_rem = (int)rem; P.sk_nch = nch; P.sk_q = (int)q; P.sk_ws = ws;
@@ -982,10 +1538,18 @@ cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, con
 			} else { cudaGetLastError(); ws = nullptr; }
 		}
 	}
-	cudaError_t e = launch_kernel<CG, CONV>(tmA, tmB, tmC, P, items, t, stream, sm_count);
+	CUtensorMap tmW = tmA;
+	if (TS && ws) {
+		// the parts of the tail travel through the TMA unit as well: workspace = {tile_n columns, slots * tile_m rows}, 32 x 32 boxes
+		cuuint64_t gdim[2] = {(cuuint64_t)tile_n, (cuuint64_t)(2 * (items - P.sk_full)) * tile_m};
+		cuuint64_t gstride[1] = {(cuuint64_t)tile_n * 4};
+		cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+		if (!cached_encode(&tmW, 2, ws, gdim, gstride, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE)) { cudaFreeAsync(ws, stream); return cudaErrorInvalidValue; }
+	}
+	cudaError_t e = launch_kernel<CG, CONV, TS>(tmA, tmB, tmC, tmW, P, items, t, stream, sm_count);
 	if (ws) {
-		if (e == cudaSuccess) {
-			k1_tail_fixup_kernel<CG><<<dim3((unsigned)P.sk_rem, FIXUP_SPLIT), 256, 0, stream>>>(P);
+		if (e == cudaSuccess && !(t.flags & 65536)) {      // (bit 16: ablation, fix-up pass skipped)
+			k1_tail_fixup_kernel<CG><<<dim3((unsigned)P.sk_rem, (unsigned)(tile_m / FIXUP_ROWS)), 256, 0, stream>>>(P);
 			e = cudaGetLastError();
 		}
 		cudaFreeAsync(ws, stream);
@@ -994,11 +1558,20 @@ cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, con
 }
 
 template <int CG>
-cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
+cudaError_t launch_cg(const Problem &p, const K1Tuning &t_in, cudaStream_t stream, int sm_count)
 {
+	// The TS kernel (A operand in tensor memory, k1ts_kernel) is the production kernel; flags bit 15 (32768) selects the round-1 SS
+	// kernel (both operands from shared memory) for A/B runs, and the RNA split experiment stays on it (truncation split only in TS).
+	const bool ts = !(t_in.flags & 32768) && t_in.split == 0;
+	K1Tuning t = t_in;
+	if (ts && t.kc_blocks > 0) {            // the TS kernel hands over one 64-column slice every kc / NSL k-blocks: kc a multiple of NSL
+		const int nsl = 2 * CG;
+		t.kc_blocks = (t.kc_blocks + nsl - 1) / nsl * nsl;
+	}
 	CUtensorMap tmA, tmB;
 	if (!make_operand_map(&tmA, p.A, p.M, p.K, p.lda, p.a_kmajor, p.batch, p.strideA)) return cudaErrorInvalidValue;
-	if (!make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.b_kmajor, p.batch, p.strideB)) return cudaErrorInvalidValue;
+	// TS kernel: K-major B is loaded in 32-row groups (see k1ts_kernel)
+	if (!make_operand_map(&tmB, p.B, p.N, p.K, p.ldb, p.b_kmajor, p.batch, p.strideB, ts ? 32 : ROWS)) return cudaErrorInvalidValue;
 	K1Params P = {};
 	P.M = p.M; P.N = p.N; P.K = p.K; P.alpha = p.alpha; P.beta = p.beta; P.C = p.C; P.ldc = p.ldc;
 	P.bias = p.bias; P.slope = p.slope;
@@ -1016,6 +1589,7 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t, cudaStream_t stream, 
 	P.tma_store = 0;
 	if (P.vecC && !(t.flags & 8192) && (p.batch <= 1 || p.strideC % 4 == 0) && make_c_map(&tmC, p.C, p.M, p.N, p.ldc, p.batch, p.strideC)) P.tma_store = 1;
 
+	if (ts) return launch_with_tail<CG, false, true>(tmA, tmB, tmC, P, nt, t, stream, sm_count);
 	return launch_with_tail<CG, false>(tmA, tmB, tmC, P, nt, t, stream, sm_count);
 }
 

@@ -100,6 +100,11 @@ __device__ __forceinline__ void tma_store_3d(const void *tmap, uint32_t src, int
 	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
 	             ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t src, int c0, int c1)
+{
+	asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+	             ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 // 4-D box store (fused convolution: x, y, output channel, image)
 __device__ __forceinline__ void tma_store_4d(const void *tmap, uint32_t src, int c0, int c1, int c2, int c3)
 {
@@ -240,9 +245,37 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float (&v)[16
 	for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- registers -> TMEM: thread t writes 16 consecutive 32-bit columns of lane (base+t) ---------------------------------
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const float (&v)[16])
+{
+	asm volatile(
+	    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+	    "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+	    ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+	      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+	      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+	      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+	    : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// one lane of a converged warp (the compiler then issues tcgen05 instructions under that predicate without an election loop)
+__device__ __forceinline__ bool elect_one()
+{
+	uint32_t p;
+	asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+	return p != 0;
+}
+// 64-bit descriptor from its two words (the low word carries the start address >> 4, so stepping a descriptor is one 32-bit add)
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi)); return d; }
+__device__ __forceinline__ float lds32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+
 // ---- register re-budgeting between warp roles (whole warpgroup must execute it) -----------------------------
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// bring the line holding `p` into L2 (no register, no scoreboard: the later load finds it there)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- 128-bit shared-memory access by 32-bit shared address --------------------------------------------------
 __device__ __forceinline__ float4 lds128(uint32_t a)
