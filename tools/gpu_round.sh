@@ -16,6 +16,6 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_
 timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; head -c 2500 $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
 if [ -z "$3" ] || [ "$3" = "0" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 5 --warmup 3 --no-ncu > $OUT/${TAG}_ncu_launches_stdout.log 2>&1; echo "ncu launches rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k1_3xtf32 -s 4 -c 1 -f -o $OUT/${TAG}_k1_c2 python bench.py --steps 5 --warmup 3 --no-shapes --no-ncu > $OUT/${TAG}_ncu_full_stdout.log 2>&1; echo "ncu full rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k1ts_kernel|k1_3xtf32" -s 4 -c 1 -f -o $OUT/${TAG}_k1_c2 python bench.py --steps 5 --warmup 3 --no-shapes --no-ncu > $OUT/${TAG}_ncu_full_stdout.log 2>&1; echo "ncu full rc=$?"
 fi
 ls -la $OUT | tail -20

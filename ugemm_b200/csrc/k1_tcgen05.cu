@@ -785,7 +785,9 @@ constexpr int B_SCHED = 26;                           // tile-index ring: full[4
 constexpr int B_TMEM = 37;
 }
 
-template <int CG, bool PROF>
+// CONV: the B operand is an image gathered by 4-D TMA boxes (implicit im2col, see the SS kernel): every 32-row group of a B stage
+// is one output-row segment, which is exactly the granularity the TS kernel loads B in.
+template <int CG, bool PROF, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmW, const K1Params P)
 {
@@ -863,6 +865,15 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 				decode_tile(wi.tile - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
 				const int a_row0 = tm * UMMA_M + (int)cta_rank * ROWS;
 				const int b_col0 = tn * BN + (CG == 2 ? 32 * (int)cta_rank : 0);    // group g: + 64 g (pair) / + 32 g (single CTA)
+				int cio[ROWS / 32], cjo[ROWS / 32];     // CONV: output row / first output column of each 32-column group
+				if (CONV) {
+#pragma unroll
+					for (int g = 0; g < ROWS / 32; g++) {
+						const int n0 = b_col0 + (CG == 2 ? 64 : 32) * g;
+						cio[g] = n0 / P.cv_wp;
+						cjo[g] = n0 - cio[g] * P.cv_wp;
+					}
+				}
 				for (int kb = wi.kb0; kb < wi.kb1; kb++) {
 					const long long tw = tick<PROF>();
 					mbar_wait(bar(B_EMPTY + s), ph ^ 1u, P.diag, 1);
@@ -870,6 +881,17 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 					mbar_arrive_expect_tx(bar(B_FULL + s), RAW_BYTES);
 					const uint32_t sA = smem_base + s * TS_STAGE_BYTES, sB = sA + OPER_BYTES, fb = bar(B_FULL + s);
 					const int k0 = kb * BK;
+					if (CONV) {
+						// k-block kb = (kernel position ki*k + kj, 32-channel block): one box {32 c, 32 x, 1 y, 1 image} per group
+						const int kpos = kb / P.cv_cblocks, c0 = (kb - kpos * P.cv_cblocks) * 32;
+						const int ki = kpos / P.cv_k, kj = kpos - ki * P.cv_k;
+						tma_load_3d_hint(sA, &tmA, fb, k0, a_row0, 0, L2_EVICT_NORMAL);        // repacked weights, K-major, shared by all images
+#pragma unroll
+						for (int g = 0; g < ROWS / 32; g++)
+							tma_load_4d_hint(sB + g * 4096, &tmB, fb, c0, cjo[g] * P.cv_stride + kj - P.cv_pad, cio[g] * P.cv_stride + ki - P.cv_pad, inst, L2_EVICT_NORMAL);
+						if (++s == TS_STAGES) { s = 0; ph ^= 1u; }
+						continue;
+					}
 					if (P.a_kmajor) tma_load_3d_hint(sA, &tmA, fb, k0, a_row0, inst, L2_EVICT_NORMAL);
 					else
 						for (int j = 0; j < ROWS / 32; j++) tma_load_3d_hint(sA + j * 4096, &tmA, fb, a_row0 + 32 * j, k0, inst, L2_EVICT_NORMAL);
@@ -1155,11 +1177,11 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 			return true;
 		};
 		auto row_of = [&](const Seg &sg) { return (long long)sg.tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane; };
-		auto crow_of = [&](const Seg &sg) { return P.C + (long long)sg.inst * P.strideC + row_of(sg) * P.ldc; };
+		auto crow_of = [&](const Seg &sg) { return P.C + (long long)sg.inst * P.strideC + row_of(sg) * (CONV ? (long long)P.cv_npix : P.ldc); };
 		// hand-overs of a segment: after k-blocks kc-1, kc-1+step, ... (not the last one), and NSL at the end
 		auto nev_of = [&](const Seg &sg) { const int nseg = sg.wi.kb1 - sg.wi.kb0; return (nseg - 1 >= kc ? (nseg - 1 - kc) / step + 1 : 0) + NSL; };
 		// beta != 0: the old C is folded in up front (running sums start at (beta/alpha) * C), see the SS kernel
-		auto from_c = [&](const Seg &sg) { return preload_c && sg.wi.slot < 0 && row_of(sg) < P.M; };
+		auto from_c = [&](const Seg &sg) { return !CONV && preload_c && sg.wi.slot < 0 && row_of(sg) < P.M; };
 		Seg cur, nxt;
 		bool have = fetch(cur);
 		if (have) {
@@ -1193,7 +1215,7 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 				while (done <= g && mbar_try_wait(bar(B_TFULL + db), dph)) { drain(done % NSL); done++; }   // (a segment has >= NSL hand-overs)
 			};
 			const long long ts0 = tick<PROF>();
-			epi_store_tile<CG, false, true>(acc, P, &tmC, cur.wi, preload_c, alpha, row_of(cur), crow_of(cur), cur.tm, cur.tn, cur.inst, q, h, e, lane, cta_rank, bar_base, after_group, P.sk_q > 0 ? &tmW : nullptr);
+			epi_store_tile<CG, CONV, true>(acc, P, &tmC, cur.wi, preload_c, alpha, row_of(cur), crow_of(cur), cur.tm, cur.tn, cur.inst, q, h, e, lane, cta_rank, bar_base, after_group, P.sk_q > 0 ? &tmW : nullptr);
 			t_store += tick<PROF>() - ts0;
 			cur = nxt;
 			have = have_next;
@@ -1466,11 +1488,11 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 	bool &attr_set = attr_sets[dev];
 	constexpr int smem_bytes = TS ? tsk::TS_SMEM_BYTES : SMEM_BYTES;
 	if (!attr_set) {
-		cudaError_t e = TS ? cudaFuncSetAttribute(k1ts_kernel<CG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+		cudaError_t e = TS ? cudaFuncSetAttribute(k1ts_kernel<CG, false, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
 		                   : cudaFuncSetAttribute(k1_3xtf32_kernel<CG, false, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 		if (e != cudaSuccess) return e;
 		if (!CONV) {
-			e = TS ? cudaFuncSetAttribute(k1ts_kernel<CG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+			e = TS ? cudaFuncSetAttribute(k1ts_kernel<CG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
 			       : cudaFuncSetAttribute(k1_3xtf32_kernel<CG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 			if (e != cudaSuccess) return e;
 		}
@@ -1487,7 +1509,7 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr; cfg.numAttrs = 1;
-	cudaError_t le = TS   ? (prof ? cudaLaunchKernelEx(&cfg, k1ts_kernel<CG, true>, tmA, tmB, tmC, tmW, P) : cudaLaunchKernelEx(&cfg, k1ts_kernel<CG, false>, tmA, tmB, tmC, tmW, P))
+	cudaError_t le = TS   ? (prof ? cudaLaunchKernelEx(&cfg, k1ts_kernel<CG, true, false>, tmA, tmB, tmC, tmW, P) : cudaLaunchKernelEx(&cfg, k1ts_kernel<CG, false, CONV>, tmA, tmB, tmC, tmW, P))
 	               : prof ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true, false>, tmA, tmB, tmC, P)
 	                      : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false, CONV>, tmA, tmB, tmC, P);
 	// a dynamically scheduled launch advances its counter by one claim per tile plus one failed claim per cluster (a launch that
@@ -1633,6 +1655,12 @@ cudaError_t launch_conv_cg(const ConvProblem &c, const K1Tuning &t, cudaStream_t
 		cuuint64_t gstride[3] = {(cuuint64_t)c.wo * 4, (cuuint64_t)npix * 4, (cuuint64_t)c.ch * npix * 4};
 		cuuint32_t box[4] = {32, 1, 32, 1}, estr[4] = {1, 1, 1, 1};
 		if (cached_encode(&tmC, 4, c.out, gdim, gstride, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE)) P.tma_store = 1;
+	}
+	// production: the TS kernel (flags bit 15 selects the round-1 SS kernel for A/B runs); kc a multiple of the slice count
+	if (!(t.flags & 32768) && t.split == 0) {
+		K1Tuning tt = t;
+		if (tt.kc_blocks > 0) { const int nsl = 2 * CG; tt.kc_blocks = (tt.kc_blocks + nsl - 1) / nsl * nsl; }
+		return launch_with_tail<CG, true, true>(tmA, tmB, tmC, P, nt, tt, stream, sm_count);
 	}
 	return launch_with_tail<CG, true>(tmA, tmB, tmC, P, nt, t, stream, sm_count);
 }
