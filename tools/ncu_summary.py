@@ -23,8 +23,11 @@ for h0, u, v in zip(hdr, units, vals):
         seen.add(h); lines.append(f"{h:88s} {u:16s} {v}"); d[h] = (u, v)
 if "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg" in d and "sm__cycles_elapsed.avg" in d:
     # 4 tensor sub-pipes per SM: busy sub-pipe cycles / (4 x elapsed cycles) = share of the elapsed time the tensor pipe is issuing
-    frac = float(d["sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg"][1]) / (4.0 * float(d["sm__cycles_elapsed.avg"][1]))
-    lines.append(f"{'tensor pipe active = hmma sub-pipe cycles / (4 x elapsed cycles)':88s} {'%':16s} {100 * frac:.2f}")
+    try:
+        frac = float(d["sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg"][1]) / (4.0 * float(d["sm__cycles_elapsed.avg"][1]))
+        lines.append(f"{'tensor pipe active = hmma sub-pipe cycles / (4 x elapsed cycles)':88s} {'%':16s} {100 * frac:.2f}")
+    except ValueError:
+        pass
 def bytes_of(k):
     u, v = d[k]; v = float(v)
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
