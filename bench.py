@@ -473,15 +473,18 @@ def run_single(args, wl_name):
 
 
 def run_multi(args, wl_name):
+    """N > 1: the sharded SGEMM of the C ABI (csrc/shard.cu, sgemm_cuda_shard_*), one process per GPU.  torch.distributed is the
+    RENDEZVOUS only (it hands rank 0's 128-byte NCCL id to every rank); communicators, buffers, streams, events, both transports
+    and the timing live behind the C ABI."""
+    import numpy as np
     import torch
     import torch.distributed as dist
 
     import ugemm_b200 as u
-    from ugemm_b200.dist import CudaOps, CudaP2POps, ShardedGemm, SlabPlan
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     # the panel broadcasts only have to keep up with the GEMM of the previous slab, not saturate NVLink: a few CTAs
-    # per communicator are enough and fit in the SMs the sharded driver leaves free (ugemm_b200/dist.py)
+    # per communicator are enough and fit in the SMs the sharded driver leaves free (csrc/shard.cu)
     os.environ.setdefault("NCCL_MAX_CTAS", "4")
     # stdout carries exactly one JSON line.  NCCL printf()s its version banner to stdout at NCCL_DEBUG=VERSION / WARN (the image
     # sets VERSION), so file descriptor 1 points at stderr for the whole run and the JSON line is written to the saved stdout.
@@ -491,129 +494,100 @@ def run_multi(args, wl_name):
     torch.cuda.set_device(local)
     u.sgemm_cuda_init(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    box = [u.Shard.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
     wl = WORKLOADS[wl_name]
     M, N, K = wl["M"], wl["N"], wl["K"]
-    plan = SlabPlan(world, rank, M, N, K)
-    sg = None
-    if args.dist == "p2p":
-        # CUDA IPC / peer access can be unavailable on a box; all ranks must then agree to fall back to NCCL broadcast
-        ok = 1
-        try:
-            sg = ShardedGemm(plan, CudaP2POps("auto"), dist)
-        except Exception as ex:  # noqa: BLE001
-            ok, sg = 0, None
-            print(f"[rank {rank}] p2p transport unavailable ({ex}); falling back to NCCL broadcast", file=sys.stderr, flush=True)
-        flag = torch.tensor([ok], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            sg = None
-    if sg is None:
-        sg = ShardedGemm(plan, CudaOps("auto"), dist)
-    sg.generate_owned(seed_a=1, seed_b=2)
     flops = 2.0 * M * N * K
+    want = u.Shard.P2P if args.dist == "p2p" else u.Shard.NCCL
+    sh = u.Shard(rank, world, box[0], M, N, K, transport=want)
+    plan = sh.p
+    if want == u.Shard.P2P and sh.transport != u.Shard.P2P and rank == 0:
+        print("peer-pull transport unavailable on this box (no CUDA IPC peer path); every rank fell back to NCCL broadcast", file=sys.stderr, flush=True)
+    sh.generate(seed_a=1, seed_b=2)
 
     def timed(distribute, steps, warmup):
-        for _ in range(warmup):
-            sg.run(distribute)
-        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            sg.run(distribute)
-        e1.record()
-        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps
+        return sh.allreduce(sh.run(distribute, steps, warmup), "max") / steps      # device time, max over ranks
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     l0 = u.launch_count()
     ms = timed(True, args.steps, args.warmup)
-    launches = u.launch_count() - l0 - args.warmup * plan.L
+    launches = u.launch_count() - l0 - args.warmup * plan["L"]
     clocks = sampler.stop() if sampler else None
     ms_compute = timed(False, max(2, args.steps // 2), 1)
+    transport = "p2p" if sh.transport == u.Shard.P2P else "nccl"
 
-    # ---- e2e: owned slabs come from pinned host memory every step, the C block goes back to pinned host memory
-    own_a = [t for t in range(plan.L) if plan.a_owner(t) == rank]
-    own_b = [t for t in range(plan.L) if plan.b_owner(t) == rank]
-    def stream_handle():
-        return torch.cuda.current_stream().cuda_stream or 1
-
-    def pinned_copy_of(buf, n):
-        h = torch.empty(n, dtype=torch.float32).pin_memory()
-        u.backend.memcpy_async(h.data_ptr(), buf.data_ptr(), 4 * n, stream_handle())
-        return h
-
-    h_a = [pinned_copy_of(sg.a[t], plan.mloc * plan.kw) for t in own_a]
-    h_b = [pinned_copy_of(sg.b[t], plan.kw * plan.nloc) for t in own_b]
-    h_c = torch.empty(plan.mloc * plan.nloc, dtype=torch.float32).pin_memory()
-    torch.cuda.synchronize()
-    h2d = sum(x.numel() for x in h_a + h_b) * 4
-    d2h = h_c.numel() * 4
-
-    def e2e_step():
-        sh = stream_handle()
-        for t, h in zip(own_a, h_a):
-            u.backend.memcpy_async(sg.a[t].data_ptr(), h.data_ptr(), 4 * h.numel(), sh)
-        for t, h in zip(own_b, h_b):
-            u.backend.memcpy_async(sg.b[t].data_ptr(), h.data_ptr(), 4 * h.numel(), sh)
-        sg.run(True)
-        u.backend.memcpy_async(h_c.data_ptr(), sg.c.data_ptr(), 4 * h_c.numel(), stream_handle())
-
-    e2e_step()
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    # ---- end to end, pipelined behind the C ABI: owned slabs start in pinned host memory every step, the C block ends there
+    sh.download_owned()
     e2e_steps = max(2, min(args.steps, 5))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1), float(h2d), float(d2h)], device="cuda")
-    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    e2e_ms = float(tmax[0].item()) / e2e_steps
+    e2e_local, h2d, d2h = sh.run_host(e2e_steps, 1)
+    e2e_ms = sh.allreduce(e2e_local, "max") / e2e_steps
+    # bytes per step over all ranks: every slab of A and B goes up exactly once (on its owner), every C block comes down once
+    h2d_all, d2h_all = 4 * (M * K + K * N), 4 * M * N
+    assert abs(sh.allreduce(float(h2d) / 2 ** 20, "sum") - h2d_all / 2 ** 20) < 1.0 and abs(sh.allreduce(float(d2h) / 2 ** 20, "sum") - d2h_all / 2 ** 20) < 1.0
+    e2e_c = sh.host_c().copy()
 
     # ---- sampled verification of this rank's C block against fp64 dot products of regenerated windows
-    import numpy as np
-    sg.run(True)
-    torch.cuda.synchronize()
-    r0, c0, rows, cols = plan.c_window()
+    sh.run(True, 1, 0)
+    c_ptr, rows, cols, r0, c0 = sh.block()
     rs = np.linspace(0, rows - 1, 6).astype(int)
     cs = np.linspace(0, cols - 1, 48).astype(int)
     full_rows = np.empty((len(rs), cols), np.float32)
     for i, r in enumerate(rs):
-        u.backend.lib().ugemm_cuda_memcpy_d2h(full_rows[i].ctypes.data, sg.c.data_ptr() + 4 * int(r) * cols, 4 * cols)
-    cblk = full_rows[:, cs]
+        u.backend.lib().ugemm_cuda_memcpy_d2h(full_rows[i].ctypes.data, c_ptr + 4 * int(r) * cols, 4 * cols)
     a_rows = np.stack([u.fill_uniform_host_2d(1, K, 1, (r0 + int(r)) * K, K) for r in rs]).astype(np.float64)
     b_cols = np.stack([u.fill_uniform_host_2d(K, 1, 2, c0 + int(c), N) for c in cs], axis=1).astype(np.float64)
     ref = a_rows @ b_cols
-    verr = float(np.linalg.norm(cblk - ref) / np.linalg.norm(ref))
-    tv = torch.tensor([verr], device="cuda")
-    dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-    verr = float(tv.item())
+    verr = float(np.linalg.norm(full_rows[:, cs] - ref) / np.linalg.norm(ref))
+    e2e_rows = e2e_c.reshape(rows, cols)[rs][:, cs]
+    verr_e2e = float(np.linalg.norm(e2e_rows - ref) / np.linalg.norm(ref))
+    verr = sh.allreduce(max(verr, verr_e2e), "max")
     if not verr <= 1e-5:
         raise SystemExit(f"sharded result failed verification: sampled relerr {verr:.3e} > 1e-5")
+
+    # ---- the other transport, same problem, same process (north_star names NCCL broadcast; the headline uses whichever --dist asks for)
+    other_ms = other_name = None
+    if world > 1:
+        sh.finish()
+        other = u.Shard.NCCL if sh.transport == u.Shard.P2P else u.Shard.P2P
+        box = [u.Shard.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        sh2 = u.Shard(rank, world, box[0], M, N, K, transport=other)
+        if sh2.transport == other:
+            sh2.generate(seed_a=1, seed_b=2)
+            steps2 = max(2, args.steps // 2)
+            other_ms = sh2.allreduce(sh2.run(True, steps2, 2), "max") / steps2
+            other_name = "p2p" if other == u.Shard.P2P else "nccl"
+        sh2.finish()
 
     if rank == 0:
         peaks = measured_peaks()
         peak = peaks["bf16_burst"] / 6.0 * world
+        recv = sum(plan["mloc"] * plan["kw"] * 4 for t in range(plan["L"]) if u.Shard.owners(world, rank, M, N, K, t)[0] != rank) + \
+               sum(plan["kw"] * plan["nloc"] * 4 for t in range(plan["L"]) if u.Shard.owners(world, rank, M, N, K, t)[1] != rank)
+        details = {"grid": f"{plan['pr']}x{plan['pc']}", "k_slabs": plan["L"], "transport": transport,
+                   "timed_region": "owner-rooted panel distribution (%s) + local GEMMs, distribution included, device time, max over ranks"
+                                   % ("NCCL broadcast in grid-row / grid-column communicators" if transport == "nccl" else "copy-engine peer pull over NVLink"),
+                   "driver": "C ABI (sgemm_cuda_shard_*): NCCL via dlopen, torch.distributed used for the rendezvous of the NCCL id only",
+                   "compute_only_tflops": flops / ms_compute / 1e9, "compute_only_ms": ms_compute,
+                   "recv_bytes_per_rank": recv, "verified_sampled_relerr_max_over_ranks": verr}
+        if other_ms is not None:
+            details[f"{other_name}_ms_per_step"] = other_ms
+            details[f"{other_name}_tflops"] = flops / other_ms / 1e9
+        details[("nccl_broadcast_ms" if transport == "nccl" else "p2p_pull_ms")] = ms
+        if other_ms is not None:
+            details[("nccl_broadcast_ms" if other_name == "nccl" else "p2p_pull_ms")] = other_ms
         line = {
             "metric": "SGEMM TFLOP/s", "value": flops / ms / 1e9, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": config_for(wl_name, world),
-            "details": {"grid": f"{plan.pr}x{plan.pc}", "k_slabs": plan.L,
-                       "transport": sg.transport,
-                       "timed_region": "owner-rooted panel distribution (%s) + local GEMMs, distribution included, max over ranks"
-                                       % ("NCCL broadcast" if sg.transport == "nccl" else "copy-engine peer pull over NVLink"),
-                       "compute_only_tflops": flops / ms_compute / 1e9, "compute_only_ms": ms_compute,
-                       "recv_bytes_per_rank": plan.recv_bytes(), "verified_sampled_relerr_max_over_ranks": verr},
-            "e2e": {"value": flops / e2e_ms / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": int(tsum[1].item()),
-                    "d2h_bytes_per_step": int(tsum[2].item()), "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "api": "ShardedGemm.run with owned slabs uploaded from pinned host memory and the C block downloaded each step"},
+            "details": details,
+            "e2e": {"value": flops / e2e_ms / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "api": "sgemm_cuda_shard_run_host: owned slabs from pinned host memory, NCCL broadcast, products and the C block's way back pipelined slab by slab; host wall clock, max over ranks"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": flops / ms_compute / 1e9, "peak": peak, "unit": "TFLOP/s",

@@ -123,6 +123,11 @@ int  ugemm_cuda_device_info(int *sm_count, int *sm_clock_khz, size_t *hbm_bytes,
  * split: 0 = truncation split, raw tile is the "big" operand; 1 = round-to-nearest split, big rewritten.
  * cta_group: 1 or 2 CTAs per MMA, 0 = by problem size (pairs once >= ~3/4 of the SM pairs have a 256x256 tile). */
 void sgemm_cuda_set_k1_tuning(int kc_blocks, int split, int cta_group);
+/* Which implementation of K1 runs: 0 = TS (op(A) in tensor memory, 64-column accumulator slices; the default),
+ * 1 = SS (round 1: both operands from shared memory, 2 x 256-column accumulators).  Same results within the gate;
+ * kept selectable for A/B measurements and so that the tests exercise both.  The
+ * round-to-nearest split experiment (split = 1) always runs on SS. */
+void sgemm_cuda_set_k1_variant(int variant);
 
 /* Cap the number of SMs K1's persistent grid occupies (0 = all).  Used by the sharded driver while NCCL panel
  * broadcasts are in flight: a persistent CTA fills an SM's registers and shared memory, so a few SMs are left
@@ -178,6 +183,38 @@ int  sgemm_cuda_mgpu(char major, char transA, char transB, int M, int N, int K, 
 /* the same call under the init / run / finish naming of the other backends' macro sets (sgemm_test.c:19-33) */
 int  sgemm_cuda_mgpu_run(char major, char transA, char transB, int M, int N, int K, float alpha, const float *A, int lda,
                          const float *B, int ldb, float beta, float *C, int ldc, int pr, int pc, int overlap, float *timings_ms);
+
+/* ---- sharded SGEMM, ONE PROCESS PER GPU (SURVEY section 8 e; csrc/shard.cu): the multi-process twin of sgemm_cuda_mgpu.
+ * Row-major NN C = A * B on a pr x pc grid of C blocks (1x1, 2x1, 2x2, 2x4 for 1/2/4/8 ranks); rank r = i*pc + j owns block (i, j).
+ * K is cut into slabs; slab t of A row-panel i starts on rank (i, t*pc/L), slab t of B column-panel j on rank (t*pr/L, j)
+ * (owner-rooted placement).  Slabs travel over NVLink by NCCL broadcast inside grid-row / grid-column communicators
+ * (transport 0: ncclCommInitRank + ncclCommSplit + ncclBroadcast; NCCL is loaded with dlopen) or by copy-engine peer pulls
+ * from CUDA-IPC-mapped allocations (transport 1; falls back to 0 on every rank when one rank has no peer path).  The product of
+ * slab t overlaps the transfer of the slabs behind it.  The reference owns one device (ocl.h:141-193); nothing there to replace.
+ * The host program brings rendezvous only: rank 0 calls sgemm_cuda_shard_unique_id and hands the 128 bytes to every rank.
+ * Every function returns 0 on success (message in sgemm_cuda_last_error); all ranks must make the same calls in the same order.
+ *   _plan / _owners   pure host arithmetic (no GPU): the partition, who owns slab t and where it sits in the owner's allocation
+ *   _init             communicators, streams, the owned-slab / received-slab / C-block allocations on the current device
+ *   _generate         every rank synthesises the slabs it owns as windows of the global ugemm_fill_uniform streams
+ *   _run              `warmup` + `steps` steps (distribute != 0: every slab travels in every step); *ms_total = this rank's
+ *                     CUDA-event time of the `steps` timed steps, taken between two barriers
+ *   _run_host         the same end to end and pipelined: owned slabs start in pinned host memory (H2D, broadcast and products
+ *                     overlap slab by slab; the last slab's product runs in row panels whose C rows go down at once); host wall clock
+ *   _allreduce        max (op 0) / sum (op 1) of one float over the ranks
+ *   _block            device pointer and global window of this rank's C block */
+int  sgemm_cuda_shard_plan(int world, int rank, int M, int N, int K, int *pr, int *pc, int *slabs, int *slab_width, int *block_rows, int *block_cols);
+int  sgemm_cuda_shard_owners(int world, int rank, int M, int N, int K, int slab, int *a_owner_rank, int *b_owner_rank, long long *a_offset, long long *b_offset);
+int  sgemm_cuda_shard_unique_id(unsigned char *id128);
+int  sgemm_cuda_shard_init(int rank, int world, const unsigned char *id128, int M, int N, int K, int transport);
+void sgemm_cuda_shard_finish(void);
+int  sgemm_cuda_shard_transport(void);   /* transport in use (0 NCCL broadcast, 1 peer pull), -1 if not initialised */
+int  sgemm_cuda_shard_generate(unsigned long long seed_a, unsigned long long seed_b, float lo, float hi);
+int  sgemm_cuda_shard_run(int distribute, int steps, int warmup, float *ms_total);
+int  sgemm_cuda_shard_allreduce(float *value, int op);
+int  sgemm_cuda_shard_block(float **d_c, int *rows, int *cols, int *row0, int *col0);
+int  sgemm_cuda_shard_host_buffers(float **h_own, long long *own_floats, float **h_c, long long *c_floats);
+int  sgemm_cuda_shard_download_owned(void);
+int  sgemm_cuda_shard_run_host(int steps, int warmup, float *ms_total, long long *h2d_bytes_per_step, long long *d2h_bytes_per_step);
 
 /* ---- counter-based uniform stream, identical on host and device (so a 32768^2 operand can be generated
  * on the GPU and any sampled row regenerated on the host for verification):

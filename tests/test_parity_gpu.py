@@ -169,6 +169,60 @@ def test_k1_all_transposes_vs_oracle(u, cg, ta, tb):
         u.set_k1_tuning(cta_group=0)
 
 
+@pytest.mark.parametrize("cg", [2, 1])
+def test_k1_ss_variant_and_rna_split_still_meet_the_gate(u, cg):
+    """The round-1 SS kernel (both operands from shared memory) stays in the library for A/B runs and the RNA-split experiment:
+    same shapes, same gate, and within round-off of the production TS kernel."""
+    M, N, K = 384, 640, 200
+    A, lda, B, ldb, Cm, ldc = O.make_problem("R", "T", "N", M, N, K, pad=(0, 0, 4), seed=21)
+    want = oracle14("R", "T", "N", M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+    u.set_k1_tuning(cta_group=cg)
+    try:
+        ts = gpu14(u, "3xtf32", "R", "T", "N", M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+        u.set_k1_variant(1)
+        ss = gpu14(u, "3xtf32", "R", "T", "N", M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+        worst = 0.0
+        for i, (m, n, k) in enumerate(K1_SHAPES):
+            for ta, tb in (("N", "N"), ("T", "T")):
+                (ar, ac), (br, bc), _ = O.stored_shapes("R", ta, tb, m, n, k)
+                worst = max(worst, check_case(u, "3xtf32", "R", ta, tb, m, n, k, 1.5, 0.5, ((-ac) % 4, (-bc) % 4, (-n) % 4 + 4), seed=40 + i))
+        u.set_k1_variant(0)
+        u.set_k1_tuning(split=1)           # round-to-nearest split: runs on the SS kernel whatever the variant
+        rna = gpu14(u, "3xtf32", "R", "T", "N", M, N, K, 1.5, A, lda, B, ldb, 0.5, Cm, ldc)
+    finally:
+        u.set_k1_variant(0)
+        u.set_k1_tuning(split=0, cta_group=0)
+    for name, got in (("TS", ts), ("SS", ss), ("SS, RNA split", rna)):
+        e = O.relerr("R", M, N, want, got, ldc)
+        print(f"cg={cg} {name}: relerr {e:.3e}")
+        assert e <= TOL, (name, e)
+    assert O.relerr("R", M, N, ts, ss, ldc) <= 2e-6
+    print(f"SS variant cg={cg}: worst relerr over the K1 shapes {worst:.3e}")
+
+
+def test_k1_promotion_interval_is_rounded_to_the_slice_count(u):
+    """The TS kernel hands one 64-column slice to the epilogue every kc / NSL k-blocks, so kc is rounded up to a multiple of the
+    slice count (4 for pair tiles, 2 for single-CTA tiles); any kc must give a correct result, and kc = 0 (never promote inside a
+    tile) must show the truncating-accumulator bias the promotion exists for."""
+    M, N, K = 512, 512, 4096
+    A, lda, B, ldb, Cm, ldc = O.make_problem("R", "N", "N", M, N, K, seed=5)
+    ref = (A.reshape(M, lda)[:, :K].astype(np.float64) @ B.reshape(K, ldb)[:, :N].astype(np.float64)).ravel()
+    errs = {}
+    try:
+        for cg in (1, 2):
+            for kc in (0, 1, 2, 3, 4, 6, 8):
+                u.set_k1_tuning(kc_blocks=kc, cta_group=cg)
+                got = gpu14(u, "3xtf32", "R", "N", "N", M, N, K, 1.0, A, lda, B, ldb, 0.0, Cm, ldc)
+                errs[(cg, kc)] = float(np.linalg.norm(got.astype(np.float64) - ref) / np.linalg.norm(ref))
+    finally:
+        u.set_k1_tuning(kc_blocks=4, cta_group=0)
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    for (cg, kc), e in errs.items():
+        if kc:
+            assert e <= TOL, (cg, kc, e)
+    assert errs[(2, 0)] > errs[(2, 4)] * 5 and errs[(1, 0)] > errs[(1, 4)] * 5
+
+
 def test_k1_column_major_and_zero_mean(u):
     for (maj, ta, tb) in (("C", "N", "N"), ("C", "T", "N"), ("C", "N", "T")):
         check_case(u, "3xtf32", maj, ta, tb, 384, 256, 160, 1.5, 0.5, (0, 0, 0), seed=3, lo=-0.5, hi=0.5)

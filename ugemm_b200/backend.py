@@ -79,6 +79,8 @@ def lib():
     L.ugemm_cuda_device_info.restype = C.c_int
     L.sgemm_cuda_set_k1_tuning.argtypes = [C.c_int, C.c_int, C.c_int]
     L.sgemm_cuda_set_k1_tuning.restype = None
+    L.sgemm_cuda_set_k1_variant.argtypes = [C.c_int]
+    L.sgemm_cuda_set_k1_variant.restype = None
     L.sgemm_cuda_set_sm_limit.argtypes = [C.c_int]
     L.sgemm_cuda_set_sm_limit.restype = None
     L.ugemm_cuda_malloc.argtypes = [C.c_size_t]
@@ -100,6 +102,23 @@ def lib():
     L.ugemm_cuda_ipc_import.restype = C.c_void_p
     L.ugemm_cuda_ipc_close.argtypes = [C.c_void_p]
     L.ugemm_cuda_ipc_close.restype = C.c_int
+    PI, PLL, PF = C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_float)
+    L.sgemm_cuda_shard_plan.argtypes = [C.c_int] * 5 + [PI] * 6
+    L.sgemm_cuda_shard_owners.argtypes = [C.c_int] * 6 + [PI, PI, PLL, PLL]
+    L.sgemm_cuda_shard_unique_id.argtypes = [C.c_char_p]
+    L.sgemm_cuda_shard_init.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.sgemm_cuda_shard_finish.argtypes = []
+    L.sgemm_cuda_shard_finish.restype = None
+    L.sgemm_cuda_shard_transport.argtypes = []
+    L.sgemm_cuda_shard_generate.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_float, C.c_float]
+    L.sgemm_cuda_shard_run.argtypes = [C.c_int, C.c_int, C.c_int, PF]
+    L.sgemm_cuda_shard_allreduce.argtypes = [PF, C.c_int]
+    L.sgemm_cuda_shard_block.argtypes = [C.POINTER(C.c_void_p), PI, PI, PI, PI]
+    L.sgemm_cuda_shard_host_buffers.argtypes = [C.POINTER(C.c_void_p), PLL, C.POINTER(C.c_void_p), PLL]
+    L.sgemm_cuda_shard_download_owned.argtypes = []
+    L.sgemm_cuda_shard_run_host.argtypes = [C.c_int, C.c_int, PF, PLL, PLL]
+    for f in ("plan", "owners", "unique_id", "init", "transport", "generate", "run", "allreduce", "block", "host_buffers", "download_owned", "run_host"):
+        getattr(L, "sgemm_cuda_shard_" + f).restype = C.c_int
     L.sgemm_cuda_mgpu_init.argtypes = [C.c_int]
     L.sgemm_cuda_mgpu_init.restype = C.c_int
     L.sgemm_cuda_mgpu_finish.argtypes = []
@@ -164,10 +183,13 @@ EXPORTED_SYMBOLS = [
     "sgemm_cuda_init", "sgemm_cuda_finish", "sgemm_cuda", "sgemm_cuda_3xtf32", "sgemm_cuda_simt",
     "sgemm_cuda_dev", "sgemm_cuda_batched", "sgemm_cuda_batched_dev", "sgemm_cuda_k1_eligible", "sgemm_cuda_time_dev", "sgemm_cuda_last_error",
     "sgemm_cuda_clear_error", "sgemm_cuda_last_kernel", "sgemm_cuda_last_repacked", "sgemm_cuda_launch_count", "ugemm_cuda_device_info",
-    "sgemm_cuda_set_k1_tuning", "sgemm_cuda_set_sm_limit", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
+    "sgemm_cuda_set_k1_tuning", "sgemm_cuda_set_k1_variant", "sgemm_cuda_set_sm_limit", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
     "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
     "ugemm_cuda_memcpy_async", "ugemm_cuda_ipc_export", "ugemm_cuda_ipc_import", "ugemm_cuda_ipc_close",
     "sgemm_cuda_mgpu_init", "sgemm_cuda_mgpu_finish", "sgemm_cuda_mgpu_count", "sgemm_cuda_mgpu", "sgemm_cuda_mgpu_run", "sgemm_cuda_mgpu_plan", "ugemm_cuda_device_count",
+    "sgemm_cuda_shard_plan", "sgemm_cuda_shard_owners", "sgemm_cuda_shard_unique_id", "sgemm_cuda_shard_init", "sgemm_cuda_shard_finish",
+    "sgemm_cuda_shard_transport", "sgemm_cuda_shard_generate", "sgemm_cuda_shard_run", "sgemm_cuda_shard_allreduce", "sgemm_cuda_shard_block",
+    "sgemm_cuda_shard_host_buffers", "sgemm_cuda_shard_download_owned", "sgemm_cuda_shard_run_host",
     "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
     "ugemm_cuda_probe_tf32", "im2col_cuda", "im2col_cuda_dev", "convolution_cuda", "convolution_cuda_LReLU",
     "convolution_cuda_dev", "convolution_cuda_batched_dev", "sgemm_cuda_set_conv_fusion", "sgemm_cuda_last_conv_fused", "saxpy_cuda", "saxpy_cuda_dev", "sgemv_cuda", "sgemv_cuda_dev",
@@ -260,6 +282,11 @@ def k1_eligible(major, ta, tb, M, N, K, dA, lda, dB, ldb, dC, ldc):
 
 def set_k1_tuning(kc_blocks=-1, split=-1, cta_group=-1):
     lib().sgemm_cuda_set_k1_tuning(kc_blocks, split, cta_group)
+
+
+def set_k1_variant(variant=0):
+    """0 = TS kernel (A in tensor memory, default), 1 = round-1 SS kernel."""
+    lib().sgemm_cuda_set_k1_variant(int(variant))
 
 
 def set_sm_limit(sms=0):
@@ -373,6 +400,86 @@ def ipc_import(handle):
 
 def ipc_close(ptr):
     lib().ugemm_cuda_ipc_close(C.c_void_p(ptr))
+
+
+class Shard:
+    """ctypes mirror of the one-process-per-GPU sharded SGEMM of the C ABI (csrc/shard.cu, sgemm_cuda_shard_*).  The caller brings
+    rendezvous only: rank 0 calls Shard.unique_id() and hands the 128 bytes to every rank."""
+    NCCL, P2P = 0, 1
+
+    @staticmethod
+    def plan(world, rank, M, N, K):
+        v = [C.c_int(0) for _ in range(6)]
+        if lib().sgemm_cuda_shard_plan(world, rank, M, N, K, *[C.byref(x) for x in v]):
+            check()
+            raise UgemmCudaError("sgemm_cuda_shard_plan failed")
+        return dict(zip(("pr", "pc", "L", "kw", "mloc", "nloc"), (x.value for x in v)))
+
+    @staticmethod
+    def owners(world, rank, M, N, K, t):
+        ao, bo, aoff, boff = C.c_int(0), C.c_int(0), C.c_longlong(0), C.c_longlong(0)
+        if lib().sgemm_cuda_shard_owners(world, rank, M, N, K, t, C.byref(ao), C.byref(bo), C.byref(aoff), C.byref(boff)):
+            check()
+            raise UgemmCudaError("sgemm_cuda_shard_owners failed")
+        return ao.value, bo.value, aoff.value, boff.value
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        if lib().sgemm_cuda_shard_unique_id(buf):
+            check()
+            raise UgemmCudaError("sgemm_cuda_shard_unique_id failed")
+        return buf.raw
+
+    def __init__(self, rank, world, uid, M, N, K, transport=1):
+        self.rank, self.world, self.M, self.N, self.K = rank, world, M, N, K
+        if lib().sgemm_cuda_shard_init(rank, world, uid, M, N, K, transport):
+            check()
+            raise UgemmCudaError("sgemm_cuda_shard_init failed")
+        self.transport = lib().sgemm_cuda_shard_transport()
+        self.p = Shard.plan(world, rank, M, N, K)
+
+    def _call(self, name, *args):
+        if getattr(lib(), "sgemm_cuda_shard_" + name)(*args):
+            check()
+            raise UgemmCudaError(f"sgemm_cuda_shard_{name} failed")
+
+    def generate(self, seed_a=1, seed_b=2, lo=0.0, hi=1.0):
+        self._call("generate", seed_a, seed_b, lo, hi)
+
+    def run(self, distribute=True, steps=1, warmup=0):
+        """this rank's CUDA-event milliseconds for `steps` steps (take the max over ranks with allreduce_max)"""
+        ms = C.c_float(0)
+        self._call("run", 1 if distribute else 0, steps, warmup, C.byref(ms))
+        return ms.value
+
+    def run_host(self, steps=1, warmup=0):
+        ms, up, down = C.c_float(0), C.c_longlong(0), C.c_longlong(0)
+        self._call("run_host", steps, warmup, C.byref(ms), C.byref(up), C.byref(down))
+        return ms.value, up.value, down.value
+
+    def download_owned(self):
+        self._call("download_owned")
+
+    def allreduce(self, value, op="max"):
+        v = C.c_float(value)
+        self._call("allreduce", C.byref(v), 0 if op == "max" else 1)
+        return v.value
+
+    def block(self):
+        """(device pointer, rows, cols, row0, col0) of this rank's C block"""
+        ptr, r, c, r0, c0 = C.c_void_p(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        self._call("block", C.byref(ptr), C.byref(r), C.byref(c), C.byref(r0), C.byref(c0))
+        return ptr.value, r.value, c.value, r0.value, c0.value
+
+    def host_c(self):
+        import numpy as np
+        hown, n1, hc, n2 = C.c_void_p(0), C.c_longlong(0), C.c_void_p(0), C.c_longlong(0)
+        self._call("host_buffers", C.byref(hown), C.byref(n1), C.byref(hc), C.byref(n2))
+        return np.ctypeslib.as_array(C.cast(hc, C.POINTER(C.c_float)), shape=(n2.value,))
+
+    def finish(self):
+        lib().sgemm_cuda_shard_finish()
 
 
 def sgemm_cuda_mgpu_init(ngpus):

@@ -62,6 +62,10 @@ void set_error(const char *fmt, ...)
 	if (getenv("UGEMM_CUDA_VERBOSE")) fprintf(stderr, "ugemm_cuda: %s\n", g_err);
 }
 
+} // namespace
+namespace ugemm { void report_error(const char *msg) { set_error("%s", msg); } }   // for the other translation units of the C ABI (shard.cu)
+namespace {
+
 #define CU_TRY(expr, what)                                                                   \
 	do {                                                                                     \
 		cudaError_t e__ = (expr);                                                            \
@@ -634,6 +638,12 @@ void sgemm_cuda_set_k1_tuning(int kc_blocks, int split, int cta_group)
 	if (kc_blocks >= 0) g.tuning.kc_blocks = kc_blocks;
 	if (split >= 0) g.tuning.split = split ? 1 : 0;
 	if (cta_group >= 0 && cta_group <= 2) g.tuning.cta_group = cta_group;   // 0 = choose by problem size
+}
+
+void sgemm_cuda_set_k1_variant(int variant)
+{
+	if (variant == 1) g.tuning.flags |= 32768;        // round-1 SS kernel (both operands from shared memory)
+	else if (variant == 0) g.tuning.flags &= ~32768;  // TS kernel (A in tensor memory): the default
 }
 
 void sgemm_cuda_set_sm_limit(int sms) { g.sm_limit = sms > 0 ? sms : 0; }
