@@ -524,10 +524,12 @@ def run_multi(args, wl_name):
     e2e_steps = max(2, min(args.steps, 5))
     e2e_local, h2d, d2h = sh.run_host(e2e_steps, 1)
     e2e_ms = sh.allreduce(e2e_local, "max") / e2e_steps
+    e2e_c_keep = sh.host_c().copy()
+    floor_ms = sh.allreduce(sh.copy_floor(3), "max") / 3        # the same bytes up and down with nothing else going on
     # bytes per step over all ranks: every slab of A and B goes up exactly once (on its owner), every C block comes down once
     h2d_all, d2h_all = 4 * (M * K + K * N), 4 * M * N
     assert abs(sh.allreduce(float(h2d) / 2 ** 20, "sum") - h2d_all / 2 ** 20) < 1.0 and abs(sh.allreduce(float(d2h) / 2 ** 20, "sum") - d2h_all / 2 ** 20) < 1.0
-    e2e_c = sh.host_c().copy()
+    e2e_c = e2e_c_keep
 
     # ---- sampled verification of this rank's C block against fp64 dot products of regenerated windows
     sh.run(True, 1, 0)
@@ -586,7 +588,7 @@ def run_multi(args, wl_name):
             "config": config_for(wl_name, world),
             "details": details,
             "e2e": {"value": flops / e2e_ms / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
-                    "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "host_link_floor_ms": floor_ms, "frac_of_host_link_floor": floor_ms / e2e_ms,
                     "api": "sgemm_cuda_shard_run_host: owned slabs from pinned host memory, NCCL broadcast, products and the C block's way back pipelined slab by slab; host wall clock, max over ranks"},
             "gpu_launches": int(launches),
             "clocks": clocks,

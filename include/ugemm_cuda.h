@@ -215,6 +215,8 @@ int  sgemm_cuda_shard_block(float **d_c, int *rows, int *cols, int *row0, int *c
 int  sgemm_cuda_shard_host_buffers(float **h_own, long long *own_floats, float **h_c, long long *c_floats);
 int  sgemm_cuda_shard_download_owned(void);
 int  sgemm_cuda_shard_run_host(int steps, int warmup, float *ms_total, long long *h2d_bytes_per_step, long long *d2h_bytes_per_step);
+/* the host-link floor of _run_host on this box: the same bytes up and down at once, no broadcast, no product; host wall clock */
+int  sgemm_cuda_shard_copy_floor(int steps, float *ms_total);
 
 /* ---- counter-based uniform stream, identical on host and device (so a 32768^2 operand can be generated
  * on the GPU and any sampled row regenerated on the host for verification):

@@ -1,5 +1,5 @@
 """Worker for tests/test_dist_cpu.py: one rank of a gloo job running the sharded-GEMM schedule on CPU tensors.
-The local GEMM is the ORACLE here (this file is test infrastructure); the product path uses CudaOps."""
+The local GEMM is the ORACLE here (this file is test infrastructure); the product path is csrc/shard.cu)."""
 import os
 import sys
 

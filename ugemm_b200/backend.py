@@ -117,7 +117,8 @@ def lib():
     L.sgemm_cuda_shard_host_buffers.argtypes = [C.POINTER(C.c_void_p), PLL, C.POINTER(C.c_void_p), PLL]
     L.sgemm_cuda_shard_download_owned.argtypes = []
     L.sgemm_cuda_shard_run_host.argtypes = [C.c_int, C.c_int, PF, PLL, PLL]
-    for f in ("plan", "owners", "unique_id", "init", "transport", "generate", "run", "allreduce", "block", "host_buffers", "download_owned", "run_host"):
+    L.sgemm_cuda_shard_copy_floor.argtypes = [C.c_int, PF]
+    for f in ("plan", "owners", "unique_id", "init", "transport", "generate", "run", "allreduce", "block", "host_buffers", "download_owned", "run_host", "copy_floor"):
         getattr(L, "sgemm_cuda_shard_" + f).restype = C.c_int
     L.sgemm_cuda_mgpu_init.argtypes = [C.c_int]
     L.sgemm_cuda_mgpu_init.restype = C.c_int
@@ -189,7 +190,7 @@ EXPORTED_SYMBOLS = [
     "sgemm_cuda_mgpu_init", "sgemm_cuda_mgpu_finish", "sgemm_cuda_mgpu_count", "sgemm_cuda_mgpu", "sgemm_cuda_mgpu_run", "sgemm_cuda_mgpu_plan", "ugemm_cuda_device_count",
     "sgemm_cuda_shard_plan", "sgemm_cuda_shard_owners", "sgemm_cuda_shard_unique_id", "sgemm_cuda_shard_init", "sgemm_cuda_shard_finish",
     "sgemm_cuda_shard_transport", "sgemm_cuda_shard_generate", "sgemm_cuda_shard_run", "sgemm_cuda_shard_allreduce", "sgemm_cuda_shard_block",
-    "sgemm_cuda_shard_host_buffers", "sgemm_cuda_shard_download_owned", "sgemm_cuda_shard_run_host",
+    "sgemm_cuda_shard_host_buffers", "sgemm_cuda_shard_download_owned", "sgemm_cuda_shard_run_host", "sgemm_cuda_shard_copy_floor",
     "ugemm_fill_uniform_host", "ugemm_fill_uniform_dev", "ugemm_fill_uniform_host_2d", "ugemm_fill_uniform_dev_2d",
     "ugemm_cuda_probe_tf32", "im2col_cuda", "im2col_cuda_dev", "convolution_cuda", "convolution_cuda_LReLU",
     "convolution_cuda_dev", "convolution_cuda_batched_dev", "sgemm_cuda_set_conv_fusion", "sgemm_cuda_last_conv_fused", "saxpy_cuda", "saxpy_cuda_dev", "sgemv_cuda", "sgemv_cuda_dev",
@@ -460,6 +461,12 @@ class Shard:
 
     def download_owned(self):
         self._call("download_owned")
+
+    def copy_floor(self, steps=2):
+        """host wall-clock ms of `steps` x (owned slabs up + C block down at once, nothing else): the host-link floor of run_host"""
+        ms = C.c_float(0)
+        self._call("copy_floor", steps, C.byref(ms))
+        return ms.value
 
     def allreduce(self, value, op="max"):
         v = C.c_float(value)

@@ -501,4 +501,25 @@ int sgemm_cuda_shard_run_host(int steps, int warmup, float *ms_total, long long 
 	return 0;
 }
 
+// The host-link floor of the end-to-end step on this box: the same bytes as sgemm_cuda_shard_run_host moves (owned slabs up, C block
+// down, both directions at once on their own streams), no broadcast, no product.  Host wall clock between two barriers.
+int sgemm_cuda_shard_copy_floor(int steps, float *ms_total)
+{
+	if (sgemm_cuda_shard_host_buffers(nullptr, nullptr, nullptr, nullptr)) return 1;
+	const Plan &p = S.p;
+	timespec t0{}, t1{};
+	if (barrier_on(S.xfer) || barrier_on(S.comp)) return 1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (int it = 0; it < steps; it++) {
+		SH_CUDA(cudaMemcpyAsync(S.own, S.h_own, (size_t)S.own_floats * 4, cudaMemcpyHostToDevice, S.up), "H2D (owned slabs)");
+		SH_CUDA(cudaMemcpyAsync(S.h_c, S.c, (size_t)p.mloc * p.nloc * 4, cudaMemcpyDeviceToHost, S.down), "D2H (C block)");
+	}
+	SH_CUDA(cudaStreamSynchronize(S.up), "cudaStreamSynchronize");
+	SH_CUDA(cudaStreamSynchronize(S.down), "cudaStreamSynchronize");
+	if (barrier_on(S.comp)) return 1;
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	if (ms_total) *ms_total = (float)((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+	return 0;
+}
+
 } // extern "C"
