@@ -13,6 +13,17 @@ harness: $(LIB)
 	$(MAKE) -C harness all
 check: all
 	cd harness && ./check_sgemm_cuda M=1024 N=1024 K=1024 && ./sgemm_test_cuda
+# compute-sanitizer over small cases of every kernel (K1 TS and SS, stream-K tail, K2, fused convolution, level 1/2, DGEMM).
+# racecheck is expected to report ONE hazard class only: the shared-memory word that tcgen05.alloc writes the TMEM base address
+# into -- the write is made by the allocation hardware and ordered for its readers by tcgen05.fence + the CTA / cluster barrier,
+# which racecheck does not model.  Needs a B200; the log goes to profiles/.
+sanitize: $(LIB) oracle
+	@mkdir -p gpurun_out
+	@for tool in memcheck synccheck racecheck; do \
+	  echo "== compute-sanitizer --tool $$tool"; \
+	  compute-sanitizer --tool $$tool --print-limit 20 python tools/sanitize_cases.py > gpurun_out/sanitize_$$tool.log 2>&1; echo "rc=$$?"; \
+	  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Error|relerr|conv|ok" gpurun_out/sanitize_$$tool.log | sort | uniq -c | sort -rn | head -40; \
+	done
 clean:
 	rm -f $(LIB); $(MAKE) -C harness clean; $(MAKE) -C oracle clean
-.PHONY: all oracle harness check clean
+.PHONY: all oracle harness check sanitize clean

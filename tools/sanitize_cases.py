@@ -22,6 +22,20 @@ for ta in "NT":
         case("3xtf32", ta, tb, 132, 260, 36, (4, 0, 4), cg=1)
         case("simt", ta, tb, 129, 97, 131, (3, 5, 7))
 case("auto", "N", "N", 300, 257, 100, (1, 2, 3))        # repack path
+# TS kernel: several tiles per CTA pair (the slice-buffer ring wraps, the pipelined epilogue re-arms groups and takes early
+# hand-overs), the stream-K tail with TMA-stored parts + fix-up pass, single-CTA tiles, and the round-1 SS kernel beside it
+u.set_sm_limit(4)
+case("3xtf32", "N", "N", 768, 768, 512, (0, 0, 0), cg=2)
+case("3xtf32", "T", "T", 640, 384, 320, (0, 0, 4), beta=0.0, cg=1)
+u.set_sm_limit(0)
+case("3xtf32", "N", "N", 1100, 900, 1024, (0, 0, 0), cg=2)
+u.set_k1_variant(1)
+u.set_sm_limit(4)
+case("3xtf32", "N", "N", 768, 768, 512, (0, 0, 0), cg=2)      # the round-1 kernel with its tile-index slots reused, too
+u.set_sm_limit(0)
+case("3xtf32", "N", "T", 300, 260, 100, (0, 0, 0), cg=2)
+case("3xtf32", "T", "N", 132, 260, 36, (4, 0, 4), cg=1)
+u.set_k1_variant(0)
 case("3xtf32", "N", "N", 512, 512, 256, (0, 0, 0), beta=0.0, cg=2)
 x = rng.uniform(-1, 1, 8 * 14 * 14).astype(np.float32); w = rng.uniform(-1, 1, 16 * 8 * 9).astype(np.float32); b = rng.uniform(-1, 1, 16).astype(np.float32)
 out = np.zeros(16 * 14 * 14, np.float32)

@@ -1014,6 +1014,13 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 					const uint32_t pempty = sched_bars + 8u * (14 + SCHED_SLOTS + ((n - 1) & (SCHED_SLOTS - 1))), pph = ((n - 1) / SCHED_SLOTS) & 1;
 					if (CG == 2) mbar_wait_cluster(pempty, pph, P.diag, 7); else mbar_wait(pempty, pph, P.diag, 7);
 				}
+				if (n >= SCHED_SLOTS) {
+					// the slot's own barrier (item n - 4 read by everyone): implied by the wait above, since roles pick items up in order, and
+					// therefore always complete already -- waited on all the same so that the overwrite below is ordered after those reads by
+					// the barrier they arrived on, not by transitivity (compute-sanitizer racecheck reports the slot otherwise)
+					const uint32_t sempty = sched_bars + 8u * (14 + SCHED_SLOTS + slot), sph = ((n / SCHED_SLOTS) & 1) ^ 1u;
+					if (CG == 2) mbar_wait_cluster(sempty, sph, P.diag, 7); else mbar_wait(sempty, sph, P.diag, 7);
+				}
 				int tile = -1;
 				if (!tail_given) {
 					tile = (int)(atomicAdd(P.sched, 1u) - P.sched_base);
