@@ -14,4 +14,4 @@ beta = float(sys.argv[1])
 print("beta", beta, flush=True)
 avg, best = u.sgemm_cuda_time_dev("3xtf32", 2, 1, "R", "N", "T", M, N, K, 1.5, dA, K, dB, K, beta, dC, N)
 PY
-for b in 0.0 0.5; do UGEMM_K1_FLAGS=$((32768+2048+32+1)) timeout 60 python /tmp/p5.py $b 2>&1 | grep -E "beta|k1prof cta[01] " | tail -3 | cut -c1-400; done
+for b in 0.0 0.5; do UGEMM_K1_FLAGS=$((2048+32+1)) timeout 60 python /tmp/p5.py $b 2>&1 | grep -E "beta|k1prof cta[01] " | tail -3 | cut -c1-400; done

@@ -203,8 +203,10 @@ template <int CG, bool TS>
 __device__ __forceinline__ int group_col(int h, int g) { return TS ? g * 64 + h * 32 : h * (64 * CG) + g * 32; }
 
 // one group's running sums at the start of a tile (TS kernel: groups are re-armed one by one while the previous tile is stored)
+// (TS kernel: the loaded values go into the accumulator registers UNTOUCHED -- no arithmetic on them, so nothing waits for the loads
+// until the first promotion adds into them, k-blocks later; the beta/alpha weighting is carried by the promotion instead, see there)
 template <int CG, bool TS>
-__device__ __forceinline__ void epi_init_group(float (&a)[32], int g, const K1Params &P, bool from_c, float bs, const float *crow, int tn, int h)
+__device__ __forceinline__ void epi_init_group(float (&a)[32], int g, const K1Params &P, bool from_c, const float *crow, int tn, int h)
 {
 	constexpr int BN = 128 * CG;
 	if (from_c) {
@@ -213,11 +215,11 @@ __device__ __forceinline__ void epi_init_group(float (&a)[32], int g, const K1Pa
 #pragma unroll
 			for (int i = 0; i < 32; i += 4) {
 				const float4 cv = *reinterpret_cast<const float4 *>(crow + col0 + i);
-				a[i + 0] = bs * cv.x; a[i + 1] = bs * cv.y; a[i + 2] = bs * cv.z; a[i + 3] = bs * cv.w;
+				a[i + 0] = cv.x; a[i + 1] = cv.y; a[i + 2] = cv.z; a[i + 3] = cv.w;
 			}
 		} else {
 #pragma unroll
-			for (int i = 0; i < 32; i++) a[i] = (col0 + i < P.N) ? bs * crow[col0 + i] : 0.f;
+			for (int i = 0; i < 32; i++) a[i] = (col0 + i < P.N) ? crow[col0 + i] : 0.f;
 		}
 	} else {
 #pragma unroll
@@ -1136,14 +1138,16 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 		const int e = warp - 12;
 		const int q = e & 3;        // TMEM lane quarter (must equal warp % 4)
 		const int h = e >> 2;       // column half of every slice
-		const float alpha = P.alpha;
-		const float bs = P.beta / P.alpha;
-		const bool preload_c = P.beta != 0.f && fabsf(bs) < 1e18f && fabsf(bs) > 1e-18f;
+		// beta != 0: the old C is folded in UP FRONT, as in the SS kernel, but with the weighting turned round: the running sums of a
+		// tile start at C itself (a pure load) and every promotion adds (alpha/beta) * partial sums (one FMA instead of one add), the
+		// tile end multiplies by beta.  A stream-K part starts at zero and stays unweighted (the fix-up pass applies alpha and beta).
+		const float ab = P.alpha / P.beta;
+		const bool preload_c = P.beta != 0.f && fabsf(ab) < 1e18f && fabsf(ab) > 1e-18f;
 		int db = 0; uint32_t dph = 0;                      // next slice buffer to be handed over, and its phase
 		long long w_tf = 0, t_store = 0; const long long t_begin = tick<PROF>();
 		float acc[NG][32];
 		// promote slice j: add the 32 columns of this thread's half of the handed-over buffer into the running fp32 sums
-		auto drain = [&](int j) {
+		auto drain = [&](int j, float r) {
 			const long long tw = tick<PROF>();
 			mbar_wait(bar(B_TFULL + db), dph, P.diag, 5);
 			w_tf += tick<PROF>() - tw;
@@ -1157,7 +1161,7 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 				for (int jj = 0; jj < NSL; jj++)
 					if (jj == j) {
 #pragma unroll
-						for (int i = 0; i < 16; i++) acc[jj][16 * half + i] += v[i];   // fp32 round-to-nearest promotion
+						for (int i = 0; i < 16; i++) acc[jj][16 * half + i] = fmaf(r, v[i], acc[jj][16 * half + i]);   // fp32 round-to-nearest promotion (r = 1: an add)
 					}
 			}
 			tc_fence_before();
@@ -1188,17 +1192,20 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 		// hand-overs of a segment: after k-blocks kc-1, kc-1+step, ... (not the last one), and NSL at the end
 		auto nev_of = [&](const Seg &sg) { const int nseg = sg.wi.kb1 - sg.wi.kb0; return (nseg - 1 >= kc ? (nseg - 1 - kc) / step + 1 : 0) + NSL; };
 		// beta != 0: the old C is folded in up front (running sums start at (beta/alpha) * C), see the SS kernel
-		auto from_c = [&](const Seg &sg) { return !CONV && preload_c && sg.wi.slot < 0 && row_of(sg) < P.M; };
+		auto weighted = [&](const Seg &sg) { return !CONV && preload_c && sg.wi.slot < 0; };     // this segment's sums are in units of beta
+		auto from_c = [&](const Seg &sg) { return weighted(sg) && row_of(sg) < P.M; };
+		auto weight = [&](const Seg &sg) { return weighted(sg) ? ab : 1.f; };
 		Seg cur, nxt;
 		bool have = fetch(cur);
 		if (have) {
 #pragma unroll
-			for (int g = 0; g < NG; g++) epi_init_group<CG, true>(acc[g], g, P, from_c(cur), bs, crow_of(cur), cur.tn, h);
+			for (int g = 0; g < NG; g++) epi_init_group<CG, true>(acc[g], g, P, from_c(cur), crow_of(cur), cur.tn, h);
 		}
 		int done = 0;                 // hand-overs of `cur` taken early, while the previous segment was being stored
 		while (have) {
 			const int nev = nev_of(cur);
-			for (int ev = done; ev < nev; ev++) drain(ev % NSL);
+			const float r_cur = weight(cur);
+			for (int ev = done; ev < nev; ev++) drain(ev % NSL, r_cur);
 			const bool have_next = fetch(nxt);
 			done = 0;
 			if (have_next && from_c(nxt)) {
@@ -1214,15 +1221,16 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 			// Store `cur` one 32-column group at a time.  As soon as group g has been staged its registers are re-armed for the next
 			// segment, and hand-overs of the next segment that are already waiting (slice <= g) are taken at once: the MMA thread
 			// needs their buffers back within a few k-blocks, a whole-tile store takes longer than that.
+			const float r_nxt = have_next ? weight(nxt) : 1.f;
 			auto after_group = [&](int g) {
 				if (!have_next) return;
 #pragma unroll
 				for (int gg = 0; gg < NG; gg++)
-					if (gg == g) epi_init_group<CG, true>(acc[gg], gg, P, from_c(nxt), bs, crow_of(nxt), nxt.tn, h);
-				while (done <= g && mbar_try_wait(bar(B_TFULL + db), dph)) { drain(done % NSL); done++; }   // (a segment has >= NSL hand-overs)
+					if (gg == g) epi_init_group<CG, true>(acc[gg], gg, P, from_c(nxt), crow_of(nxt), nxt.tn, h);
+				while (done <= g && mbar_try_wait(bar(B_TFULL + db), dph)) { drain(done % NSL, r_nxt); done++; }   // (a segment has >= NSL hand-overs)
 			};
 			const long long ts0 = tick<PROF>();
-			epi_store_tile<CG, CONV, true>(acc, P, &tmC, cur.wi, preload_c, alpha, row_of(cur), crow_of(cur), cur.tm, cur.tn, cur.inst, q, h, e, lane, cta_rank, bar_base, after_group, P.sk_q > 0 ? &tmW : nullptr);
+			epi_store_tile<CG, CONV, true>(acc, P, &tmC, cur.wi, preload_c, weighted(cur) ? P.beta : P.alpha, row_of(cur), crow_of(cur), cur.tm, cur.tn, cur.inst, q, h, e, lane, cta_rank, bar_base, after_group, P.sk_q > 0 ? &tmW : nullptr);
 			t_store += tick<PROF>() - ts0;
 			cur = nxt;
 			have = have_next;
