@@ -14,4 +14,4 @@ for (M, N, K) in ((4096, 3072, 2048), (4096, 4096, 4096), (2560, 2560, 2560)):
     out[f"{M}x{N}x{K}"] = [round(avg * 1000, 1), round(best * 1000, 1)]
 print(json.dumps(out))
 PY
-for F in 32769 $((32769+65536)) $((32769+65536+16)) 34817 $((34817+16)); do UGEMM_K1_FLAGS=$F timeout 100 python /tmp/ska.py 2>&1 | tail -1; done
+for F in $((1+131072)) $((1+131072+65536)) $((1+131072+65536+16)) 2049 $((2049+16)); do UGEMM_K1_FLAGS=$F timeout 100 python /tmp/ska.py 2>&1 | tail -1; done

@@ -1567,7 +1567,7 @@ cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, con
 		// (4096 x 3072 x 2048: 24 k-blocks saved, 219 vs 209 us), above it a gain (2560^3: 48 saved, 155 vs 175 us; 4096^3: 68, 494 vs 522)
 		const bool worth = TS ? (full == 0 ? saved_rounds >= 0.15 : (nch - q) * (long long)kc_eff >= 32)
 		                      : (saved_rounds >= 0.15 && saved_rounds / rounds >= 0.12);
-		if (worth && rem * nch < 0x3fffffffLL) {
+		if ((worth || ((t.flags & 131072) && saved_rounds > 0.0)) && rem * nch < 0x3fffffffLL) {      // (bit 17: tail whenever it saves anything, A/B runs)
 			const size_t tile_bytes = (size_t)tile_m * tile_n * sizeof(float);
 			if (cudaMallocAsync(reinterpret_cast<void **>(&ws), (size_t)(2 * ranges) * tile_bytes, stream) == cudaSuccess) {
 				P.sk_full = (int)full; P.sk_rem = (int)rem; P.sk_nch = nch; P.sk_q = (int)q; P.sk_ws = ws;
