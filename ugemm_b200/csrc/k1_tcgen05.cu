@@ -269,80 +269,63 @@ __device__ __forceinline__ void epi_store_tile(float (&acc)[2 * CG][32], const K
                                                After after = After(), const CUtensorMap *tmWp = nullptr)
 {
 	constexpr int BN = 128 * CG, UMMA_M = 128 * CG, NG = 2 * CG;
-	if (wi.slot >= 0 && tmWp != nullptr && (P.flags & 16)) {      // ablation: parts not stored
-#pragma unroll
-		for (int g = 0; g < NG; g++) after(g);
-		return;
-	}
-	if (wi.slot >= 0 && tmWp != nullptr) {
-		// stream-K part through the TMA unit: the workspace is a {BN, slots * UMMA_M} tensor, the part's tile starts at row slot * UMMA_M
+	// fused alpha/beta + store; ld padding and ragged edges are never written
+	const float beta = preload_c ? 0.f : P.beta;   // already folded into acc when preloaded
+	const bool part = wi.slot >= 0;                // stream-K part: raw partial sums to the workspace tile of this item
+	const bool part_tma = part && tmWp != nullptr;
+	if (part_tma || (!part && P.tma_store && beta == 0.f)) {
+		// TMA-store epilogue: each warp stages one 32-row x 32-column box at a time in shared memory (128B-swizzled, so a
+		// thread's eight 16-byte stores of its row are conflict-free) and hands it to the TMA unit, which writes whole
+		// 128-byte lines and clips the box at the matrix edge -- instead of 32 row-strided 16-byte stores per instruction.
+		// A stream-K part takes the same way into the workspace, a {BN, slots * UMMA_M} tensor whose tile `slot` starts at row
+		// slot * UMMA_M: raw sums, no alpha, no bias.  (One loop for both, so that the `after` hook is expanded once per group.)
+		const float slope = P.slope;
+		const bool post = !part && (P.bias != nullptr || slope != 1.f);
+		const float bm = (post && P.bias && row < P.M) ? __ldg(P.bias + row) : 0.f;
+		const float scale = part ? 1.f : alpha;
+		auto act = [&](float x) { x += bm; return x > 0.f ? x : x * slope; };
 		const uint32_t cst = bar_base + 1024u + (uint32_t)e * CSTAGE_BYTES;
-		const int row0 = wi.slot * UMMA_M + (int)cta_rank * ROWS + q * 32;
+		const int row0 = (part ? wi.slot * UMMA_M : tm * UMMA_M) + (int)cta_rank * ROWS + q * 32;
+		const bool skip = (P.flags & 16) != 0;         // ablation: nothing is stored
 #pragma unroll
 		for (int g = 0; g < NG; g++) {
-			if (lane == 0) bulk_wait_group_read0();
-			__syncwarp();
+			const int col0 = (part ? 0 : tn * BN) + group_col<CG, TS>(h, g);
+			// CONV: the 32 columns are one output-row segment (io, jo0 .. jo0+31) of the padded column index
+			const int io = (CONV && !part) ? col0 / P.cv_wp : 0, jo0 = (CONV && !part) ? col0 - io * P.cv_wp : 0;
+			// warp-uniform: the whole box lies outside C
+			const bool outside = !part && (row0 >= P.M || col0 >= P.N || (CONV && (io >= P.cv_ho || jo0 >= P.cv_wo)));
+			if (!outside && !skip) {
+				if (lane == 0) bulk_wait_group_read0();             // this warp's previous box has left shared memory
+				__syncwarp();
 #pragma unroll
-			for (int i = 0; i < 32; i += 4)
-				sts128(cst + (uint32_t)lane * 128u + (uint32_t)(((i >> 2) ^ (lane & 7)) << 4), make_float4(acc[g][i], acc[g][i + 1], acc[g][i + 2], acc[g][i + 3]));
-			fence_proxy_async_smem();
-			__syncwarp();
-			if (lane == 0) { tma_store_2d(tmWp, cst, group_col<CG, TS>(h, g), row0); bulk_commit_group(); }
+				for (int i = 0; i < 32; i += 4) {
+					float4 o;
+					o.x = scale * acc[g][i + 0]; o.y = scale * acc[g][i + 1]; o.z = scale * acc[g][i + 2]; o.w = scale * acc[g][i + 3];
+					if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
+					sts128(cst + (uint32_t)lane * 128u + (uint32_t)(((i >> 2) ^ (lane & 7)) << 4), o);
+				}
+				fence_proxy_async_smem();
+				__syncwarp();
+				if (lane == 0) {
+					if (part) tma_store_2d(tmWp, cst, col0, row0);
+					else if (CONV) tma_store_4d(tmCp, cst, jo0, io, row0, inst);     // clipped at the output width and at the filter count
+					else tma_store_3d(tmCp, cst, col0, row0, inst);
+					bulk_commit_group();
+				}
+			}
 			after(g);
 		}
 		return;
 	}
-	if (wi.slot >= 0) {
-		// stream-K part: raw partial sums to the workspace tile of this item (tile-local layout, UMMA_M x BN floats)
+	if (part) {
+		// (SS kernel) stream-K part with plain stores: tile-local layout, UMMA_M x BN floats
 		float *wrow = P.sk_ws + (long long)wi.slot * (UMMA_M * BN) + (long long)((int)cta_rank * ROWS + q * 32 + lane) * BN;
 #pragma unroll
 		for (int g = 0; g < NG; g++)
 #pragma unroll
 			for (int i = 0; i < 32; i += 4)
 				*reinterpret_cast<float4 *>(wrow + group_col<CG, TS>(h, g) + i) = make_float4(acc[g][i], acc[g][i + 1], acc[g][i + 2], acc[g][i + 3]);
-#pragma unroll
-		for (int g = 0; g < NG; g++) after(g);
-		return;
-	}
-	// fused alpha/beta + store; row per thread, ld padding and ragged edges never written
-	const float beta = preload_c ? 0.f : P.beta;   // already folded into acc when preloaded
-	if (P.tma_store && beta == 0.f && !(P.flags & 16)) {
-		// TMA-store epilogue: each warp stages one 32-row x 32-column box at a time in shared memory (128B-swizzled, so a
-		// thread's eight 16-byte stores of its row are conflict-free) and hands it to the TMA unit, which writes whole
-		// 128-byte lines and clips the box at the matrix edge -- instead of 32 row-strided 16-byte stores per instruction.
-		const float slope = P.slope;
-		const bool post = P.bias != nullptr || slope != 1.f;
-		const float bm = (P.bias && row < P.M) ? __ldg(P.bias + row) : 0.f;
-		auto act = [&](float x) { x += bm; return x > 0.f ? x : x * slope; };
-		const uint32_t cst = bar_base + 1024u + (uint32_t)e * CSTAGE_BYTES;
-		const int row0 = tm * UMMA_M + (int)cta_rank * ROWS + q * 32;
-#pragma unroll
-		for (int g = 0; g < NG; g++) {
-			const int col0 = tn * BN + group_col<CG, TS>(h, g);
-			// CONV: the 32 columns are one output-row segment (io, jo0 .. jo0+31) of the padded column index
-			const int io = CONV ? col0 / P.cv_wp : 0, jo0 = CONV ? col0 - io * P.cv_wp : 0;
-			// warp-uniform: the whole box lies outside C
-			if (row0 >= P.M || col0 >= P.N || (CONV && (io >= P.cv_ho || jo0 >= P.cv_wo))) { after(g); continue; }
-			if (lane == 0) bulk_wait_group_read0();             // this warp's previous box has left shared memory
-			__syncwarp();
-#pragma unroll
-			for (int i = 0; i < 32; i += 4) {
-				float4 o;
-				o.x = alpha * acc[g][i + 0]; o.y = alpha * acc[g][i + 1]; o.z = alpha * acc[g][i + 2]; o.w = alpha * acc[g][i + 3];
-				if (post) { o.x = act(o.x); o.y = act(o.y); o.z = act(o.z); o.w = act(o.w); }
-				sts128(cst + (uint32_t)lane * 128u + (uint32_t)(((i >> 2) ^ (lane & 7)) << 4), o);
-			}
-			fence_proxy_async_smem();
-			__syncwarp();
-			if (lane == 0) {
-				if (CONV) tma_store_4d(tmCp, cst, jo0, io, row0, inst);     // clipped at the output width and at the filter count
-				else tma_store_3d(tmCp, cst, col0, row0, inst);
-				bulk_commit_group();
-			}
-			after(g);
-		}
-		return;
-	}
+	} else
 	if (row < P.M && !(P.flags & 16)) {
 		const float slope = P.slope;
 		const bool post = P.bias != nullptr || slope != 1.f;   // bias[row] + LeakyReLU (convolution callers)
