@@ -833,6 +833,12 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 	if (CG == 2) { cluster_arrive(); cluster_wait(); } else __syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot_ptr;
+	// Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touched nothing an earlier kernel of the
+	// stream wrote, so a CTA of this launch may do it while the previous kernel's last tiles are still running on other SMs; from
+	// here on the operands, C, the scheduler counter and the stream-K workspace are read, which needs the predecessor finished.
+	// The next launch in the stream may be scheduled as soon as this one's CTAs leave their SMs.
+	griddep_launch_dependents();
+	griddep_wait();
 
 	if (warp < 4) {
 		reg_dec<48>();
@@ -1238,6 +1244,7 @@ k1_tail_fixup_kernel(const K1Params P)
 {
 	constexpr int TM_ = 128 * CG, TN_ = 128 * CG, Q = TN_ / 4;
 	static_assert(FIXUP_ROWS * Q % 256 == 0 || FIXUP_ROWS * Q <= 256, "one quad per thread");
+	griddep_wait();        // launched with programmatic stream serialization: the parts are complete once the GEMM kernel has finished
 	const int r = blockIdx.x;
 	int tm, tn;
 	const int inst = (P.sk_full + r) / P.tiles_per_batch;
@@ -1503,10 +1510,13 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 	cfg.blockDim = dim3(NUM_THREADS);
 	cfg.dynamicSmemBytes = smem_bytes;
 	cfg.stream = stream;
-	cudaLaunchAttribute attr[1];
+	cudaLaunchAttribute attr[2];
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-	cfg.attrs = attr; cfg.numAttrs = 1;
+	// TS kernel: programmatic dependent launch (the kernel waits with griddepcontrol.wait before it reads anything); flags bit 18 = off
+	attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[1].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = (TS && !(t.flags & 262144)) ? 2 : 1;
 	cudaError_t le = TS   ? (prof ? cudaLaunchKernelEx(&cfg, k1ts_kernel<CG, true, false>, tmA, tmB, tmC, tmW, P) : cudaLaunchKernelEx(&cfg, k1ts_kernel<CG, false, CONV>, tmA, tmB, tmC, tmW, P))
 	               : prof ? cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, true, false>, tmA, tmB, tmC, P)
 	                      : cudaLaunchKernelEx(&cfg, k1_3xtf32_kernel<CG, false, CONV>, tmA, tmB, tmC, P);
@@ -1569,8 +1579,15 @@ cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, con
 	cudaError_t e = launch_kernel<CG, CONV, TS>(tmA, tmB, tmC, tmW, P, items, t, stream, sm_count);
 	if (ws) {
 		if (e == cudaSuccess && !(t.flags & 65536)) {      // (bit 16: ablation, fix-up pass skipped)
-			k1_tail_fixup_kernel<CG><<<dim3((unsigned)P.sk_rem, (unsigned)(tile_m / FIXUP_ROWS)), 256, 0, stream>>>(P);
-			e = cudaGetLastError();
+			cudaLaunchConfig_t fc = {};
+			fc.gridDim = dim3((unsigned)P.sk_rem, (unsigned)(tile_m / FIXUP_ROWS));
+			fc.blockDim = dim3(256);
+			fc.stream = stream;
+			cudaLaunchAttribute fa[1];
+			fa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+			fa[0].val.programmaticStreamSerializationAllowed = 1;
+			fc.attrs = fa; fc.numAttrs = (t.flags & 262144) ? 0 : 1;
+			e = cudaLaunchKernelEx(&fc, k1_tail_fixup_kernel<CG>, P);
 		}
 		cudaFreeAsync(ws, stream);
 	}

@@ -277,6 +277,12 @@ template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setma
 // bring the line holding `p` into L2 (no register, no scoreboard: the later load finds it there)
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// ---- programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start before its
+// predecessor in the stream has finished; nothing the predecessor wrote may be touched before griddep_wait() returns.  The
+// predecessor lets its dependents be scheduled with griddep_launch_dependents() (else: when it has completed).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- 128-bit shared-memory access by 32-bit shared address --------------------------------------------------
 __device__ __forceinline__ float4 lds128(uint32_t a)
 {
