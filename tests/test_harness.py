@@ -3,8 +3,8 @@
 CPU part: the programs build with gcc against include/ugemm_cuda.h, and check_sgemm_cuda's host-only pass (`mode=cpu`, BASELINE
 config 1: the reference's own uut rows on this host, no GPU touched) runs green over the reference's 11 stacked instances.
 GPU part (-m gpu): every harness binary runs on the box -- config 1 with 11 instances, config 3 with a transpose (padded and odd
-leading dimensions), the sgemm_test.c macro harness, the DGEMM harness and the single-process sharded harness -- exit status 0 and
-no failed gate line."""
+leading dimensions), the sgemm_test.c macro harness, the DGEMM harness, the single-process sharded harness and the one-process-per-GPU
+sharded harness -- exit status 0 and no failed gate line."""
 import os
 import subprocess
 
@@ -12,7 +12,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HARNESS = os.path.join(ROOT, "harness")
-BINARIES = ("check_sgemm_cuda", "sgemm_test_cuda", "check_dgemm_cuda", "sgemm_mgpu_cuda")
+BINARIES = ("check_sgemm_cuda", "sgemm_test_cuda", "check_dgemm_cuda", "sgemm_mgpu_cuda", "sgemm_shard_cuda")
 
 
 @pytest.fixture(scope="module")
@@ -106,3 +106,13 @@ def test_sgemm_mgpu_cuda(harness):
     res = run(harness, "sgemm_mgpu_cuda", 0, 8192, 8192, 8192, 1)
     green(res)
     assert "sampled relerr" in res.stdout and " ok" in res.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport", [1, 0])
+def test_sgemm_shard_cuda(harness, transport):
+    """Config 5's C host program with one process per GPU (fork, NCCL id through a shared page, sgemm_cuda_shard_*) on every GPU
+    of the box, both transports, at a size that keeps the test short."""
+    res = run(harness, "sgemm_shard_cuda", 0, 8192, 8192, 8192, 2, transport)
+    green(res)
+    assert "sampled relerr" in res.stdout and " ok" in res.stdout and "FAIL" not in res.stdout
