@@ -52,6 +52,7 @@ struct ConvProblem {
 // bits 7-10: L2 eviction hints of the TMA loads (experiments); bit 11 (2048): stream-K tail off (A/B runs, SM-limited launches).
 // bit 13 (8192): TMA-store epilogue off (row-strided 128-bit global stores instead; A/B runs).
 // bit 15 (32768): round-1 SS kernel (A and B from shared memory) instead of the TS kernel (A in tensor memory); A/B runs.
+// bit 19 (524288): serpentine K off (every tile walks its k-blocks upwards; A/B runs of the DRAM traffic).
 // bit 18 (262144): programmatic dependent launch off (A/B runs).
 // bit 17 (131072): stream-K tail whenever the model predicts any saving (A/B runs of the rule).
 // bit 16 (65536): ABLATION, stream-K fix-up pass skipped (results wrong).

@@ -78,6 +78,8 @@ struct K1Params {
 	// implicit-GEMM convolution (CONV instantiation): padded output width (multiple of 32), output width / height,
 	// kernel size, padding, 32-channel blocks per kernel position, pixels per output plane
 	int cv_wp, cv_wo, cv_ho, cv_k, cv_pad, cv_cblocks, cv_npix, cv_stride;
+	int group;                  // m-tiles that share an n sweep in the tile order (decode_tile)
+	int serpentine;             // TS kernel: every other wave of tiles walks K downwards (see the producer)
 	unsigned *diag;
 	// dynamic scheduler: *sched is a device counter that only ever grows; a launch claims the values [sched_base, sched_base +
 	// num_tiles + clusters) (every cluster makes exactly one claim past the end), so the host knows the base of the next launch
@@ -112,9 +114,8 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
 }
 
 // grouped tile order: 8 consecutive m-tiles share an n sweep so a wave's A and B panels stay in L2
-__device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int &tm, int &tn)
+__device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int &tm, int &tn, int GROUP = 8)
 {
-	constexpr int GROUP = 8;
 	const int per_group = GROUP * tiles_n;
 	const int group = tile / per_group;
 	const int first_m = group * GROUP;
@@ -853,7 +854,7 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 				if (wi.kb1 <= wi.kb0) continue;
 				int tm, tn;
 				const int inst = wi.tile / P.tiles_per_batch;
-				decode_tile(wi.tile - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
+				decode_tile(wi.tile - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn, P.group);
 				const int a_row0 = tm * UMMA_M + (int)cta_rank * ROWS;
 				const int b_col0 = tn * BN + (CG == 2 ? 32 * (int)cta_rank : 0);    // group g: + 64 g (pair) / + 32 g (single CTA)
 				int cio[ROWS / 32], cjo[ROWS / 32];     // CONV: output row / first output column of each 32-column group
@@ -865,7 +866,16 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 						cjo[g] = n0 - cio[g] * P.cv_wp;
 					}
 				}
-				for (int kb = wi.kb0; kb < wi.kb1; kb++) {
+				// Serpentine K: every other wave of tiles walks its k-blocks downwards.  All pairs of a wave sweep K together, so a wave
+				// ends with the high-k blocks of its panels freshest in L2; the next wave shares one operand's panels with it (8 m-tiles
+				// share an n sweep) and, walking down, meets them while they are still there (an upward walk finds its first blocks evicted
+				// by its own predecessor: the wave's working set is larger than the L2).  Only the load coordinates change -- the other
+				// roles count k-blocks -- and the order of a tile's k-blocks is a fixed function of the tile index and the grid size.
+				// (Only where panels are re-read from DRAM: a problem that fits the L2, or one whose big operand is streamed once like
+				// config 4's, loses with a downward walk -- the L2's 256-byte promotion then fetches the half line already consumed.)
+				const bool down = P.serpentine && ((wi.tile / num_clusters) & 1);
+				for (int kbi = wi.kb0; kbi < wi.kb1; kbi++) {
+					const int kb = down ? wi.kb1 - 1 - (kbi - wi.kb0) : kbi;
 					const long long tw = tick<PROF>();
 					mbar_wait(bar(B_EMPTY + s), ph ^ 1u, P.diag, 1);
 					w_empty += tick<PROF>() - tw;
@@ -1173,7 +1183,7 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 				if (sg.wi.kb1 > sg.wi.kb0) break;
 			}
 			sg.inst = sg.wi.tile / P.tiles_per_batch;
-			decode_tile(sg.wi.tile - sg.inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, sg.tm, sg.tn);
+			decode_tile(sg.wi.tile - sg.inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, sg.tm, sg.tn, P.group);
 			return true;
 		};
 		auto row_of = [&](const Seg &sg) { return (long long)sg.tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane; };
@@ -1248,7 +1258,7 @@ k1_tail_fixup_kernel(const K1Params P)
 	const int r = blockIdx.x;
 	int tm, tn;
 	const int inst = (P.sk_full + r) / P.tiles_per_batch;
-	decode_tile(P.sk_full + r - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn);
+	decode_tile(P.sk_full + r - inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm, tn, P.group);
 	const bool conv = P.cv_wp > 0;
 	const int r_lo = (r * P.sk_nch) / P.sk_q, r_hi = ((r + 1) * P.sk_nch - 1) / P.sk_q;   // chunk ranges that hold a part of this tile
 	const float alpha = P.alpha, beta = P.beta, slope = P.slope;
@@ -1457,6 +1467,10 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 	P.kc_blocks = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
 	P.split = t.split;
 	P.flags = t.flags;
+	P.group = TS && ((t.flags >> 24) & 31) ? ((t.flags >> 24) & 31) : 8;       // (bits 24-28 of the flags: tile-order experiments)
+	// serpentine K where waves re-read panels from DRAM: operands well beyond the L2 and at least four tiles either way
+	P.serpentine = TS && !CONV && !(t.flags & 524288) && P.tiles_m >= 4 && P.tiles_n >= 4 &&
+	               4.0 * ((double)P.M * P.K + (double)P.K * P.N) > 96e6;
 	P.diag = diag_dev();
 	// Device-resident launch state is kept PER DEVICE (the single-process multi-GPU driver, sgemm_cuda_mgpu, launches this
 	// kernel on every GPU of the box from one host thread): scheduler counters, profiling buffer, function attributes.
@@ -1558,7 +1572,10 @@ cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, con
 		// TS kernel [measured, profiles/r2n_sk_sweep.jsonl, r2o_sk_ablate.txt]: once at least one full round precedes the tail, the part
 		// stores, the fix-up pass and the tail's colder start cost about as much as 30 k-blocks of a pair; below that the tail is a loss
 		// (4096 x 3072 x 2048: 24 k-blocks saved, 219 vs 209 us), above it a gain (2560^3: 48 saved, 155 vs 175 us; 4096^3: 68, 494 vs 522)
-		const bool worth = TS ? (full == 0 ? saved_rounds >= 0.15 : (nch - q) * (long long)kc_eff >= 32)
+		// ... and at least 2 % of a pair's whole work: at 8192^3 the tail saves 40 of 3543 k-blocks per pair, costs 0.36 GB of extra DRAM
+		// traffic (parts, colder tail) and measures as nothing (3.66 vs 3.64 ms, profiles/r3a_traffic.csv)
+		const long long saved_kb = (nch - q) * (long long)kc_eff, pair_kb = (nt * (long long)P.num_k_blocks + pairs - 1) / pairs;
+		const bool worth = TS ? (full == 0 ? saved_rounds >= 0.15 : (saved_kb >= 32 && saved_kb * 50 >= pair_kb))
 		                      : (saved_rounds >= 0.15 && saved_rounds / rounds >= 0.12);
 		if ((worth || ((t.flags & 131072) && saved_rounds > 0.0)) && rem * nch < 0x3fffffffLL) {      // (bit 17: tail whenever it saves anything, A/B runs)
 			const size_t tile_bytes = (size_t)tile_m * tile_n * sizeof(float);
