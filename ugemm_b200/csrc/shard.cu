@@ -129,12 +129,12 @@ struct Shard {
 	int device = 0, sm_count = 148, transport = 0;       // transport actually in use: 0 NCCL broadcast, 1 copy-engine peer pull
 	ncclComm_t comm = nullptr, row = nullptr, col = nullptr;
 	cudaStream_t comp = nullptr, xfer = nullptr, up = nullptr, down = nullptr;
-	float *own = nullptr, *recv = nullptr, *c = nullptr, *scratch = nullptr;
+	float *own = nullptr, *recv = nullptr, *c = nullptr, *c_alt = nullptr, *scratch = nullptr;   // c_alt: second C block of the end-to-end path
 	long long own_floats = 0;
 	float *a[MAX_SLABS] = {nullptr}, *b[MAX_SLABS] = {nullptr};
 	const float *a_src[MAX_SLABS] = {nullptr}, *b_src[MAX_SLABS] = {nullptr};   // P2P: where a non-owned slab is pulled from
 	cudaEvent_t landed[MAX_SLABS] = {nullptr}, used[MAX_SLABS] = {nullptr}, uploaded[MAX_SLABS] = {nullptr};
-	cudaEvent_t e0 = nullptr, e1 = nullptr, e_panel[8] = {nullptr};
+	cudaEvent_t e0 = nullptr, e1 = nullptr, e_panel[8] = {nullptr}, c_down[2] = {nullptr, nullptr};
 	std::vector<void *> mapped;
 	float *h_own = nullptr, *h_c = nullptr;              // pinned host mirrors for the end-to-end path
 } S;
@@ -174,6 +174,7 @@ void release_all()
 	if (S.own) cudaFree(S.own);
 	if (S.recv) cudaFree(S.recv);
 	if (S.c) cudaFree(S.c);
+	if (S.c_alt) cudaFree(S.c_alt);
 	if (S.scratch) cudaFree(S.scratch);
 	if (S.h_own) cudaFreeHost(S.h_own);
 	if (S.h_c) cudaFreeHost(S.h_c);
@@ -184,6 +185,7 @@ void release_all()
 	}
 	for (cudaEvent_t e : {S.e0, S.e1}) if (e) cudaEventDestroy(e);
 	for (cudaEvent_t e : S.e_panel) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : S.c_down) if (e) cudaEventDestroy(e);
 	for (cudaStream_t st : {S.comp, S.xfer, S.up, S.down}) if (st) cudaStreamDestroy(st);
 	if (nccl.h) {
 		if (S.row) nccl.CommDestroy(S.row);
@@ -268,6 +270,7 @@ int sgemm_cuda_shard_init(int rank, int world, const unsigned char *id128, int M
 	SH_CUDA(cudaEventCreate(&S.e0), "cudaEventCreate");
 	SH_CUDA(cudaEventCreate(&S.e1), "cudaEventCreate");
 	for (cudaEvent_t &e : S.e_panel) SH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+	for (cudaEvent_t &e : S.c_down) SH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
 
 	// owned slabs in ONE allocation (exportable), received slabs in another, the C block, a scratch word for barriers
 	const long long an = (long long)p.mloc * p.kw, bn = (long long)p.kw * p.nloc;
@@ -413,6 +416,7 @@ int sgemm_cuda_shard_host_buffers(float **h_own, long long *own_floats, float **
 	if (!S.ready) { fail("sgemm_cuda_shard_host_buffers: not initialised"); return 1; }
 	if (!S.h_own) SH_CUDA(cudaMallocHost(&S.h_own, (size_t)(S.own_floats > 0 ? S.own_floats : 1) * 4), "cudaMallocHost (owned slabs)");
 	if (!S.h_c) SH_CUDA(cudaMallocHost(&S.h_c, (size_t)S.p.mloc * S.p.nloc * 4), "cudaMallocHost (C block)");
+	if (!S.c_alt) SH_CUDA(cudaMalloc(&S.c_alt, (size_t)S.p.mloc * S.p.nloc * 4), "cudaMalloc (second C block)");
 	if (h_own) *h_own = S.h_own;
 	if (own_floats) *own_floats = S.own_floats;
 	if (h_c) *h_c = S.h_c;
@@ -443,6 +447,10 @@ int sgemm_cuda_shard_run_host(int steps, int warmup, float *ms_total, long long 
 			if (barrier_on(S.xfer) || barrier_on(S.comp)) return 1;
 			clock_gettime(CLOCK_MONOTONIC, &t0);
 		}
+		// two C blocks take turns: the way down of a finished C (as long on the host link as half the uploads) overlaps the next
+		// step's products instead of holding them up; a block is written again only when its previous content has gone down
+		float *cbuf = (it & 1) ? S.c_alt : S.c;
+		if (it >= 2) SH_CUDA(cudaStreamWaitEvent(S.comp, S.c_down[it & 1], 0), "cudaStreamWaitEvent");
 		if (p.world > 1) sgemm_cuda_set_sm_limit(S.sm_count - COMM_SMS);
 		for (int t = 0; t < p.L && !rc; t++) {
 			// upload what this rank owns of slab t (the buffer may still be read by the previous step's product)
@@ -465,31 +473,27 @@ int sgemm_cuda_shard_run_host(int steps, int warmup, float *ms_total, long long 
 			SH_CUDA(cudaStreamWaitEvent(S.comp, S.landed[t], 0), "cudaStreamWaitEvent");
 			if (t == p.L - 1) sgemm_cuda_set_sm_limit(0);
 			if (t < p.L - 1 || panels == 1) {
-				rc = sgemm_cuda_dev(UGEMM_MODE_AUTO, S.comp, 'R', 'N', 'N', p.mloc, p.nloc, p.kw, 1.f, S.a[t], p.kw, S.b[t], p.nloc, t == 0 ? 0.f : 1.f, S.c, p.nloc);
+				rc = sgemm_cuda_dev(UGEMM_MODE_AUTO, S.comp, 'R', 'N', 'N', p.mloc, p.nloc, p.kw, 1.f, S.a[t], p.kw, S.b[t], p.nloc, t == 0 ? 0.f : 1.f, cbuf, p.nloc);
 				if (!rc && t == p.L - 1) {
 					SH_CUDA(cudaEventRecord(S.e_panel[0], S.comp), "cudaEventRecord");
 					SH_CUDA(cudaStreamWaitEvent(S.down, S.e_panel[0], 0), "cudaStreamWaitEvent");
-					SH_CUDA(cudaMemcpyAsync(S.h_c, S.c, (size_t)p.mloc * p.nloc * 4, cudaMemcpyDeviceToHost, S.down), "D2H (C block)");
+					SH_CUDA(cudaMemcpyAsync(S.h_c, cbuf, (size_t)p.mloc * p.nloc * 4, cudaMemcpyDeviceToHost, S.down), "D2H (C block)");
 				}
 			} else {
 				for (int q = 0; q < panels && !rc; q++) {
 					const size_t r0 = (size_t)q * prow;
 					rc = sgemm_cuda_dev(UGEMM_MODE_AUTO, S.comp, 'R', 'N', 'N', prow, p.nloc, p.kw, 1.f, S.a[t] + r0 * p.kw, p.kw, S.b[t], p.nloc, t == 0 ? 0.f : 1.f,
-					                    S.c + r0 * p.nloc, p.nloc);
+					                    cbuf + r0 * p.nloc, p.nloc);
 					if (rc) break;
 					SH_CUDA(cudaEventRecord(S.e_panel[q], S.comp), "cudaEventRecord");
 					SH_CUDA(cudaStreamWaitEvent(S.down, S.e_panel[q], 0), "cudaStreamWaitEvent");
-					SH_CUDA(cudaMemcpyAsync(S.h_c + r0 * p.nloc, S.c + r0 * p.nloc, (size_t)prow * p.nloc * 4, cudaMemcpyDeviceToHost, S.down), "D2H (C panel)");
+					SH_CUDA(cudaMemcpyAsync(S.h_c + r0 * p.nloc, cbuf + r0 * p.nloc, (size_t)prow * p.nloc * 4, cudaMemcpyDeviceToHost, S.down), "D2H (C panel)");
 				}
 			}
 			if (!rc) SH_CUDA(cudaEventRecord(S.used[t], S.comp), "cudaEventRecord");
 		}
 		sgemm_cuda_set_sm_limit(0);
-		// the next step's first product overwrites C: it must not start before this step's C has gone down
-		if (!rc) {
-			SH_CUDA(cudaEventRecord(S.e1, S.down), "cudaEventRecord");
-			SH_CUDA(cudaStreamWaitEvent(S.comp, S.e1, 0), "cudaStreamWaitEvent");
-		}
+		if (!rc) SH_CUDA(cudaEventRecord(S.c_down[it & 1], S.down), "cudaEventRecord");
 	}
 	if (rc) return 1;
 	SH_CUDA(cudaStreamSynchronize(S.down), "cudaStreamSynchronize");
