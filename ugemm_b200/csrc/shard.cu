@@ -122,7 +122,11 @@ long long own_offset(const Plan &p, int r, bool is_b, int t, long long *total)
 	return found;
 }
 
-constexpr int MAX_SLABS = 64, COMM_SMS = 8;
+// NCCL transport: SMs left to NCCL's CTAs, and for how many slab products.  All broadcasts of a step are issued up front and are short
+// next to the products (32768^3 on 8 GPUs: 2.1 GB per rank and step over NVLink, a few ms, against 4.6 ms per slab product), and the
+// product of slab t only starts once broadcast t has landed -- so by the third product they have normally all finished and the
+// products can have every SM again; a broadcast that is late then waits for one product at worst.
+constexpr int MAX_SLABS = 64, COMM_SMS = 8, COMM_SLABS = 2;
 struct Shard {
 	bool ready = false;
 	Plan p{};
@@ -382,7 +386,7 @@ int sgemm_cuda_shard_run(int distribute, int steps, int warmup, float *ms_total)
 		}
 		for (int t = 0; t < p.L && !rc; t++) {
 			if (dist) SH_CUDA(cudaStreamWaitEvent(S.comp, S.landed[t], 0), "cudaStreamWaitEvent");
-			if (dist && S.transport == 0 && t == p.L - 1) sgemm_cuda_set_sm_limit(0);     // nothing left in flight behind the last slab
+			if (dist && S.transport == 0 && (t == p.L - 1 || t == COMM_SLABS)) sgemm_cuda_set_sm_limit(0);
 			rc = sgemm_cuda_dev(UGEMM_MODE_AUTO, S.comp, 'R', 'N', 'N', p.mloc, p.nloc, p.kw, 1.f, S.a[t], p.kw, S.b[t], p.nloc, t == 0 ? 0.f : 1.f, S.c, p.nloc);
 			if (!rc) SH_CUDA(cudaEventRecord(S.used[t], S.comp), "cudaEventRecord");
 		}
