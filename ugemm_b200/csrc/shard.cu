@@ -122,11 +122,13 @@ long long own_offset(const Plan &p, int r, bool is_b, int t, long long *total)
 	return found;
 }
 
-// NCCL transport: SMs left to NCCL's CTAs, and for how many slab products.  All broadcasts of a step are issued up front and are short
-// next to the products (32768^3 on 8 GPUs: 2.1 GB per rank and step over NVLink, a few ms, against 4.6 ms per slab product), and the
-// product of slab t only starts once broadcast t has landed -- so by the third product they have normally all finished and the
-// products can have every SM again; a broadcast that is late then waits for one product at worst.
-constexpr int MAX_SLABS = 64, COMM_SMS = 8, COMM_SLABS = 2;
+// NCCL transport: SMs left to NCCL's CTAs while broadcasts may be in flight (a persistent K1 CTA fills an SM, and an NCCL kernel that
+// finds no free SM waits for the whole product in front of it).  Every product but the last of a step runs on the reduced grid: the
+// broadcasts of the NEXT step are issued right behind this step's products and need their SMs during this step's later slabs.
+// [measured, 8 GPUs, NCCL_MAX_CTAS=4] reserving only for the first two products of a step -- with or without the host waiting for
+// the step's last broadcast before it launches the rest -- serialises the next step's broadcasts behind full-grid products:
+// 42 -> 82 ms per step (4 GPUs: 77 -> 108 ms).
+constexpr int MAX_SLABS = 64, COMM_SMS = 8;
 struct Shard {
 	bool ready = false;
 	Plan p{};
@@ -386,7 +388,7 @@ int sgemm_cuda_shard_run(int distribute, int steps, int warmup, float *ms_total)
 		}
 		for (int t = 0; t < p.L && !rc; t++) {
 			if (dist) SH_CUDA(cudaStreamWaitEvent(S.comp, S.landed[t], 0), "cudaStreamWaitEvent");
-			if (dist && S.transport == 0 && (t == p.L - 1 || t == COMM_SLABS)) sgemm_cuda_set_sm_limit(0);
+			if (dist && S.transport == 0 && t == p.L - 1) sgemm_cuda_set_sm_limit(0);     // nothing of this step left in flight behind the last slab
 			rc = sgemm_cuda_dev(UGEMM_MODE_AUTO, S.comp, 'R', 'N', 'N', p.mloc, p.nloc, p.kw, 1.f, S.a[t], p.kw, S.b[t], p.nloc, t == 0 ? 0.f : 1.f, S.c, p.nloc);
 			if (!rc) SH_CUDA(cudaEventRecord(S.used[t], S.comp), "cudaEventRecord");
 		}
