@@ -18,6 +18,8 @@
 // (backend.cu).  The host program brings RENDEZVOUS ONLY: rank 0 obtains a 128-byte id (sgemm_cuda_shard_unique_id) and hands it
 // to every rank by whatever it has (torch.distributed in bench.py, MPI, a file).  NCCL is loaded with dlopen, so the library
 // keeps no link-time dependency on it and single-GPU users never touch it.
+// One sharded problem per process at a time, driven from one host thread at a time (the state below is a single object, like the
+// backend's); every rank must make the same calls in the same order, as with any collective library.
 #include "common.cuh"
 #include "../../include/ugemm_cuda.h"
 #include <nccl.h>
@@ -245,9 +247,18 @@ int sgemm_cuda_shard_unique_id(unsigned char *id128)
 
 void sgemm_cuda_shard_finish(void) { release_all(); }
 
+static int shard_init_body(int rank, int world, const unsigned char *id128, int M, int N, int K, int transport);
+
 int sgemm_cuda_shard_init(int rank, int world, const unsigned char *id128, int M, int N, int K, int transport)
 {
 	if (S.ready) { fail("sgemm_cuda_shard_init: already initialised (call sgemm_cuda_shard_finish first)"); return 1; }
+	const int rc = shard_init_body(rank, world, id128, M, N, K, transport);
+	if (rc) release_all();          // nothing half-built stays behind: communicators, streams, events and allocations made so far are returned
+	return rc;
+}
+
+static int shard_init_body(int rank, int world, const unsigned char *id128, int M, int N, int K, int transport)
+{
 	Plan p;
 	if (make_plan(world, rank, M, N, K, &p)) return 1;
 	if (p.L > MAX_SLABS) { fail("sgemm_cuda_shard_init: %d slabs (max %d)", p.L, MAX_SLABS); return 1; }
@@ -357,6 +368,7 @@ int sgemm_cuda_shard_block(float **d_c, int *rows, int *cols, int *row0, int *co
 int sgemm_cuda_shard_generate(unsigned long long seed_a, unsigned long long seed_b, float lo, float hi)
 {
 	if (!S.ready) { fail("sgemm_cuda_shard_generate: not initialised"); return 1; }
+	SH_CUDA(cudaSetDevice(S.device), "cudaSetDevice");      // the calling thread may be a different one than at init
 	const Plan &p = S.p;
 	for (int t = 0; t < p.L; t++) {
 		if (a_owner(p, p.i, t) == p.rank &&
@@ -372,6 +384,7 @@ int sgemm_cuda_shard_generate(unsigned long long seed_a, unsigned long long seed
 int sgemm_cuda_shard_run(int distribute, int steps, int warmup, float *ms_total)
 {
 	if (!S.ready) { fail("sgemm_cuda_shard_run: not initialised"); return 1; }
+	SH_CUDA(cudaSetDevice(S.device), "cudaSetDevice");      // the calling thread may be a different one than at init
 	const Plan &p = S.p;
 	const bool dist = distribute && p.world > 1;
 	int rc = 0;
@@ -407,6 +420,7 @@ int sgemm_cuda_shard_run(int distribute, int steps, int warmup, float *ms_total)
 int sgemm_cuda_shard_allreduce(float *value, int op)
 {
 	if (!S.ready || !value) { fail("sgemm_cuda_shard_allreduce: not initialised"); return 1; }
+	SH_CUDA(cudaSetDevice(S.device), "cudaSetDevice");      // the calling thread may be a different one than at init
 	if (S.p.world == 1) return 0;
 	SH_CUDA(cudaMemcpyAsync(S.scratch + 1, value, 4, cudaMemcpyHostToDevice, S.comp), "cudaMemcpyAsync");
 	SH_NCCL(nccl.AllReduce(S.scratch + 1, S.scratch + 1, 1, ncclFloat, op == 0 ? ncclMax : ncclSum, S.comm, S.comp), "ncclAllReduce");
@@ -420,6 +434,7 @@ int sgemm_cuda_shard_allreduce(float *value, int op)
 int sgemm_cuda_shard_host_buffers(float **h_own, long long *own_floats, float **h_c, long long *c_floats)
 {
 	if (!S.ready) { fail("sgemm_cuda_shard_host_buffers: not initialised"); return 1; }
+	SH_CUDA(cudaSetDevice(S.device), "cudaSetDevice");      // the calling thread may be a different one than at init
 	if (!S.h_own) SH_CUDA(cudaMallocHost(&S.h_own, (size_t)(S.own_floats > 0 ? S.own_floats : 1) * 4), "cudaMallocHost (owned slabs)");
 	if (!S.h_c) SH_CUDA(cudaMallocHost(&S.h_c, (size_t)S.p.mloc * S.p.nloc * 4), "cudaMallocHost (C block)");
 	if (!S.c_alt) SH_CUDA(cudaMalloc(&S.c_alt, (size_t)S.p.mloc * S.p.nloc * 4), "cudaMalloc (second C block)");
