@@ -93,7 +93,7 @@ int  sgemm_cuda_batched_dev(int mode, void *stream, char major, char transA, cha
 
 /* 1 if UGEMM_MODE_AUTO would pick K1 DIRECTLY for this problem: A, B 16-byte aligned, lda and ldb multiples
  * of 4 (TMA global-stride rule), K >= 32, and M,N >= 128 (at least one full tile of tensor work) -- or one of M, N >= 128,
- * the other >= 48 and M*N*K >= 2^26 (a skinny but large product: K1's padded tile still beats the FFMA kernel).
+ * the other >= 48 (>= 8 when K >= 512) and M*N*K >= 2^26 (a skinny but large product: K1's padded tile still beats the FFMA kernel).
  * The complete auto rule: (1) that -> K1; (2) else, if M,N >= 256 and K >= 64, the operand(s) TMA cannot take are
  * first copied to a stream-ordered scratch buffer with an aligned leading dimension (one HBM pass, reported by
  * sgemm_cuda_last_repacked) and K1 runs on the copy; (3) else K2.  Forced modes never repack. */

@@ -562,9 +562,14 @@ def test_k2_narrow_n_tiles(u, ta, tb):
             pad = (0, 0, 0) if i % 2 == 0 else (3, 1, 5)
             mm, nn = (M, N) if maj == "R" else (N, M)   # column-major swaps the roles, so keep the skinny side on N after the swap
             check_case(u, "simt", maj, ta, tb, mm, nn, K, 1.5, 0.5, pad, seed=60 + i, naive=True)
-    # the memory-bound corner at size: 200704 x 16 x 1152 through auto (N < 128 -> K2)
-    e = sampled_rows_check(u, "auto", 200704, 16, 1152, [(0, 32), (200672, 32)], 0.0, 1.0)
+    # the memory-bound corner at size: 200704 x 16 x 1152 on K2's narrow tiles (forced: since round 2 the auto rule sends this
+    # shape to K1, which skips the accumulator slices without columns and is faster from a narrow side of 8 when K >= 512) ...
+    e = sampled_rows_check(u, "simt", 200704, 16, 1152, [(0, 32), (200672, 32)], 0.0, 1.0)
     assert u.last_kernel() == "simt"
+    assert e <= TOL
+    # ... and through auto, on K1
+    e = sampled_rows_check(u, "auto", 200704, 16, 1152, [(0, 32), (200672, 32)], 0.0, 1.0)
+    assert u.last_kernel() == "3xtf32"
     assert e <= TOL
 
 
@@ -608,8 +613,9 @@ def test_k1_stream_k_tail_is_deterministic_and_exact_enough(u):
 
 
 def test_auto_dispatch_skinny_but_large_goes_to_k1(u):
-    """One side >= 128, the other >= 48, M*N*K >= 2^26: K1 on a zero-filled tile beats K2 (dispatch rule)."""
-    for (M, N, K, want) in ((4096, 64, 512, "3xtf32"), (64, 4096, 512, "3xtf32"), (8192, 48, 256, "3xtf32"), (4096, 32, 512, "simt"),
+    """One side >= 128, the other >= 48 (>= 8 with K >= 512), M*N*K >= 2^26: K1 on a zero-filled tile beats K2 (dispatch rule)."""
+    for (M, N, K, want) in ((4096, 64, 512, "3xtf32"), (64, 4096, 512, "3xtf32"), (8192, 48, 256, "3xtf32"), (4096, 32, 512, "3xtf32"),
+                            (16384, 8, 1024, "3xtf32"), (8, 16384, 1024, "3xtf32"), (8192, 32, 256, "simt"), (16384, 4, 2048, "simt"),
                             (4096, 64, 128, "simt"), (100, 100, 8192, "simt")):
         for ta, tb in (("N", "N"), ("T", "T")):
             (ar, ac), (br, bc), _ = O.stored_shapes("R", ta, tb, M, N, K)

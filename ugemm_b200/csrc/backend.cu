@@ -116,14 +116,20 @@ int normalise(char major, char ta, char tb, int M, int N, int K, float alpha, co
 	return 0;
 }
 
-// At least one full 128-wide tile side of tensor work; the other side may be as narrow as 48 once the problem is big enough to
-// amortise K1's launch (its zero-filled tile columns cost nothing extra: a 200704 x 64 x 1152 product takes 0.50 ms on K1,
+// At least one full 128-wide tile side of tensor work; the other side may be as narrow as 48 (8 with K >= 512) once the problem is big
+// enough to amortise K1's launch (its zero-filled tile columns cost nothing extra: a 200704 x 64 x 1152 product takes 0.50 ms on K1,
 // 0.66 ms on K2; 200704 x 96: 0.50 vs 1.47 ms; at N = 32 K2's narrow tiles win, 0.40 vs 0.49 ms -- profiles/r1_skinny_k1_vs_k2.jsonl).
 bool auto_prefers_k1(const Problem &p)
 {
 	if (!k1_eligible(p, nullptr) || p.K < 32) return false;
 	if (p.M >= 128 && p.N >= 128) return true;
-	return p.M >= 48 && p.N >= 48 && (p.M >= 128 || p.N >= 128) && (double)p.M * p.N * p.K >= 67108864.0;
+	if (!(p.M >= 128 || p.N >= 128) || (double)p.M * p.N * p.K < 67108864.0) return false;
+	// round 2: the TS kernel neither multiplies nor promotes accumulator slices that hold no column of C, so from a narrow side of 8 it
+	// beats K2's narrow tiles once K is long (>= 512): 200704 x 32 x 1152 0.24 vs 0.39 ms, 8192 x 16 x 4096 56 vs 232 us,
+	// 4096 x 32 x 512 22 vs 40 us; with a short K the FFMA kernel keeps the very narrow shapes (100000 x 12 x 300: 74 vs 58 us)
+	// -- tools/gpu_skinny3.py, profiles/r3i_skinny.json
+	const int narrow = p.M < p.N ? p.M : p.N;
+	return narrow >= 48 || (narrow >= 8 && p.K >= 512);
 }
 
 bool tma_ok(const float *ptr, long long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 4 == 0; }

@@ -926,6 +926,16 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 					const Item wi = decode_item(item, sg, P.sk_full, P.sk_rem, P.sk_nch, P.sk_q, kc, nkb);
 					if (wi.kb1 <= wi.kb0) continue;
 					const int nseg = wi.kb1 - wi.kb0;
+					// slices that hold columns of C at all: the others (a ragged last n-tile, N <= 64 on a 128-wide tile ...) are neither
+					// multiplied nor handed over -- their B rows are TMA zero fill and their columns are never stored
+					int nact;
+					{
+						int tm_, tn_;
+						const int inst_ = wi.tile / P.tiles_per_batch;
+						decode_tile(wi.tile - inst_ * P.tiles_per_batch, P.tiles_m, P.tiles_n, tm_, tn_, P.group);
+						nact = (P.N - tn_ * BN + SLICE - 1) / SLICE;
+						nact = nact < 1 ? 1 : nact > NSL ? NSL : nact;
+					}
 					int buf[NSL];                      // ring buffer of each slice
 					uint32_t fresh = (1u << NSL) - 1u; // slices whose next MMA starts a new chunk (overwrites its buffer)
 					auto take_buffer = [&]() {
@@ -953,6 +963,7 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 						const uint32_t a_raw = tmem_base + A_COL0 + (uint32_t)a * 64u, a_small = a_raw + 32u;
 #pragma unroll
 						for (int j = 0; j < NSL; j++) {
+							if (j >= nact) continue;
 							if (t == 0) { buf[j] = take_buffer(); tc_fence_after(); }
 							const uint32_t d_tmem = tmem_base + (uint32_t)buf[j] * SLICE;
 #pragma unroll
@@ -973,7 +984,8 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 							// end of the tile (or stream-K part): every slice hands over, oldest buffer first
 #pragma unroll
 							for (int n = 0; n < NSL; n++) {
-								const int j = (jo + n) % NSL;
+								if (n >= nact) continue;
+								const int j = jo + n < nact ? jo + n : jo + n - nact;
 								int b = buf[0];
 #pragma unroll
 								for (int jj = 1; jj < NSL; jj++) b = (jj == j) ? buf[jj] : b;
@@ -990,7 +1002,7 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
 							for (int jj = 0; jj < NSL; jj++) buf[jj] = (jj == jo) ? nb : buf[jj];
 							fresh |= 1u << jo;
-							jo = (jo + 1 == NSL) ? 0 : jo + 1;
+							jo = (jo + 1 == nact) ? 0 : jo + 1;
 							next_evt += step;
 						}
 					}
@@ -1169,8 +1181,8 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 			if (++db == NBUF) { db = 0; dph ^= 1u; }
 		};
 		// The work items of this CTA as a stream of segments (a whole tile, or one part of a stream-K range).  Hand-over number ev of
-		// a segment always belongs to slice ev % NSL (natural hand-overs go round the slices, the final ones continue the round).
-		struct Seg { Item wi; int tm, tn, inst; };          // (kept small: two of them live beside 128 accumulator registers)
+		// a segment always belongs to slice ev % nact (natural hand-overs go round the active slices, the final ones continue the round).
+		struct Seg { Item wi; int tm, tn, inst, nact; };    // (kept small: two of them live beside 128 accumulator registers); nact: see the MMA thread
 		int nt = 0, item = -1, sgn = 2;
 		auto fetch = [&](Seg &sg) -> bool {
 			for (;;) {
@@ -1184,12 +1196,14 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 			}
 			sg.inst = sg.wi.tile / P.tiles_per_batch;
 			decode_tile(sg.wi.tile - sg.inst * P.tiles_per_batch, P.tiles_m, P.tiles_n, sg.tm, sg.tn, P.group);
+			sg.nact = (P.N - sg.tn * BN + SLICE - 1) / SLICE;
+			sg.nact = sg.nact < 1 ? 1 : sg.nact > NSL ? NSL : sg.nact;
 			return true;
 		};
 		auto row_of = [&](const Seg &sg) { return (long long)sg.tm * UMMA_M + (long long)cta_rank * ROWS + q * 32 + lane; };
 		auto crow_of = [&](const Seg &sg) { return P.C + (long long)sg.inst * P.strideC + row_of(sg) * (CONV ? (long long)P.cv_npix : P.ldc); };
-		// hand-overs of a segment: after k-blocks kc-1, kc-1+step, ... (not the last one), and NSL at the end
-		auto nev_of = [&](const Seg &sg) { const int nseg = sg.wi.kb1 - sg.wi.kb0; return (nseg - 1 >= kc ? (nseg - 1 - kc) / step + 1 : 0) + NSL; };
+		// hand-overs of a segment: after k-blocks kc-1, kc-1+step, ... (not the last one), and one per active slice at the end
+		auto nev_of = [&](const Seg &sg) { const int nseg = sg.wi.kb1 - sg.wi.kb0; return (nseg - 1 >= kc ? (nseg - 1 - kc) / step + 1 : 0) + sg.nact; };
 		// beta != 0: the old C is folded in up front (running sums start at (beta/alpha) * C), see the SS kernel
 		auto weighted = [&](const Seg &sg) { return !CONV && preload_c && sg.wi.slot < 0; };     // this segment's sums are in units of beta
 		auto from_c = [&](const Seg &sg) { return weighted(sg) && row_of(sg) < P.M; };
@@ -1204,7 +1218,7 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 		while (have) {
 			const int nev = nev_of(cur);
 			const float r_cur = weight(cur);
-			for (int ev = done; ev < nev; ev++) drain(ev % NSL, r_cur);
+			for (int ev = done; ev < nev; ev++) drain(ev % cur.nact, r_cur);
 			const bool have_next = fetch(nxt);
 			done = 0;
 			if (have_next && from_c(nxt)) {
@@ -1221,12 +1235,13 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 			// segment, and hand-overs of the next segment that are already waiting (slice <= g) are taken at once: the MMA thread
 			// needs their buffers back within a few k-blocks, a whole-tile store takes longer than that.
 			const float r_nxt = have_next ? weight(nxt) : 1.f;
+			const int nev_nxt = have_next ? nev_of(nxt) : 0;
 			auto after_group = [&](int g) {
 				if (!have_next) return;
 #pragma unroll
 				for (int gg = 0; gg < NG; gg++)
 					if (gg == g) epi_init_group<CG, true>(acc[gg], gg, P, from_c(nxt), crow_of(nxt), nxt.tn, h);
-				while (done <= g && mbar_try_wait(bar(B_TFULL + db), dph)) { drain(done % NSL, r_nxt); done++; }   // (a segment has >= NSL hand-overs)
+				while (done <= g && done < nev_nxt && mbar_try_wait(bar(B_TFULL + db), dph)) { drain(done % nxt.nact, r_nxt); done++; }
 			};
 			const long long ts0 = tick<PROF>();
 			epi_store_tile<CG, CONV, true>(acc, P, &tmC, cur.wi, preload_c, weighted(cur) ? P.beta : P.alpha, row_of(cur), crow_of(cur), cur.tm, cur.tn, cur.inst, q, h, e, lane, cta_rank, bar_base, after_group, P.sk_q > 0 ? &tmW : nullptr);
