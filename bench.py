@@ -389,10 +389,13 @@ def run_single(args, wl_name):
     for _ in range(e2e_steps):
         u.sgemm_cuda("R", "N", "N", M, N, K, 1.0, hA, K, hB, N, 0.0, hC, N)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    # cheap integrity check of the e2e result against the device-resident run (same inputs, same kernel)
+    # cheap integrity check of the e2e result against the device-resident run (same inputs, same kernel).  Not bit for bit: the host
+    # path multiplies row panels, whose tiles fall into other waves of the persistent grid than the whole problem's, and the order in
+    # which a tile walks K (serpentine) and the stream-K cut points depend on that -- two roundings of the same product.
     res_host = np.ctypeslib.as_array(C.cast(hC, C.POINTER(C.c_float)), shape=(M * N,))
     res_dev = dC.download(4096)
-    assert np.array_equal(res_host[:4096], res_dev), "e2e result differs from device-resident result"
+    diff = float(np.linalg.norm(res_host[:4096].astype(np.float64) - res_dev) / np.linalg.norm(res_dev.astype(np.float64)))
+    assert diff <= 2e-6, f"e2e result differs from the device-resident result: relative difference {diff:.3e}"
     for h in (hA, hB, hC):
         L.ugemm_cuda_free_host(h)
 

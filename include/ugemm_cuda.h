@@ -71,6 +71,11 @@ void sgemm_cuda_3xtf32(char major, char transA, char transB, int M, int N, int K
 void sgemm_cuda_simt(char major, char transA, char transB, int M, int N, int K, float alpha,
                      const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc);
 
+/* Reproducibility: a call is deterministic -- the same arguments (shape, leading dimensions, pointer alignment) on the same device
+ * with the same SM limit give the same bits, stream-K tail and serpentine K included (no atomics on data).  Two DIFFERENT ways of
+ * computing the same product (the pipelined host-pointer path, which multiplies row panels; the sharded drivers; another SM limit)
+ * order the K sum differently and agree to round-off (~1e-6 relative), not bit for bit. */
+
 /* ---- the timed path: DEVICE pointers, asynchronous on `stream` (a cudaStream_t; NULL = the backend's
  * own non-blocking stream -- pass cudaStreamLegacy (0x1) to mean CUDA's legacy default stream).  Replaces the body of sgemm_ocl after its uploads (kernel launch, sgemm_ocl2.h:201-215),
  * including the work of the separate `transpose` kernel (sgemm_ocl2.h:95-128,180-199): transposes are
