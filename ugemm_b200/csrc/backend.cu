@@ -176,7 +176,9 @@ cudaError_t launch_k1(const Problem &p, cudaStream_t stream)
 {
 	const bool limited = g.sm_limit > 0 && g.sm_limit < g.sm_count;
 	K1Tuning t = g.tuning;
-	if (limited) t.flags |= 2048;
+	// ... and no programmatic dependent launch either: the next product's CTAs would settle on the SMs left free for NCCL while this
+	// product is still running, and the broadcasts would wait behind both (8 GPUs, NCCL transport: 42 -> 65 ms per step [measured])
+	if (limited) t.flags |= 2048 | 262144;
 	return launch_k1_3xtf32(p, t, stream, limited ? g.sm_limit : g.sm_count);
 }
 
