@@ -5,7 +5,7 @@ SRC   := ugemm_b200/csrc/backend.cu ugemm_b200/csrc/k1_tcgen05.cu ugemm_b200/csr
 LIB   := ugemm_b200/libugemm_cuda.so
 
 all: $(LIB) oracle harness
-$(LIB): $(SRC) ugemm_b200/csrc/common.cuh ugemm_b200/csrc/ptx.cuh include/ugemm_cuda.h
+$(LIB): $(SRC) ugemm_b200/csrc/common.cuh ugemm_b200/csrc/ptx.cuh ugemm_b200/csrc/k1_common.cuh ugemm_b200/csrc/k1_ss.cuh ugemm_b200/csrc/k1_ts.cuh include/ugemm_cuda.h
 	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -o $@ $(SRC) -ldl
 oracle:
 	$(MAKE) -C oracle all

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libugemm_cuda.so")
 SOURCES = ["backend.cu", "k1_tcgen05.cu", "k2_simt.cu", "k3_level12.cu", "k4_dgemm.cu", "shard.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "ugemm_cuda.h")]
+HEADERS = ["common.cuh", "ptx.cuh", "k1_common.cuh", "k1_ss.cuh", "k1_ts.cuh", os.path.join("..", "..", "include", "ugemm_cuda.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-ldl",
