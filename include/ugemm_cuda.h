@@ -134,6 +134,15 @@ void sgemm_cuda_set_k1_tuning(int kc_blocks, int split, int cta_group);
  * round-to-nearest split experiment (split = 1) always runs on SS. */
 void sgemm_cuda_set_k1_variant(int variant);
 
+/* The schedule K1 would use for a dense M x N x K problem (`batch` instances) on `sm_count` SMs (0 = 148) with the current tuning,
+ * as pure host arithmetic (no GPU): plan12[0..11] = cta_group, tile_m, tile_n, tiles_m, tiles_n, k-blocks per tile, promotion
+ * interval in k-blocks, whole tiles, stream-K tail tiles, promotion chunks per tile, chunks per tail range, work items.  Work items
+ * below plan12[7] are whole tiles; the others are chunk ranges of the tail, each of up to two segments:
+ * sgemm_cuda_k1_plan_item gives segment h (0 / 1) of an item as out4 = tile, first k-block, end k-block, workspace slot (-1: a whole
+ * tile; end <= first: no such segment) -- the very function the kernel's roles decode their work with.  For tests and tools. */
+int  sgemm_cuda_k1_plan(int M, int N, int K, int batch, int sm_count, int *plan12);
+int  sgemm_cuda_k1_plan_item(const int *plan12, int item, int h, int *out4);
+
 /* Cap the number of SMs K1's persistent grid occupies (0 = all).  Used by the sharded driver while NCCL panel
  * broadcasts are in flight: a persistent CTA fills an SM's registers and shared memory, so a few SMs are left
  * free for the collective's own CTAs instead of serialising the transfer behind the GEMM. */

@@ -93,3 +93,53 @@ def test_product_never_references_the_oracle():
     assert not bad, bad
     out = subprocess.run(["ldd", os.path.join(ROOT, "ugemm_b200", "libugemm_cuda.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out and "ugemm_ref" not in out
+
+
+def test_k1_schedule_partition_invariants():
+    """sgemm_cuda_k1_plan / _plan_item (pure host arithmetic, the function the kernel's roles decode their work with): whole tiles
+    appear once, the stream-K tail's chunk ranges tile every tail tile's K extent exactly once in multiples of the promotion
+    interval, workspace slots are distinct, and there are never more ranges than CTA pairs (one range per pair)."""
+    import random
+    import ugemm_b200 as u
+    rng = random.Random(7)
+    shapes = [(8192, 8192, 8192), (4095, 3001, 2047), (4096, 4096, 4096), (2560, 2560, 2560), (1024, 1024, 1024), (512, 512, 4096),
+              (200704, 256, 1152), (1100, 900, 1024), (768, 640, 4096), (129, 257, 33), (128, 128, 32)]
+    shapes += [(rng.randint(1, 6000), rng.randint(1, 6000), rng.randint(1, 9000)) for _ in range(150)]
+    tails = 0
+    try:
+        for kc in (4, 2, 8, 0):
+            u.set_k1_tuning(kc_blocks=kc)
+            for (M, N, K) in shapes:
+                for sms in (148, 140, 4, 3):
+                    p = u.k1_plan(M, N, K, 1, sms)
+                    cg, nkb, kcp = p["cta_group"], p["k_blocks"], p["kc"]
+                    assert cg in (1, 2) and p["tile_m"] == 128 * cg and p["tiles_m"] == -(-M // p["tile_m"]) and p["tiles_n"] == -(-N // p["tile_n"])
+                    nt = p["tiles_m"] * p["tiles_n"]
+                    assert nkb == -(-K // 32) and 1 <= kcp <= nkb
+                    assert p["whole_tiles"] + p["tail_tiles"] == nt
+                    ranges = p["items"] - p["whole_tiles"]
+                    if p["tail_tiles"] == 0:
+                        assert p["items"] == nt
+                        continue
+                    tails += 1
+                    assert 0 < ranges <= max(1, sms // cg) and p["whole_tiles"] % max(1, sms // cg) == 0
+                    assert u.k1_plan_item(p, 0, 0) == (0, 0, nkb, -1) if p["whole_tiles"] else True
+                    cover, slots = {}, set()
+                    for item in range(p["whole_tiles"], p["items"]):
+                        segs = [u.k1_plan_item(p, item, h) for h in (0, 1)]
+                        assert segs[0][2] > segs[0][1], "a range has at least its first segment"
+                        for (tile, kb0, kb1, slot) in segs:
+                            if kb1 <= kb0:
+                                continue
+                            assert p["whole_tiles"] <= tile < nt and 0 <= kb0 < kb1 <= nkb and kb0 % kcp == 0 and (kb1 % kcp == 0 or kb1 == nkb)
+                            assert 0 <= slot < 2 * ranges and slot not in slots
+                            slots.add(slot)
+                            cover.setdefault(tile, []).append((kb0, kb1))
+                    assert sorted(cover) == list(range(p["whole_tiles"], nt))
+                    for tile, spans in cover.items():
+                        spans.sort()
+                        assert spans[0][0] == 0 and spans[-1][1] == nkb and all(a[1] == b[0] for a, b in zip(spans, spans[1:])), (M, N, K, tile, spans)
+    finally:
+        u.set_k1_tuning(kc_blocks=4)
+    assert tails > 50, tails          # the sweep did exercise the tail
+    assert u.last_error() is None

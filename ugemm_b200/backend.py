@@ -79,6 +79,10 @@ def lib():
     L.ugemm_cuda_device_info.restype = C.c_int
     L.sgemm_cuda_set_k1_tuning.argtypes = [C.c_int, C.c_int, C.c_int]
     L.sgemm_cuda_set_k1_tuning.restype = None
+    L.sgemm_cuda_k1_plan.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_int)]
+    L.sgemm_cuda_k1_plan.restype = C.c_int
+    L.sgemm_cuda_k1_plan_item.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.sgemm_cuda_k1_plan_item.restype = C.c_int
     L.sgemm_cuda_set_k1_variant.argtypes = [C.c_int]
     L.sgemm_cuda_set_k1_variant.restype = None
     L.sgemm_cuda_set_sm_limit.argtypes = [C.c_int]
@@ -184,7 +188,7 @@ EXPORTED_SYMBOLS = [
     "sgemm_cuda_init", "sgemm_cuda_finish", "sgemm_cuda", "sgemm_cuda_3xtf32", "sgemm_cuda_simt",
     "sgemm_cuda_dev", "sgemm_cuda_batched", "sgemm_cuda_batched_dev", "sgemm_cuda_k1_eligible", "sgemm_cuda_time_dev", "sgemm_cuda_last_error",
     "sgemm_cuda_clear_error", "sgemm_cuda_last_kernel", "sgemm_cuda_last_repacked", "sgemm_cuda_launch_count", "ugemm_cuda_device_info",
-    "sgemm_cuda_set_k1_tuning", "sgemm_cuda_set_k1_variant", "sgemm_cuda_set_sm_limit", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
+    "sgemm_cuda_set_k1_tuning", "sgemm_cuda_set_k1_variant", "sgemm_cuda_k1_plan", "sgemm_cuda_k1_plan_item", "sgemm_cuda_set_sm_limit", "ugemm_cuda_malloc", "ugemm_cuda_free", "ugemm_cuda_malloc_host",
     "ugemm_cuda_free_host", "ugemm_cuda_memcpy_h2d", "ugemm_cuda_memcpy_d2h", "ugemm_cuda_sync",
     "ugemm_cuda_memcpy_async", "ugemm_cuda_ipc_export", "ugemm_cuda_ipc_import", "ugemm_cuda_ipc_close",
     "sgemm_cuda_mgpu_init", "sgemm_cuda_mgpu_finish", "sgemm_cuda_mgpu_count", "sgemm_cuda_mgpu", "sgemm_cuda_mgpu_run", "sgemm_cuda_mgpu_plan", "ugemm_cuda_device_count",
@@ -283,6 +287,29 @@ def k1_eligible(major, ta, tb, M, N, K, dA, lda, dB, ldb, dC, ldc):
 
 def set_k1_tuning(kc_blocks=-1, split=-1, cta_group=-1):
     lib().sgemm_cuda_set_k1_tuning(kc_blocks, split, cta_group)
+
+
+K1_PLAN_KEYS = ("cta_group", "tile_m", "tile_n", "tiles_m", "tiles_n", "k_blocks", "kc", "whole_tiles", "tail_tiles", "chunks_per_tile", "chunks_per_range", "items")
+
+
+def k1_plan(M, N, K, batch=1, sm_count=0):
+    """The schedule K1 would use (pure host arithmetic, no GPU): dict of K1_PLAN_KEYS plus the raw int array under "_raw"."""
+    raw = (C.c_int * 12)()
+    if lib().sgemm_cuda_k1_plan(M, N, K, batch, sm_count, raw):
+        check()
+        raise UgemmCudaError("sgemm_cuda_k1_plan failed")
+    d = dict(zip(K1_PLAN_KEYS, list(raw)))
+    d["_raw"] = raw
+    return d
+
+
+def k1_plan_item(plan, item, h):
+    """(tile, kb0, kb1, slot) of segment h of work item `item` of a k1_plan()"""
+    out = (C.c_int * 4)()
+    if lib().sgemm_cuda_k1_plan_item(plan["_raw"], item, h, out):
+        check()
+        raise UgemmCudaError("sgemm_cuda_k1_plan_item failed")
+    return tuple(out)
 
 
 def set_k1_variant(variant=0):

@@ -648,6 +648,24 @@ void sgemm_cuda_set_k1_tuning(int kc_blocks, int split, int cta_group)
 	if (cta_group >= 0 && cta_group <= 2) g.tuning.cta_group = cta_group;   // 0 = choose by problem size
 }
 
+// The schedule K1 would use for a dense M x N x K problem (`batch` instances) on `sm_count` SMs (0: 148, a B200) with the current
+// tuning: pure host arithmetic, no GPU needed.  out[0..11] = cta_group, tile_m, tile_n, tiles_m, tiles_n, k-blocks per tile,
+// promotion interval (k-blocks), whole tiles, stream-K tail tiles, promotion chunks per tile, chunks per tail range, work items.
+int sgemm_cuda_k1_plan(int M, int N, int K, int batch, int sm_count, int *out12)
+{
+	if (M < 1 || N < 1 || K < 1 || !out12) { set_error("sgemm_cuda_k1_plan: bad arguments"); return 1; }
+	k1_plan(M, N, K, batch > 0 ? batch : 1, g.tuning, sm_count > 0 ? sm_count : 148, out12);
+	return 0;
+}
+// Segment h (0 or 1) of work item `item` of such a schedule: out[0..3] = tile, first k-block, end k-block, workspace slot (-1 for a
+// whole tile); an absent segment has end <= first.  The same function the kernel's roles decode their work with.
+int sgemm_cuda_k1_plan_item(const int *plan12, int item, int h, int *out4)
+{
+	if (!plan12 || !out4 || item < 0 || item >= plan12[11] || h < 0 || h > 1) { set_error("sgemm_cuda_k1_plan_item: bad arguments"); return 1; }
+	k1_plan_item(item, h, plan12[7], plan12[8], plan12[9], plan12[10], plan12[6], plan12[5], out4);
+	return 0;
+}
+
 void sgemm_cuda_set_k1_variant(int variant)
 {
 	if (variant == 1) g.tuning.flags |= 32768;        // round-1 SS kernel (both operands from shared memory)

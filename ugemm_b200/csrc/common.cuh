@@ -64,6 +64,9 @@ cudaError_t launch_k2_simt(const Problem &p, cudaStream_t stream, int sm_count);
 // K1: 3xTF32 tcgen05 kernel (k1_tcgen05.cu).  *why (optional) receives a static string on ineligibility.
 bool        k1_eligible(const Problem &p, const char **why);
 cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count);
+// the schedule of a dense K1 launch as host arithmetic (k1_tcgen05.cu; exported as sgemm_cuda_k1_plan / _plan_item)
+void k1_plan(int M, int N, int K, int batch, const K1Tuning &t, int sm_count, int *out12);
+void k1_plan_item(int item, int h, int sk_full, int sk_rem, int sk_nch, int sk_q, int kc, int nkb, int *out4);
 // implicit-GEMM convolution (k1_tcgen05.cu): weight repack [co][c][ki][kj] -> [co][ki*k+kj][ichp] (zero padded), and the launch
 cudaError_t launch_conv_weight_repack(const float *w, int ch, int ich, int k, int ichp, float *dst, cudaStream_t stream);
 cudaError_t launch_chw_to_hwc(const float *in, int nimg, int ich, int h, int w, int cs, float *out, cudaStream_t stream);

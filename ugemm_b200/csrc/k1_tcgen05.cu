@@ -348,37 +348,49 @@ cudaError_t launch_kernel(const CUtensorMap &tmA, const CUtensorMap &tmB, const 
 // only partly filled (c3: 192 tiles on 74 pairs = 2.6 rounds, 4096^3: 3.5, anything smaller than the machine: < 1), its
 // tiles are cut along K into equal chunk ranges, one per pair, whose partial sums meet in a workspace (decode_item,
 // k1_tail_fixup_kernel).  Taken when it shortens the last round by at least 15 % and the launch by at least 12 %.
+// The decision as pure host arithmetic (also exported through sgemm_cuda_k1_plan, so that the partition is checked without a GPU):
+// nt tiles of nkb k-blocks on `pairs` CTA pairs (or single CTAs), promotion chunks of kc k-blocks.  Returns true when the tail is cut,
+// with full = whole tiles, rem = tail tiles, nch = chunks per tile, q = chunks per range, ranges = number of ranges.
+struct TailPlan { long long full, rem, q, ranges; int nch; };
+bool plan_tail(long long nt, int nkb, int kc_eff, long long pairs, bool ts, int flags, TailPlan *tp)
+{
+	const int nch = (nkb + kc_eff - 1) / kc_eff;
+	tp->full = nt; tp->rem = 0; tp->q = 0; tp->ranges = 0; tp->nch = nch;
+	if ((flags & 2048) || nch < 2 || pairs <= 0 || nt % pairs == 0) return false;
+	const long long full = nt / pairs * pairs, rem = nt - full;
+	const long long q = (rem * nch + pairs - 1) / pairs, ranges = (rem * nch + q - 1) / q;
+	// expected saving: (1 - q/nch) of one round out of ceil(nt / pairs); the fix-up pass and the tail's poorer L2 locality
+	// (parts of one tile run at different k offsets) cost a few percent of a round, so small savings are not worth it
+	const double saved_rounds = 1.0 - (double)q / nch, rounds = (double)((nt + pairs - 1) / pairs);
+	// (SS kernel, measured: a modelled saving of 7-11 % of the launch came out as a 2-4 % loss, 13 % as a 10 % gain)
+	// TS kernel [measured, profiles/r2n_sk_sweep.jsonl, r2p_sk_sweep.jsonl]: once at least one full round precedes the tail, the part
+	// stores, the fix-up pass and the tail's colder start cost about as much as 30 k-blocks of a pair; below that the tail is a loss
+	// (4096 x 3072 x 2048: 24 k-blocks saved, 219 vs 209 us), above it a gain (2560^3: 48 saved, 155 vs 175 us; 4096^3: 68, 494 vs 522)
+	// ... and at least 2 % of a pair's whole work: at 8192^3 the tail saves 40 of 3543 k-blocks per pair, costs 0.36 GB of extra DRAM
+	// traffic (parts, colder tail) and measures as nothing (3.66 vs 3.64 ms, profiles/r3a_traffic.csv)
+	const long long saved_kb = (nch - q) * (long long)kc_eff, pair_kb = (nt * (long long)nkb + pairs - 1) / pairs;
+	const bool worth = ts ? (full == 0 ? saved_rounds >= 0.15 : (saved_kb >= 32 && saved_kb * 50 >= pair_kb))
+	                      : (saved_rounds >= 0.15 && saved_rounds / rounds >= 0.12);
+	if (!((worth || ((flags & 131072) && saved_rounds > 0.0)) && rem * nch < 0x3fffffffLL)) return false;      // (bit 17: tail whenever it saves anything, A/B runs)
+	tp->full = full; tp->rem = rem; tp->q = q; tp->ranges = ranges;
+	return true;
+}
+
 template <int CG, bool CONV, bool TS = false>
 cudaError_t launch_with_tail(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, K1Params &P, long long nt, const K1Tuning &t, cudaStream_t stream, int sm_count)
 {
 	const int kc_eff = (t.kc_blocks > 0 && t.kc_blocks < P.num_k_blocks) ? t.kc_blocks : P.num_k_blocks;
-	const int nch = (P.num_k_blocks + kc_eff - 1) / kc_eff;
 	const long long pairs = sm_count / CG;
 	const int tile_m = 128 * CG, tile_n = 128 * CG;
 	long long items = nt;
 	float *ws = nullptr;
-	if (!(t.flags & 2048) && nch >= 2 && pairs > 0 && nt % pairs != 0) {
-		const long long full = nt / pairs * pairs, rem = nt - full;
-		const long long q = (rem * nch + pairs - 1) / pairs, ranges = (rem * nch + q - 1) / q;
-		// expected saving: (1 - q/nch) of one round out of ceil(nt / pairs); the fix-up pass and the tail's poorer L2 locality
-		// (parts of one tile run at different k offsets) cost a few percent of a round, so small savings are not worth it
-		const double saved_rounds = 1.0 - (double)q / nch, rounds = (double)((nt + pairs - 1) / pairs);
-		// (measured: a modelled saving of 7-11 % of the launch came out as a 2-4 % loss, 13 % as a 10 % gain)
-		// TS kernel [measured, profiles/r2n_sk_sweep.jsonl, r2o_sk_ablate.txt]: once at least one full round precedes the tail, the part
-		// stores, the fix-up pass and the tail's colder start cost about as much as 30 k-blocks of a pair; below that the tail is a loss
-		// (4096 x 3072 x 2048: 24 k-blocks saved, 219 vs 209 us), above it a gain (2560^3: 48 saved, 155 vs 175 us; 4096^3: 68, 494 vs 522)
-		// ... and at least 2 % of a pair's whole work: at 8192^3 the tail saves 40 of 3543 k-blocks per pair, costs 0.36 GB of extra DRAM
-		// traffic (parts, colder tail) and measures as nothing (3.66 vs 3.64 ms, profiles/r3a_traffic.csv)
-		const long long saved_kb = (nch - q) * (long long)kc_eff, pair_kb = (nt * (long long)P.num_k_blocks + pairs - 1) / pairs;
-		const bool worth = TS ? (full == 0 ? saved_rounds >= 0.15 : (saved_kb >= 32 && saved_kb * 50 >= pair_kb))
-		                      : (saved_rounds >= 0.15 && saved_rounds / rounds >= 0.12);
-		if ((worth || ((t.flags & 131072) && saved_rounds > 0.0)) && rem * nch < 0x3fffffffLL) {      // (bit 17: tail whenever it saves anything, A/B runs)
-			const size_t tile_bytes = (size_t)tile_m * tile_n * sizeof(float);
-			if (cudaMallocAsync(reinterpret_cast<void **>(&ws), (size_t)(2 * ranges) * tile_bytes, stream) == cudaSuccess) {
-				P.sk_full = (int)full; P.sk_rem = (int)rem; P.sk_nch = nch; P.sk_q = (int)q; P.sk_ws = ws;
-				items = full + ranges;
-			} else { cudaGetLastError(); ws = nullptr; }
-		}
+	TailPlan tp;
+	if (plan_tail(nt, P.num_k_blocks, kc_eff, pairs, TS, t.flags, &tp)) {
+		const size_t tile_bytes = (size_t)tile_m * tile_n * sizeof(float);
+		if (cudaMallocAsync(reinterpret_cast<void **>(&ws), (size_t)(2 * tp.ranges) * tile_bytes, stream) == cudaSuccess) {
+			P.sk_full = (int)tp.full; P.sk_rem = (int)tp.rem; P.sk_nch = tp.nch; P.sk_q = (int)tp.q; P.sk_ws = ws;
+			items = tp.full + tp.ranges;
+		} else { cudaGetLastError(); ws = nullptr; }
 	}
 	CUtensorMap tmW = tmA;
 	if (TS && ws) {
@@ -544,8 +556,10 @@ bool k1_eligible(const Problem &p, const char **why)
 	return w == nullptr;
 }
 
-cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
+// CTA pairing of a dense problem (pure host arithmetic): 2 = 256 x 256 tiles on CTA pairs, 1 = 128 x 128 tiles on single CTAs
+int choose_cta_group(int M, int N, int K, int batch, const K1Tuning &t, int sm_count)
 {
+	struct { int M, N, K, batch; } p = {M, N, K, batch};
 	int cg = t.cta_group;
 	if (cg != 1 && cg != 2) {
 		// auto: 2-CTA pairs (256x256 tiles, half the shared-memory operand traffic per flop) once there are enough
@@ -561,8 +575,36 @@ cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t s
 		// (200704 x 128 x 1152: 0.42 vs 0.50 ms; 8192 x 64 x 8192: 0.14 vs 0.17 ms; profiles/r1_skinny_k1_vs_k2.jsonl)
 		if (p.M <= 128 || p.N <= 128) cg = 1;
 	}
-	if (cg == 1) return launch_cg<1>(p, t, stream, sm_count);
+	return cg;
+}
+
+cudaError_t launch_k1_3xtf32(const Problem &p, const K1Tuning &t, cudaStream_t stream, int sm_count)
+{
+	if (choose_cta_group(p.M, p.N, p.K, p.batch, t, sm_count) == 1) return launch_cg<1>(p, t, stream, sm_count);
 	return launch_cg<2>(p, t, stream, sm_count);
+}
+
+// The schedule of a dense K1 launch as numbers (sgemm_cuda_k1_plan): out[0..11] = cta_group, tile_m, tile_n, tiles_m, tiles_n,
+// k-blocks per tile, promotion interval in k-blocks, whole tiles, tail tiles, chunks per tile, chunks per tail range, work items.
+void k1_plan(int M, int N, int K, int batch, const K1Tuning &t_in, int sm_count, int *out)
+{
+	const bool ts = !(t_in.flags & 32768) && t_in.split == 0;
+	const int cg = choose_cta_group(M, N, K, batch, t_in, sm_count);
+	K1Tuning t = t_in;
+	if (ts && t.kc_blocks > 0) { const int nsl = 2 * cg; t.kc_blocks = (t.kc_blocks + nsl - 1) / nsl * nsl; }
+	const int tile = 128 * cg, tiles_m = (M + tile - 1) / tile, tiles_n = (N + tile - 1) / tile, nkb = (K + BK - 1) / BK;
+	const long long nt = (long long)tiles_m * tiles_n * (batch > 0 ? batch : 1);
+	const int kc_eff = (t.kc_blocks > 0 && t.kc_blocks < nkb) ? t.kc_blocks : nkb;
+	TailPlan tp;
+	const bool tail = plan_tail(nt, nkb, kc_eff, sm_count / cg, ts, t.flags, &tp);
+	const long long v[12] = {cg, tile, tile, tiles_m, tiles_n, nkb, kc_eff, tail ? tp.full : nt, tail ? tp.rem : 0, tp.nch, tail ? tp.q : 0, tail ? tp.full + tp.ranges : nt};
+	for (int i = 0; i < 12; i++) out[i] = (int)v[i];
+}
+// one segment of a work item of that schedule (decode_item, the function every role of the kernel decodes items with)
+void k1_plan_item(int item, int h, int sk_full, int sk_rem, int sk_nch, int sk_q, int kc, int nkb, int *out)
+{
+	const Item it = decode_item(item, h, sk_full, sk_rem, sk_nch, sk_q, kc, nkb);
+	out[0] = it.tile; out[1] = it.kb0; out[2] = it.kb1; out[3] = it.slot;
 }
 
 cudaError_t launch_conv_weight_repack(const float *w, int ch, int ich, int k, int ichp, float *dst, cudaStream_t stream)
