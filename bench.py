@@ -28,7 +28,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-IDLE_GAP_S = 1.0      # idle time in front of every side-table shape (see other_shapes)
+IDLE_GAP_S = 2.0      # idle time in front of every side-table shape (see other_shapes)
 
 WORKLOADS = {
     "c1": dict(M=1024, N=1024, K=1024, desc="SGEMM row-major NN 1024x1024x1024 fp32 alpha=1 beta=0 (BASELINE configs[0]: the check_sgemm CPU case)"),
