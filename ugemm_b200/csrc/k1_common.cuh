@@ -184,7 +184,25 @@ __device__ __forceinline__ void epi_init_group(float (&a)[32], int g, const K1Pa
 	constexpr int BN = 128 * CG;
 	if (from_c) {
 		const long long col0 = (long long)tn * BN + group_col<CG, TS>(h, g);
-		if (P.vecC && col0 + 31 < P.N) {
+		if (P.vecC && col0 + 31 < P.N && !(P.flags & 1048576)) {
+			// One row per thread: a warp's load instruction touches 32 different lines whatever its width, and the L1 takes one
+			// wavefront per line -- so 256-bit loads (sm_100: LDG.E.256) halve the wavefronts of the preload against 128-bit ones
+			// (4 x 32 instead of 8 x 32 per warp and group).  A row that starts on an odd 16-byte boundary (ldc % 8 == 4) takes
+			// 16 + 3 x 32 + 16 bytes; the two kinds of rows alternate within a warp, each load then touches 16 lines.
+			const float *p = crow + col0;
+			if ((reinterpret_cast<uintptr_t>(p) & 31u) == 0) {
+#pragma unroll
+				for (int i = 0; i < 32; i += 8) ldg256(p + i, &a[i]);
+			} else {
+				const float4 c0 = *reinterpret_cast<const float4 *>(p);
+				a[0] = c0.x; a[1] = c0.y; a[2] = c0.z; a[3] = c0.w;
+#pragma unroll
+				for (int i = 4; i < 28; i += 8) ldg256(p + i, &a[i]);
+				const float4 c7 = *reinterpret_cast<const float4 *>(p + 28);
+				a[28] = c7.x; a[29] = c7.y; a[30] = c7.z; a[31] = c7.w;
+			}
+		} else if (P.vecC && col0 + 31 < P.N) {
+			// (flags bit 20, A/B runs: the 128-bit form)
 #pragma unroll
 			for (int i = 0; i < 32; i += 4) {
 				const float4 cv = *reinterpret_cast<const float4 *>(crow + col0 + i);

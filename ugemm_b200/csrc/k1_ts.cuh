@@ -39,6 +39,7 @@ static_assert(TS_SMEM_BYTES <= 232448, "shared-memory budget of one CTA (227 KiB
 constexpr int B_FULL = 0, B_XF = 4, B_EMPTY = 8, B_AFREE = 12, B_TFULL = 16, B_TEMPTY = 21;
 constexpr int B_SCHED = 26;                           // tile-index ring: full[4], empty[4], 4 x 4-byte slots (next_tile's layout, rebased)
 constexpr int B_TMEM = 37;
+constexpr int B_CLOAD = 40;                           // one per epilogue warp: the old C of a 32 x 32 box has landed in the warp's staging box (beta != 0)
 }
 
 // CONV: the B operand is an image gathered by 4-D TMA boxes (implicit im2col, see the SS kernel): every 32-row group of a B stage
@@ -89,6 +90,7 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 			mbar_init(bar(B_TFULL + b), 1);
 			mbar_init(bar(B_TEMPTY + b), 8 * CG);    // 8 epilogue warps per CTA of the pair
 		}
+		for (int w = 0; w < 8; w++) mbar_init(bar(B_CLOAD + w), 1);
 		for (int d = 0; d < SCHED_SLOTS; d++) {
 			mbar_init(bar(B_SCHED + d), 1);
 			mbar_init(bar(B_SCHED + SCHED_SLOTS + d), (1 + 8 + 8) * CG + 1);   // TMA thread, 8 transform + 8 epilogue warps per CTA, the MMA thread
@@ -424,6 +426,14 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 		// tile end multiplies by beta.  A stream-K part starts at zero and stays unweighted (the fix-up pass applies alpha and beta).
 		const float ab = P.alpha / P.beta;
 		const bool preload_c = P.beta != 0.f && fabsf(ab) < 1e18f && fabsf(ab) > 1e-18f;
+		// Where the old C comes from.  With a TMA-addressable C it is fetched by the TMA unit, one 32 x 32 box at a time, into the warp's
+		// staging box (idle between two tile stores) and ADDED to the running sums between two promotions, any time before the tile
+		// ends (the sums are in units of beta either way).  Loading it into the registers with global loads when a group is re-armed
+		// (flags bit 22, and any C the TMA unit cannot address) costs the load/store pipe 32 wavefronts per warp instruction -- one row
+		// per thread -- which the transform warps' shared-memory traffic has to share: 10 % on config 3.
+		const bool c_tma = preload_c && !CONV && P.tma_store && !(P.flags & 4194304);
+		const uint32_t cbar = bar(B_CLOAD + e), cbox = bar_base + 1024u + (uint32_t)e * CSTAGE_BYTES;
+		uint32_t cph = 0;
 		int db = 0; uint32_t dph = 0;                      // next slice buffer to be handed over, and its phase
 		long long w_tf = 0, t_store = 0; const long long t_begin = tick<PROF>();
 		float acc[NG][32];
@@ -476,7 +486,33 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 		auto nev_of = [&](const Seg &sg) { const int nseg = sg.wi.kb1 - sg.wi.kb0; return (nseg - 1 >= kc ? (nseg - 1 - kc) / step + 1 : 0) + sg.nact; };
 		// beta != 0: the old C is folded in up front (running sums start at (beta/alpha) * C), see the SS kernel
 		auto weighted = [&](const Seg &sg) { return !CONV && preload_c && sg.wi.slot < 0; };     // this segment's sums are in units of beta
-		auto from_c = [&](const Seg &sg) { return weighted(sg) && row_of(sg) < P.M; };
+		auto from_c = [&](const Seg &sg) { return weighted(sg) && !c_tma && row_of(sg) < P.M; };             // registers start at C (global loads)
+		auto box_row0 = [&](const Seg &sg) { return sg.tm * UMMA_M + (int)cta_rank * ROWS + q * 32; };
+		// c_tma: how many of this warp's 32-column groups hold elements of C (group g starts at tile column 64 g + 32 h; warp-uniform)
+		auto c_groups = [&](const Seg &sg) {
+			if (!c_tma || !weighted(sg) || box_row0(sg) >= P.M) return 0;
+			const int rem = P.N - sg.tn * BN - h * 32;
+			return rem <= 0 ? 0 : (rem + 63) / 64 > NG ? NG : (rem + 63) / 64;
+		};
+		auto c_issue = [&](const Seg &sg, int g) {
+			if (lane == 0) {
+				bulk_wait_group_read0();                       // the box's last TMA store has left shared memory
+				mbar_arrive_expect_tx(cbar, CSTAGE_BYTES);     // (a box that sticks out of C is zero-filled and counts in full)
+				tma_load_3d_hint(cbox, &tmC, cbar, sg.tn * BN + group_col<CG, true>(h, g), box_row0(sg), sg.inst, L2_EVICT_NORMAL);
+			}
+		};
+		auto c_take = [&](int g) {
+			mbar_wait(cbar, cph, P.diag, 9);
+			cph ^= 1u;
+#pragma unroll
+			for (int i = 0; i < 32; i += 4) {
+				const float4 v = lds128(cbox + (uint32_t)lane * 128u + (uint32_t)(((i >> 2) ^ (lane & 7)) << 4));
+#pragma unroll
+				for (int gg = 0; gg < NG; gg++)
+					if (gg == g) { acc[gg][i + 0] += v.x; acc[gg][i + 1] += v.y; acc[gg][i + 2] += v.z; acc[gg][i + 3] += v.w; }
+			}
+			__syncwarp();                                      // every lane has read the box before lane 0 lets the TMA unit overwrite it
+		};
 		auto weight = [&](const Seg &sg) { return weighted(sg) ? ab : 1.f; };
 		Seg cur, nxt;
 		bool have = fetch(cur);
@@ -488,17 +524,45 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 		while (have) {
 			const int nev = nev_of(cur);
 			const float r_cur = weight(cur);
-			for (int ev = done; ev < nev; ev++) drain(ev % cur.nact, r_cur);
+			// c_tma: after a promotion, take the box asked for after the previous one and ask for the next.  Reproducibility: the place
+			// of "+ C" in a group's chain of roundings must not depend on timing, so it is tied to the hand-over NUMBER of the tile --
+			// group g is asked for after hand-over NG + g and added after hand-over NG + g + 1 (or after the last one of a short tile);
+			// up to NG hand-overs may have been taken early during the previous store (`done`), never more.
+			const int ncg = c_groups(cur);
+			int cg = 0;
+			bool cpend = false;
+			auto c_step = [&]() {
+				if (cpend) { c_take(cg); cg++; cpend = false; }
+				if (cg < ncg) { c_issue(cur, cg); cpend = true; }
+			};
+			for (int ev = done; ev < nev; ev++) {
+				drain(ev % cur.nact, r_cur);
+				if (ev >= NG && cg < ncg) c_step();
+			}
+			while (cg < ncg) c_step();
 			const bool have_next = fetch(nxt);
 			done = 0;
-			if (have_next && from_c(nxt)) {
+			if (have_next && weighted(nxt) && (c_tma || from_c(nxt))) {
 				// beta != 0: the next segment's old C is needed group by group during the store below; start it towards L2 now, so that
 				// those loads are L2 hits instead of four DRAM round trips in a row on the path that gives slice buffers back
-				const float *c0 = crow_of(nxt) + (long long)nxt.tn * BN;
+				if (P.tma_store && !(P.flags & 2097152)) {
+					// one lane asks the TMA unit for the warp's four 32 x 32 boxes (a per-thread prefetch.global.L2 touches 32 lines per
+					// instruction and costs the L1 as many wavefronts as the loads it is meant to speed up; flags bit 21 = that form, A/B runs)
+					const int prow0 = box_row0(nxt);
+					if (lane == 0 && prow0 < P.M) {
 #pragma unroll
-				for (int g = 0; g < NG; g++) {
-					const long long col0 = (long long)nxt.tn * BN + group_col<CG, true>(h, g);
-					if (col0 < P.N) { prefetch_l2(c0 + group_col<CG, true>(h, g)); if (col0 + 31 < P.N) prefetch_l2(c0 + group_col<CG, true>(h, g) + 31); }
+						for (int g = 0; g < NG; g++) {
+							const int col0 = nxt.tn * BN + group_col<CG, true>(h, g);
+							if (col0 < P.N) tma_prefetch_3d(&tmC, col0, prow0, nxt.inst);
+						}
+					}
+				} else if (row_of(nxt) < P.M) {
+					const float *c0 = crow_of(nxt) + (long long)nxt.tn * BN;
+#pragma unroll
+					for (int g = 0; g < NG; g++) {
+						const long long col0 = (long long)nxt.tn * BN + group_col<CG, true>(h, g);
+						if (col0 < P.N) { prefetch_l2(c0 + group_col<CG, true>(h, g)); if (col0 + 31 < P.N) prefetch_l2(c0 + group_col<CG, true>(h, g) + 31); }
+					}
 				}
 			}
 			// Store `cur` one 32-column group at a time.  As soon as group g has been staged its registers are re-armed for the next
