@@ -56,9 +56,9 @@ struct ConvProblem {
 // bit 18 (262144): programmatic dependent launch off (A/B runs).
 // bit 17 (131072): stream-K tail whenever the model predicts any saving (A/B runs of the rule).
 // bit 16 (65536): ABLATION, stream-K fix-up pass skipped (results wrong).
-// bit 20 (1048576): beta != 0 preload of C with 128-bit loads instead of 256-bit ones; bit 21 (2097152): per-thread prefetch.global.L2
-// of the next tile's C instead of one TMA prefetch per box (A/B runs); bit 22 (4194304): beta != 0 takes the old C into the registers
-// with global loads when a group is re-armed instead of fetching it box by box through the TMA unit and adding it between promotions.
+// bit 20 (1048576): register path of the beta != 0 preload with 128-bit loads instead of 256-bit ones (A/B runs).
+// bit 22 (4194304): beta != 0 takes the old C into the registers with global loads when a group is re-armed (the path of a C the TMA
+// unit cannot address) instead of fetching it box by box through the TMA unit and adding it between promotions (A/B runs).
 // bit 14 (16384): round-1 barrier arrives (.release.cluster = MEMBAR.ALL.GPU in front of every transform / epilogue arrive; A/B runs).
 struct K1Tuning { int kc_blocks; int split; int cta_group; int flags; };
 

@@ -527,7 +527,8 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 			// c_tma: after a promotion, take the box asked for after the previous one and ask for the next.  Reproducibility: the place
 			// of "+ C" in a group's chain of roundings must not depend on timing, so it is tied to the hand-over NUMBER of the tile --
 			// group g is asked for after hand-over NG + g and added after hand-over NG + g + 1 (or after the last one of a short tile);
-			// up to NG hand-overs may have been taken early during the previous store (`done`), never more.
+			// up to NG hand-overs may have been taken early during the previous store (`done`), never more.  (Later places in the tile
+			// measure the same: hand-over 12 or 24 instead of NG, profiles/r4e_beta_ab.jsonl.)
 			const int ncg = c_groups(cur);
 			int cg = 0;
 			bool cpend = false;
@@ -542,27 +543,16 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 			while (cg < ncg) c_step();
 			const bool have_next = fetch(nxt);
 			done = 0;
-			if (have_next && weighted(nxt) && (c_tma || from_c(nxt))) {
-				// beta != 0: the next segment's old C is needed group by group during the store below; start it towards L2 now, so that
-				// those loads are L2 hits instead of four DRAM round trips in a row on the path that gives slice buffers back
-				if (P.tma_store && !(P.flags & 2097152)) {
-					// one lane asks the TMA unit for the warp's four 32 x 32 boxes (a per-thread prefetch.global.L2 touches 32 lines per
-					// instruction and costs the L1 as many wavefronts as the loads it is meant to speed up; flags bit 21 = that form, A/B runs)
-					const int prow0 = box_row0(nxt);
-					if (lane == 0 && prow0 < P.M) {
+			if (have_next && from_c(nxt)) {
+				// register path of beta != 0: the next segment's old C is needed group by group during the store below; start it towards
+				// L2 now, so that those loads are L2 hits instead of four DRAM round trips in a row on the path that gives slice buffers
+				// back.  (The TMA path asks a k-block ahead and gains nothing from a prefetch: 0.2217 vs 0.2235 ms on config 3 with one
+				// cp.async.bulk.prefetch.tensor per box, profiles/r4e_beta_ab.jsonl.)
+				const float *c0 = crow_of(nxt) + (long long)nxt.tn * BN;
 #pragma unroll
-						for (int g = 0; g < NG; g++) {
-							const int col0 = nxt.tn * BN + group_col<CG, true>(h, g);
-							if (col0 < P.N) tma_prefetch_3d(&tmC, col0, prow0, nxt.inst);
-						}
-					}
-				} else if (row_of(nxt) < P.M) {
-					const float *c0 = crow_of(nxt) + (long long)nxt.tn * BN;
-#pragma unroll
-					for (int g = 0; g < NG; g++) {
-						const long long col0 = (long long)nxt.tn * BN + group_col<CG, true>(h, g);
-						if (col0 < P.N) { prefetch_l2(c0 + group_col<CG, true>(h, g)); if (col0 + 31 < P.N) prefetch_l2(c0 + group_col<CG, true>(h, g) + 31); }
-					}
+				for (int g = 0; g < NG; g++) {
+					const long long col0 = (long long)nxt.tn * BN + group_col<CG, true>(h, g);
+					if (col0 < P.N) { prefetch_l2(c0 + group_col<CG, true>(h, g)); if (col0 + 31 < P.N) prefetch_l2(c0 + group_col<CG, true>(h, g) + 31); }
 				}
 			}
 			// Store `cur` one 32-column group at a time.  As soon as group g has been staged its registers are re-armed for the next

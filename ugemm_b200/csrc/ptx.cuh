@@ -276,12 +276,6 @@ template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setma
 
 // bring the line holding `p` into L2 (no register, no scoreboard: the later load finds it there)
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// one box of a tensor map towards L2 (no shared-memory destination, no completion to wait for); out-of-bounds parts are not fetched
-__device__ __forceinline__ void tma_prefetch_3d(const void *tmap, int c0, int c1, int c2)
-{
-	asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-	             ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 // 256-bit global load (sm_100: LDG.E.256), 32-byte aligned address; dst = 8 consecutive floats
 __device__ __forceinline__ void ldg256(const float *p, float *dst)
 {
