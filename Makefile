@@ -17,11 +17,14 @@ check: all
 # racecheck is expected to report ONE hazard class only: the shared-memory word that tcgen05.alloc writes the TMEM base address
 # into -- the write is made by the allocation hardware and ordered for its readers by tcgen05.fence + the CTA / cluster barrier,
 # which racecheck does not model.  Needs a B200; the log goes to profiles/.
+# (SANITIZE_CASES=tools/sanitize_beta.py SANITIZE_TOOLS="memcheck racecheck": the beta != 0 path alone)
+SANITIZE_CASES ?= tools/sanitize_cases.py
+SANITIZE_TOOLS ?= memcheck synccheck racecheck
 sanitize: $(LIB) oracle
 	@mkdir -p gpurun_out
-	@for tool in memcheck synccheck racecheck; do \
+	@for tool in $(SANITIZE_TOOLS); do \
 	  echo "== compute-sanitizer --tool $$tool"; \
-	  compute-sanitizer --tool $$tool --print-limit 20 python tools/sanitize_cases.py > gpurun_out/sanitize_$$tool.log 2>&1; echo "rc=$$?"; \
+	  compute-sanitizer --tool $$tool --print-limit 20 python $(SANITIZE_CASES) > gpurun_out/sanitize_$$tool.log 2>&1; echo "rc=$$?"; \
 	  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Error|relerr|conv|ok" gpurun_out/sanitize_$$tool.log | sort | uniq -c | sort -rn | head -40; \
 	done
 clean:
