@@ -21,8 +21,9 @@ using namespace ptx;
 // floor: same tensor throughput as one 256-column MMA), and the promotion schedule of the slices is STAGGERED: with promotion
 // every kc = 4 k-blocks, slice j hands its partial sums to the epilogue after k-blocks j, j+4, j+8, ... -- one 64-column slice
 // per k-block instead of 256 columns every fourth.  A slice that has been handed over continues in a free buffer, so
-// NSL + 1 slice buffers in a FIFO ring (5 x 64 = 320 columns for a 256-wide tile) replace 2 x 256, and 3 A stages fit.
-// Both sides count hand-overs with one running index: buffer = index % (NSL + 1).
+// NSL + 1 slice buffers in a FIFO ring (5 x 64 = 320 columns for a 256-wide tile) would replace 2 x 256 and leave room for 3 A
+// stages; the pair kernel runs NSL + 2 buffers and 2 A stages (see UGEMM_TS_XBUF2 below for the measurement).
+// Both sides count hand-overs with one running index: buffer = index % NBUF.
 //
 // Shared memory: 4 stages of 48 KiB (A raw | B raw | B small).  With cta_group::2 an N = 64 MMA takes accumulator columns
 // 0..31 from the leader's B rows and 32..63 from the peer's, so CTA r loads B in 32-row groups: shared-memory rows 32g..32g+31
@@ -36,9 +37,24 @@ constexpr int SLICE = 64;                             // accumulator columns per
 constexpr int TS_SMEM_BYTES = TS_STAGES * TS_STAGE_BYTES + 1024 + 8 * CSTAGE_BYTES + 1024;   // ring | barriers | C staging | alignment slack
 static_assert(TS_SMEM_BYTES <= 232448, "shared-memory budget of one CTA (227 KiB)");
 // barrier block: 8-byte slots counted from bar_base
-constexpr int B_FULL = 0, B_XF = 4, B_EMPTY = 8, B_AFREE = 12, B_TFULL = 16, B_TEMPTY = 21;
-constexpr int B_SCHED = 26;                           // tile-index ring: full[4], empty[4], 4 x 4-byte slots (next_tile's layout, rebased)
-constexpr int B_TMEM = 37;
+constexpr int B_FULL = 0, B_XF = 4, B_EMPTY = 8, B_AFREE = 12, B_TFULL = 16, B_TEMPTY = 22;      // (room for 6 slice buffers)
+constexpr int B_SCHED = 28;                           // tile-index ring: full[4], empty[4], 4 x 4-byte slots (next_tile's layout, rebased)
+constexpr int B_TMEM = 39;
+// Slice buffers beyond NSL + 1 (build-time knobs; single CTA / CTA pair).  A pair runs SIX buffers and TWO TMEM A stages (6 x 64 +
+// 2 x 64 = 512 columns) instead of five and three: at a tile boundary the four final hand-overs leave two buffers instead of one for
+// the next tile's first slices, and in the steady state the MMA thread -- which issues about a k-block ahead of the tensor pipe --
+// finds a free buffer without waiting for the drain of the hand-over before.  [measured] one box, alternating processes
+// (profiles/r4j_xbuf_ab.jsonl, r4k_xbuf_ab2.jsonl): c3 NT 0.2106 -> 0.2064 ms (beta 0.5: 0.2222 -> 0.2172), TN / TT -1.5 %, c4 -0.6 %
+// (beta = 1 -0.8 %), 16384 x 8192 x 2048 beta = 1 -0.9 %, fused convolution of config 4's layer -1 %, 2048^3 -0.7 %; 4096^3 NN and
+// 8192^3 unchanged; the one loser is a long-K product with an MN-major A, whose slower transform misses the third A stage
+// (4096^3 TN +1.2 %).  A single CTA (448 of 512 columns in use) gains nothing from a fourth buffer (1024^3, 1536^3, 2560^3 forced to
+// single CTAs, 200704 x 128 x 1152: all within 0.5 %), so it keeps three.
+#ifndef UGEMM_TS_XBUF1
+#define UGEMM_TS_XBUF1 0
+#endif
+#ifndef UGEMM_TS_XBUF2
+#define UGEMM_TS_XBUF2 1
+#endif
 constexpr int B_CLOAD = 40;                           // one per epilogue warp: the old C of a 32 x 32 box has landed in the warp's staging box (beta != 0)
 }
 
@@ -50,8 +66,9 @@ k1ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 {
 	using namespace tsk;
 	constexpr int BN = 128 * CG, UMMA_M = 128 * CG;
-	constexpr int NSL = BN / SLICE, NBUF = NSL + 1;                      // slices per tile, slice buffers in the ring
-	constexpr int NA = (512 - NBUF * SLICE) / 64 < TS_STAGES ? (512 - NBUF * SLICE) / 64 : TS_STAGES;   // TMEM A stages: 3 (CG = 2), 4 (CG = 1)
+	constexpr int NSL = BN / SLICE, NBUF = NSL + 1 + (CG == 1 ? UGEMM_TS_XBUF1 : UGEMM_TS_XBUF2);   // slices per tile, slice buffers in the ring
+	static_assert(NBUF <= 6, "barrier block has room for six slice buffers");
+	constexpr int NA = (512 - NBUF * SLICE) / 64 < TS_STAGES ? (512 - NBUF * SLICE) / 64 : TS_STAGES;   // TMEM A stages: 2 (CG = 2, six slice buffers), 4 (CG = 1)
 	constexpr uint32_t A_COL0 = NBUF * SLICE;
 	constexpr uint32_t SL16 = (SLICE / CG) * 128 / 16;                   // one slice's B rows in this CTA's stage, in 16-byte units
 	static_assert(NA >= 2, "need at least two TMEM A stages");
