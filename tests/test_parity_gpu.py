@@ -612,6 +612,41 @@ def test_k1_stream_k_tail_is_deterministic_and_exact_enough(u):
             assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= TOL
 
 
+@pytest.mark.parametrize("cg", [2, 1])
+def test_k1_old_c_through_tma_and_through_registers(u, cg):
+    """beta != 0 on K1: a C the TMA unit can address (16-byte aligned, ldc % 4 == 0) is fetched box by box into the epilogue warps'
+    staging boxes and added between two promotions at a fixed hand-over number; any other C is loaded into the registers.  Both
+    against the oracle (the old C is 2 % of the result at the shortest K here: a missing or misplaced 32 x 32 box is 1000 x the
+    gate), reproducible bit for bit, ld padding untouched.  Shapes: boxes clipped at both edges, K so short that the hand-overs
+    run out before a warp's four boxes are in, and -- on 8 SMs -- many tiles per CTA, so that every staging box alternates
+    between C loads and tile stores."""
+    u.set_k1_tuning(cta_group=cg)
+    try:
+        worst = 0.0
+        for sms in (0, 8):
+            u.set_sm_limit(sms)
+            for i, (M, N, K, ta, tb) in enumerate(((700, 500, 96, "N", "T"), (300, 260, 100, "T", "N"), (1100, 900, 1024, "N", "N"), (513, 1030, 160, "T", "T"))):
+                if sms and K > 512:
+                    continue
+                (ar, ac), (br, bc), _ = O.stored_shapes("R", ta, tb, M, N, K)
+                for padc, beta in ((0, 0.5), (4, 1.0), (3, -2.0), (1, 0.5)):
+                    pad = ((-ac) % 4, (-bc) % 4, (-N) % 4 + padc)
+                    A, lda, B, ldb, Cm, ldc = O.make_problem("R", ta, tb, M, N, K, pad=pad, seed=80 + i, sentinel=-77.0)
+                    g1 = gpu14(u, "3xtf32", "R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, beta, Cm, ldc)
+                    assert u.last_kernel() == "3xtf32"
+                    g2 = gpu14(u, "3xtf32", "R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, beta, Cm, ldc)
+                    assert np.array_equal(g1, g2), f"result changed between two identical calls ({M}x{N}x{K} ldc={ldc} beta={beta} sms={sms})"
+                    assert np.array_equal(g1.reshape(M, ldc)[:, N:], Cm.reshape(M, ldc)[:, N:]), "ld padding of C was written"
+                    want = oracle14("R", ta, tb, M, N, K, 1.5, A, lda, B, ldb, beta, Cm, ldc)
+                    e = O.relerr("R", M, N, want, g1, ldc)
+                    assert e <= TOL, f"{ta}{tb} {M}x{N}x{K} ldc={ldc} beta={beta} sms={sms}: relerr {e:.3e}"
+                    worst = max(worst, e)
+        print(f"k1 old C, cg={cg}: worst relerr {worst:.3e}")
+    finally:
+        u.set_sm_limit(0)
+        u.set_k1_tuning(cta_group=0)
+
+
 def test_auto_dispatch_skinny_but_large_goes_to_k1(u):
     """One side >= 128, the other >= 48 (>= 8 with K >= 512), M*N*K >= 2^26: K1 on a zero-filled tile beats K2 (dispatch rule)."""
     for (M, N, K, want) in ((4096, 64, 512, "3xtf32"), (64, 4096, 512, "3xtf32"), (8192, 48, 256, "3xtf32"), (4096, 32, 512, "3xtf32"),
