@@ -507,6 +507,25 @@ def test_batched_stacked_instances(u, case):
             assert np.array_equal(got[b * sC:(b + 1) * sC].reshape(cr, ldc)[:, cc:], C0[b * sC:(b + 1) * sC].reshape(cr, ldc)[:, cc:])
 
 
+def test_batched_k1_with_an_unaligned_instance_stride_of_c(u):
+    """ldc % 4 == 0 but strideC % 4 != 0: rows of instances 1.. do not start on 16-byte boundaries, so K1 must fall back to scalar
+    accesses to C (no TMA boxes, no 128-bit loads or stores) -- and still match the per-instance oracle loop; gaps untouched."""
+    M, N, K, batch = 256, 384, 200, 3
+    lda, ldb, ldc = K, N, N
+    sA, sB, sC = M * lda, K * ldb, M * ldc + 2
+    A = O.fill_uniform(batch * sA, 911, -0.5, 0.5)
+    B = O.fill_uniform(batch * sB, 912, -0.5, 0.5)
+    C0 = O.fill_uniform(batch * sC, 913, -0.5, 0.5)
+    got = C0.copy()
+    u.sgemm_cuda_batched("R", "N", "N", M, N, K, 1.5, A, lda, sA, B, ldb, sB, 0.5, got, ldc, sC, batch)
+    assert u.last_kernel() == "3xtf32"
+    for b in range(batch):
+        want = oracle14("R", "N", "N", M, N, K, 1.5, A[b * sA:(b + 1) * sA], lda, B[b * sB:(b + 1) * sB], ldb, 0.5, C0[b * sC:b * sC + M * ldc], ldc)
+        e = O.relerr("R", M, N, want, got[b * sC:b * sC + M * ldc], ldc)
+        assert e <= TOL, (b, e)
+        assert np.array_equal(got[b * sC + M * ldc:(b + 1) * sC], C0[b * sC + M * ldc:(b + 1) * sC]), "the gap between instances was written"
+
+
 def test_batched_host_scale_only_and_stride_checks(u):
     """sgemm_cuda_batched (host pointers): K == 0 / alpha == 0 never read A or B (NULL is legal, transposed operands included);
     bad strides are an error that leaves C untouched."""

@@ -445,7 +445,8 @@ cudaError_t launch_cg(const Problem &p, const K1Tuning &t_in, cudaStream_t strea
 	P.strideC = p.strideC;
 	const long long nt = (long long)P.tiles_m * P.tiles_n * (p.batch > 0 ? p.batch : 1);
 	P.num_k_blocks = (p.K + BK - 1) / BK;
-	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0) ? 1 : 0;
+	// 128-bit (and wider) accesses to rows of C: every row of every instance must start on a 16-byte boundary
+	P.vecC = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0 && (p.batch <= 1 || p.strideC % 4 == 0)) ? 1 : 0;
 	// C as a TMA-store target: {N, M, batch} with 32 x 32 boxes (flags bit 13 = 8192 switches the TMA-store epilogue off)
 	CUtensorMap tmC = tmA;
 	P.tma_store = 0;
