@@ -56,6 +56,9 @@ constexpr int B_TMEM = 39;
 #define UGEMM_TS_XBUF2 1
 #endif
 constexpr int B_CLOAD = 40;                           // one per epilogue warp: the old C of a 32 x 32 box has landed in the warp's staging box (beta != 0)
+static_assert(B_XF >= B_FULL + TS_STAGES && B_EMPTY >= B_XF + TS_STAGES && B_AFREE >= B_EMPTY + TS_STAGES && B_TFULL >= B_AFREE + TS_STAGES &&
+              B_TEMPTY >= B_TFULL + 6 && B_SCHED >= B_TEMPTY + 6 && B_TMEM >= B_SCHED + 2 * SCHED_SLOTS + 2 && B_CLOAD > B_TMEM &&
+              8 * (B_CLOAD + 8) <= 1024, "barrier block: slots overlap or leave the 1 KiB reserved for them");
 }
 
 // CONV: the B operand is an image gathered by 4-D TMA boxes (implicit im2col, see the SS kernel): every 32-row group of a B stage
